@@ -1,0 +1,205 @@
+/* pkb200.h -- C ABI of libpkb200.so, the B200 (sm_100a) implementation of the
+ * Parasitoids drift-diffusion forward solve.
+ *
+ * The reference (mountaindust/Parasitoids) is pure Python and has no FFI of its
+ * own; its plugin seam for this path is the Python class cuda_lib.CudaSolve
+ * (cuda_lib.py:16-221) plus the module-level functions of ParasitoidModel.py
+ * and CalcSol.py.  Each entry point below names the reference interface it
+ * replaces; parasitoids_b200/*.py binds them with ctypes and re-exposes the
+ * reference's Python names.
+ *
+ * Conventions: every function returns 0 on success or a negative PKB_E* code
+ * and stores a message retrievable with pkb_last_error() (thread-local).  All
+ * pointers are caller-owned HOST buffers of C-order IEEE fp64 / int32 unless a
+ * comment says otherwise.  Handles are not thread-safe; use one per thread.
+ * There is no CPU fallback: without a CUDA device pkb_create() fails.
+ */
+#ifndef PKB200_H
+#define PKB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PKB_OK 0
+#define PKB_EINVAL (-1)   /* bad argument */
+#define PKB_ECUDA (-2)    /* CUDA runtime error */
+#define PKB_ENOMEM (-3)
+#define PKB_ELIMIT (-4)   /* problem exceeds an implementation limit */
+#define PKB_ESTATE (-5)   /* call sequence error */
+
+/* status bits of pkb_day_meta.status (reference assertion / warning sites) */
+#define PKB_ST_HPROB_RANGE 1   /* ParasitoidModel.py:529 */
+#define PKB_ST_NEG_LOSS 2      /* :569 */
+#define PKB_ST_PMF_NEG 4       /* :570 */
+#define PKB_ST_PMF_GT1 8       /* :571 */
+#define PKB_ST_PMF_NEG2 16     /* :589 */
+#define PKB_ST_TOT_GT1 32      /* :590 */
+#define PKB_ST_WARNED 64       /* RuntimeWarning, :547-558 */
+#define PKB_ST_BORDERLINE 128  /* ring-growth test within 1e-13 of cdf_eps (:348) */
+#define PKB_ST_SUPPORT_OVF 256
+
+typedef struct pkb_ctx pkb_ctx;       /* one device + stream + plan cache */
+typedef struct pkb_kset pkb_kset;     /* device-resident set of per-day kernels */
+typedef struct pkb_chain pkb_chain;   /* convolution-chain state (CudaSolve instance) */
+typedef struct pkb_result pkb_result; /* outputs of a fused solve */
+
+/* arguments of one prob_mass evaluation (ParasitoidModel.py:384-385) */
+typedef struct pkb_day_args {
+    double hparams[7];   /* lam, aw, bw, a1, b1, a2, b2 */
+    double dparams[3];   /* sig_x, sig_y, rho   (in-flow diffusion) */
+    double dlparams[3];  /* sig_x, sig_y, rho   (out-of-flow diffusion) */
+    double mu_r;
+    double rad_dist;
+    double start_time;   /* fraction of the day; < 0 means None */
+    int n_periods;
+    int rad_res;
+    int wind_day;        /* row of the wind array that holds this day */
+    int single;          /* 1: wind row is a single (wx, wy, wr) triple (test form, :426-428) */
+} pkb_day_args;
+
+typedef struct pkb_day_meta {
+    double loss, pmfsum, total, kept_sum, add;
+    int rad;      /* returned pmf has shape (2*rad+1)^2 */
+    int nnz;
+    int status;   /* PKB_ST_* bits */
+    int ext, hl, pad_;
+} pkb_day_meta;
+
+typedef struct pkb_step_meta {
+    double padmax, ksum, add, vmin;
+    long long kcnt;
+    int flag;     /* boundary flag, CalcSol.py:36-40 */
+    int pad_;
+} pkb_step_meta;
+
+const char* pkb_last_error(void);
+int pkb_version(void);
+
+/* ---- context ------------------------------------------------------------- */
+int pkb_create(int device, pkb_ctx** out);
+int pkb_destroy(pkb_ctx* ctx);
+int pkb_sync(pkb_ctx* ctx);
+/* option keys: "stencil_max_radius" (direct-convolution switch point),
+ * "fft_threads" */
+int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
+/* device time in ms of the phases of the last pkb_solve: [0] phase 1,
+ * [1] chain, [2] output compaction + D2H, [3] total */
+int pkb_timing(pkb_ctx* ctx, double out_ms[4]);
+/* number of kernel launches issued through this context so far */
+long long pkb_launch_count(pkb_ctx* ctx);
+
+/* ---- phase 1: ParasitoidModel.py ------------------------------------------ */
+/* h_flight_prob(day_wind, lam, aw, bw, a1, b1, a2, b2)  (ParasitoidModel.py:282-309)
+ * wind: [periods][3] (or [3] when single != 0); out: [periods] (or [1]) */
+int pkb_hprob(pkb_ctx* ctx, const double* wind, int periods, int single, const double hparams[7], double* out,
+              double* f_out /* f_time_prob, :243-267, may be NULL */, double* g_out /* g_wind_prob, :231-240, may be NULL */);
+
+/* get_mvn_cdf_values(cell_length, mu, S)  (ParasitoidModel.py:311-380)
+ * cov = (S[0][0], S[1][1], S[0][1]); out receives (2h+1)^2 values, h_out the
+ * half-width; fails with PKB_ELIMIT if (2h+1)^2 > cap */
+int pkb_mvn_cdf(pkb_ctx* ctx, double cell_length, const double mu[2], const double cov[3], double* out, int cap, int* h_out);
+
+/* prob_mass for `nprob` independent (proposal, day) problems sharing one wind
+ * array [nd_wind][periods][3]  (ParasitoidModel.py:384-613; the fan-out is
+ * Run.py:412-425 / Bayes_Run.py:236-272).  All problems must share rad_res.
+ * keep_pre != 0 also keeps the pre-threshold grids (parity export). */
+int pkb_kernels_build(pkb_ctx* ctx, const double* wind, int nd_wind, int periods, const pkb_day_args* args, int nprob,
+                      int keep_pre, pkb_kset** out);
+int pkb_kset_meta(pkb_kset* ks, int i, pkb_day_meta* out);
+/* dense (2*rad+1)^2 thresholded + renormalised pmf of problem i */
+int pkb_kset_get(pkb_kset* ks, int i, double* out);
+/* dense (2*racc+1)^2 pre-threshold window (needs keep_pre); racc via pkb_kset_racc */
+int pkb_kset_get_pre(pkb_kset* ks, int i, double* out);
+int pkb_kset_racc(pkb_kset* ks);
+/* per-period (row_cent, col_cent, h) triples and hprob of problem i */
+int pkb_kset_periods(pkb_kset* ks, int i, int* rch /*[periods][3]*/, double* hprob /*[periods]*/);
+int pkb_kset_destroy(pkb_kset* ks);
+
+/* ---- phase 2: CalcSol.py / cuda_lib.CudaSolve ----------------------------- */
+/* CudaSolve.__init__(A, max_shape)  (cuda_lib.py:18-54; CalcSol.fft2, CalcSol.py:11-24)
+ * dom_len: side of the square domain; max_shape: side of the largest filter.
+ * The reference torus is P = dom_len + max_shape/2. */
+int pkb_chain_create(pkb_ctx* ctx, int dom_len, int max_shape, pkb_chain** out);
+int pkb_chain_destroy(pkb_chain* ch);
+/* state := A (dense dom_len^2), zero padded */
+int pkb_chain_set_state(pkb_chain* ch, const double* A);
+/* state := kernel i of ks re-centred on the domain (Run.py:454-458) */
+int pkb_chain_set_state_kernel(pkb_chain* ch, pkb_kset* ks, int i);
+/* CudaSolve.fftconv2(B)  (cuda_lib.py:58-94; CalcSol.fftconv2, CalcSol.py:45-66)
+ * B: dense odd-sided square (k x k), centre at [k/2][k/2] */
+int pkb_chain_conv(pkb_chain* ch, const double* B, int k);
+int pkb_chain_conv_kernel(pkb_chain* ch, pkb_kset* ks, int i);
+/* CudaSolve.get_cursol(dom_shape, negval)  (cuda_lib.py:98-140; CalcSol.ifft2 +
+ * the flag/re-fft logic of CalcSol.py:197-201).  apply_trunc != 0 applies the
+ * boundary-flag truncation to the chain state (the "Re-fft" of cuda_lib.py:130-136);
+ * apply_trunc == 0 only reports the flag (CalcSol.ifft2).  mode 0: raw domain
+ * values (CPU-path ifft2), 1: entries < negval zeroed, 2: r_small_vals(
+ * prob_model=True) applied.  out: dense dom_len^2 (may be NULL). */
+int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int apply_trunc, double* out, pkb_step_meta* meta);
+/* CudaSolve.back_solve(prev_spread, dom_shape)  (cuda_lib.py:145-221;
+ * CalcSol.back_solve, CalcSol.py:72-109 with the same-shape re-FFT).
+ * filters: nf dense k_i x k_i arrays in chronological order; out: nf dense
+ * dom_len^2 grids in emergence order (may be NULL: cohorts stay on the device
+ * for pkb_chain_population); threshold < 0: un-thresholded (CPU path), else
+ * entries <= threshold zeroed per cohort (cuda_lib path). */
+int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters, const int* ks, int nf, double threshold, double* out,
+                         int* flags);
+/* Cohort superposition of the population model (CalcSol.py:236-237,271-274,
+ * 303-306,322-323): out = r_small_vals((sum_c cohort_c * weights[c]) * r_number)
+ * (+ centre_extra at the release cell if add_centre).  Cohorts 0..ncoh-2 are
+ * those left on the device by the last pkb_chain_back_solve, cohort ncoh-1 is
+ * the current state.  first_day != 0: the day-0 form r_small_vals(state) *
+ * r_number * weights[0].  out (and optional pre, the un-thresholded sum):
+ * dense dom_len^2. */
+int pkb_chain_population(pkb_chain* ch, int ncoh, const double* weights, double r_number, double centre_extra, int add_centre,
+                         double negval, int first_day, double* out, double* pre);
+/* full padded P x P state (diagnostics / tests); P via pkb_chain_dims */
+int pkb_chain_get_state(pkb_chain* ch, double* out);
+int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N);
+
+/* ---- diagnostics ---------------------------------------------------------- */
+/* length-n complex DFT of one vector through the shared-memory FFT used by the
+ * chain (interleaved re,im; natural order in and out; inverse is unnormalised).
+ * n must be 7-smooth.  Test hook: the reference reaches pocketfft through
+ * scipy.fftpack (CalcSol.py:24,35). */
+int pkb_debug_fft(pkb_ctx* ctx, int n, const double* in, double* out, int inverse);
+/* smallest 7-smooth length >= n (the torus side the chain uses) */
+int pkb_smooth_len(int n);
+
+/* ---- fused forward solve: Run.main's hot path (Run.py:399-481) ------------- */
+typedef struct pkb_solve_args {
+    const double* wind;      /* [nd_wind][periods][3] */
+    int wind_on_device;      /* wind is a device pointer (already resident) */
+    int nd_wind, periods;
+    int ndays;               /* days to simulate (<= nd_wind) */
+    pkb_day_args day;        /* model parameters; wind_day/start_time are per-day and filled internally */
+    int prob_model;          /* 1: get_solutions, 0: get_populations */
+    int r_dur;               /* population model: release duration (days) */
+    double r_number;
+    const double* r_dist;    /* [r_dur] emergence fractions dist(1..r_dur) */
+    double r_start;          /* start_time of day 0 for the population model; < 0 none */
+    double negval;           /* 1e-8 */
+    int want_dense_host;     /* copy dense solutions to host */
+    int want_coo;            /* build COO (row-major) on device and copy to host */
+    int keep_dense_device;   /* keep [ndays][D][D] on device (bench / gather) */
+} pkb_solve_args;
+
+int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
+int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape);
+int pkb_result_day_meta(pkb_result* r, int day, pkb_day_meta* kmeta, pkb_step_meta* smeta);
+/* dense solution of one day: device->host copy on demand */
+int pkb_result_dense(pkb_result* r, int day, double* out);
+/* COO of all days (host pointers owned by the result, valid until destroy) */
+int pkb_result_coo(pkb_result* r, const long long** day_offsets /*[ndays+1]*/, const int** rows, const int** cols,
+                   const double** vals);
+/* gather values at K (row, col) cells for every day: out[ndays][K] */
+int pkb_result_sample(pkb_result* r, const int* cells /*[K][2]*/, int K, double* out);
+/* device pointer of the dense solutions [ndays][D][D] (keep_dense_device) */
+int pkb_result_device_ptr(pkb_result* r, void** dptr);
+int pkb_result_destroy(pkb_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PKB200_H */

@@ -1,0 +1,459 @@
+// Phase 1 kernels: per-day dispersal kernel construction (ParasitoidModel.py).
+//
+//   k_bvn_setup      covariance constants + support half-width for mu = 0
+//   k_hprob          h_flight_prob                   (ParasitoidModel.py:231-309)
+//   k_drift          flight-averaged drift, cell offsets, per-period support
+//                                                    (:439-495, :329-348)
+//   k_period         BVN corner lattice -> cell masses -> clipped accumulation
+//                                                    (:311-380, :497-558)
+//   k_day_finalize   loss/total checks, local-diffusion blob, threshold +
+//                    renormalise, crop radius        (:562-613, CalcSol.py:112-136)
+//   k_mvn_cdf        stand-alone get_mvn_cdf_values  (:311-380)
+//
+// All arithmetic is IEEE fp64.  One CTA handles one take-off period of one day;
+// the days of a solve (and the proposals of a batch) are the grid's y/z extent.
+#pragma once
+#include "bvn.cuh"
+
+namespace pkb {
+
+#define PKB_ST_HPROB_RANGE 1      // hprob[t] outside [-1e-9, 1.000000001]  (:529)
+#define PKB_ST_NEG_LOSS 2         // loss < 0                               (:569)
+#define PKB_ST_PMF_NEG 4          // pmf.min() < -1e-8, first block         (:570)
+#define PKB_ST_PMF_GT1 8          // pmfsum > 1.00001, first block          (:571)
+#define PKB_ST_PMF_NEG2 16        // pmf.min() < -1e-8 after local blob     (:589)
+#define PKB_ST_TOT_GT1 32         // total > 1.00001 after local blob       (:590)
+#define PKB_ST_WARNED 64          // RuntimeWarning path taken              (:547-558)
+#define PKB_ST_BORDERLINE 128     // ring-growth test within 1e-13 of cdf_eps
+#define PKB_ST_SUPPORT_OVF 256    // support half-width exceeds kernel limits
+
+#define PKB_CDF_EPS 0.001
+#define PKB_LATTICE_CAP 5120      // doubles of shared memory for the corner lattice tile
+
+struct DayParams {      // one per (proposal, day) problem
+    double lam, aw, bw, a1, b1, a2, b2;   // hparams (Run.py:377)
+    double mu_r;
+    double cell;                          // rad_dist / rad_res
+    int n_periods;
+    int rad_res;
+    int start_indx;                       // floor(start_time * periods), 0 if None
+    int wind_day;                         // row of the wind array holding this day
+    int has_next;                         // wind_day + 1 exists in the wind data
+    int single;                           // 1-D wind row test form (:426-428)
+    int bvn_S, bvn_Sl;                    // indices into the BvnPar array
+    int pad_;
+};
+
+struct DayMeta {        // results of one (proposal, day) problem
+    double loss, pmfsum, total, kept_sum, add;
+    int rad;            // crop radius of the returned pmf
+    int nnz;
+    int status;
+    int ext;            // max over periods of |cell offset| + support half-width
+    int hl;             // support half-width of the local-diffusion blob
+    int pad_;
+};
+
+// ---------------------------------------------------------------------------
+// dpar[i] = (sig_x, sig_y, rho) if !is_cov, else (S00, S11, S01)
+__global__ void k_bvn_setup(BvnPar* pars, const double* __restrict__ dpar /*[n][3]*/, const double* __restrict__ cell, int is_cov) {
+    // one 32-thread block per covariance
+    const int i = blockIdx.x;
+    PKB_SHARED(int, found, 1);
+    PKB_SHARED(int, okv, 32);
+    BvnPar& p = pars[i];
+    if (threadIdx.x == 0) {
+        if (is_cov) bvn_setup_cov(p, dpar[3 * i], dpar[3 * i + 1], dpar[3 * i + 2]);
+        else bvn_setup(p, dpar[3 * i], dpar[3 * i + 1], dpar[3 * i + 2]);
+        found[0] = -1;
+    }
+    __syncthreads();
+    const double c = cell[i];
+    for (int base = 0; base < 4096; base += 32) {
+        const int h = base + threadIdx.x;
+        okv[threadIdx.x] = (1.0 - square_prob(p, c, h, 0.0, 0.0) < PKB_CDF_EPS) ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < 32; ++t)
+                if (okv[t]) { found[0] = base + t; break; }
+        }
+        __syncthreads();
+        if (found[0] >= 0) break;
+    }
+    if (threadIdx.x == 0) p.h0 = found[0];   // -1 => not found below 4096 (caller reports)
+}
+
+// ---------------------------------------------------------------------------
+// h_flight_prob: grid = problems, block = 256, dyn smem = 4*periods doubles
+// f_out / g_out (optional, one problem only): f_time_prob and g_wind_prob (:231-267)
+__global__ void k_hprob(const DayParams* __restrict__ dps, const double* __restrict__ wind, int periods,
+                        double* __restrict__ hprob_out, DayMeta* __restrict__ meta, double* __restrict__ f_out,
+                        double* __restrict__ g_out) {
+    PKB_DYN_SMEM(raw);
+    PKB_SHARED(double, red, 256);
+    double* f = reinterpret_cast<double*>(raw);   // likelihood -> f
+    double* g = f + periods;
+    double* c1 = g + periods;
+    double* c2 = c1 + periods;
+    const DayParams dp = dps[blockIdx.x];
+    const int n = dp.single ? 1 : periods;
+    const double* w = wind + (size_t)dp.wind_day * periods * 3;
+    const int tid = threadIdx.x, T = blockDim.x;
+    // t_tild = linspace(0, 24 - 24/n, n)  (:260); numpy: start + i*step, last = stop
+    const double stop = 24.0 - 24.0 / n;
+    const double step = n > 1 ? stop / (n - 1) : 0.0;
+    double part = 0.0, pmax = 0.0;
+    for (int i = tid; i < n; i += T) {
+        double t = (i == n - 1 && n > 1) ? stop : i * step;
+        double up = 1.0 / (1.0 + exp(-dp.b1 * (t - dp.a1)));
+        double dn = 1.0 / (1.0 + exp(-dp.b2 * (t - dp.a2)));
+        double lik = fmax(up - dn, 0.0);
+        f[i] = lik;
+        part += lik;
+        const double wr = dp.single ? w[2] : w[3 * i + 2];
+        g[i] = 1.0 / (1.0 + exp(dp.bw * (wr - dp.aw)));   // g_wind_prob (:240)
+    }
+    const double tot = block_sum(part, red);
+    for (int i = tid; i < n; i += T) {
+        f[i] = f[i] / tot;                                // (:267)
+        pmax = fmax(pmax, f[i]);
+    }
+    const double fmx = block_max(pmax, red);
+    // two sequential prefix sums, same order as np.cumsum (:306-307)
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) { acc += f[i]; c1[i] = acc; }
+        acc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double fg = f[i] * g[i];
+            acc += (1.0 - c1[i]) * (f[i] - fg);
+            c2[i] = acc;
+        }
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int i = tid; i < n; i += T) {
+        const double fg = f[i] * g[i];
+        const double tv = (double)(i + 1);
+        const double integral_avg = fg / tv / fmx * c2[i];
+        const double h = dp.lam * (fg + integral_avg);
+        hprob_out[(size_t)blockIdx.x * periods + i] = h;
+        if (f_out) f_out[i] = f[i];
+        if (g_out) g_out[i] = g[i];
+        if (i >= dp.start_indx && !(-1e-9 <= h && h <= 1.000000001)) bad = 1;
+    }
+    if (bad) atomicOr(&meta[blockIdx.x].status, PKB_ST_HPROB_RANGE);
+}
+
+// ---------------------------------------------------------------------------
+struct PeriodInfo {
+    double mux, muy;    // sub-cell remainder of the drift (cdf_mu, :485)
+    int row_c, col_c;   // window centre in the domain grid (:491-494)
+    int h;              // support half-width for this period
+    int pad_;
+};
+
+// grid = problems, block = 256
+__global__ void k_drift(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const double* __restrict__ wind,
+                        int periods, PeriodInfo* __restrict__ pinfo, DayMeta* __restrict__ meta) {
+    PKB_SHARED(double, red, 256);
+    const DayParams dp = dps[blockIdx.x];
+    const BvnPar& bp = bvn[dp.bvn_S];
+    const int P = dp.single ? 1 : periods;
+    const double* w = wind + (size_t)dp.wind_day * periods * 3;
+    const double* wn = w + (size_t)periods * 3;
+    const int n = dp.n_periods;
+    int ext = 0, flags = 0;
+    for (int t = dp.start_indx + threadIdx.x; t < P; t += blockDim.x) {
+        double mx, my;
+        if (dp.single) {
+            mx = w[0]; my = w[1];
+        } else if (n > 1) {
+            if (t + n - 1 < P) {
+                double sx = 0.0, sy = 0.0;
+                for (int i = 0; i < n; ++i) { sx += w[3 * (t + i)]; sy += w[3 * (t + i) + 1]; }
+                mx = sx / n; my = sy / n;
+            } else if (dp.has_next) {
+                double sx, sy;
+                if (t != P - 1) {
+                    sx = 0.0; sy = 0.0;
+                    for (int i = t; i < P; ++i) { sx += w[3 * i]; sy += w[3 * i + 1]; }
+                } else { sx = w[3 * (P - 1)]; sy = w[3 * (P - 1) + 1]; }
+                const int wrap = n - (P - t);
+                if (wrap != 1) {
+                    double ax = 0.0, ay = 0.0;
+                    for (int i = 0; i < wrap; ++i) { ax += wn[3 * i]; ay += wn[3 * i + 1]; }
+                    sx += ax; sy += ay;
+                } else { sx += wn[0]; sy += wn[1]; }
+                mx = sx / n; my = sy / n;
+            } else {
+                if (t != P - 1) {
+                    double sx = 0.0, sy = 0.0;
+                    for (int i = t; i < P; ++i) { sx += w[3 * i]; sy += w[3 * i + 1]; }
+                    mx = sx / (P - t); my = sy / (P - t);
+                } else { mx = w[3 * (P - 1)]; my = w[3 * (P - 1) + 1]; }
+            }
+        } else {
+            mx = w[3 * t]; my = w[3 * t + 1];
+        }
+        const double scale = 86400.0 * ((double)n / (double)P);   // 3600*24*(n_periods/periods) (:468)
+        mx *= scale; my *= scale;
+        mx *= dp.mu_r; my *= dp.mu_r;                              // (:472)
+        const double cell = dp.cell;
+        PeriodInfo pi;
+        pi.mux = mx - rint(mx / cell) * cell;                      // (:485)
+        pi.muy = my - rint(my / cell) * cell;
+        pi.col_c = dp.rad_res + (int)rint(mx / cell);              // (:491,494)
+        pi.row_c = dp.rad_res + (int)rint(-my / cell);             // (:492,493)
+        // support half-width: |cdf_mu| <= cell/2 => h in {h0-1, h0, h0+1}
+        const int h0 = bp.h0;
+        int h = h0 + 1;
+        double d1 = 1.0, d0 = 1.0;
+        if (h0 >= 1) d1 = 1.0 - square_prob(bp, cell, h0 - 1, pi.mux, pi.muy);
+        d0 = 1.0 - square_prob(bp, cell, h0, pi.mux, pi.muy);
+        if (h0 >= 1 && d1 < PKB_CDF_EPS) h = h0 - 1;
+        else if (d0 < PKB_CDF_EPS) h = h0;
+        if (fabs(d1 - PKB_CDF_EPS) < 1e-13 || fabs(d0 - PKB_CDF_EPS) < 1e-13) flags |= PKB_ST_BORDERLINE;
+        pi.h = h;
+        pi.pad_ = 0;
+        pinfo[(size_t)blockIdx.x * periods + t] = pi;
+        int ro = pi.row_c - dp.rad_res, co = pi.col_c - dp.rad_res;
+        if (ro < 0) ro = -ro;
+        if (co < 0) co = -co;
+        const int e = (ro > co ? ro : co) + h;
+        if (e > ext) ext = e;
+    }
+    const int emax = (int)block_max((double)ext, red);
+    if (flags) atomicOr(&meta[blockIdx.x].status, flags);
+    if (threadIdx.x == 0) {
+        meta[blockIdx.x].ext = emax;
+        meta[blockIdx.x].hl = bvn[dp.bvn_Sl].h0;
+    }
+}
+
+// python basic-slice length of seq[start:stop] for len n, start >= 0
+__device__ __forceinline__ int py_slice_len(int start, int stop, int n) {
+    if (stop < 0) { stop += n; if (stop < 0) stop = 0; }
+    if (stop > n) stop = n;
+    if (start > n) start = n;
+    return stop > start ? stop - start : 0;
+}
+
+// ---------------------------------------------------------------------------
+// grid = (periods, problems), block = 256, dyn smem = (6*nmax + PKB_LATTICE_CAP) doubles
+// acc: per problem (2*racc+1)^2 window centred on the release cell
+__global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
+                         const double* __restrict__ hprob, int periods, int nmax, double* __restrict__ acc, int racc,
+                         double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
+    PKB_DYN_SMEM(raw);
+    PKB_SHARED(double, red, 256);
+    const int prob = blockIdx.y;
+    const int t = blockIdx.x;
+    const DayParams dp = dps[prob];
+    const int P = dp.single ? 1 : periods;
+    if (t < dp.start_indx || t >= P) return;
+    const BvnPar& bp = bvn[dp.bvn_S];
+    const PeriodInfo pi = pinfo[(size_t)prob * periods + t];
+    const double hp = hprob[(size_t)prob * periods + t];
+    const int h = pi.h;
+    const int n = 2 * h + 2;             // corners per side
+    const int nc = 2 * h + 1;            // cells per side
+    const int dom = 2 * dp.rad_res + 1;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    // --- window clipping exactly as the reference's index arithmetic (:501-527)
+    int row_min = pi.row_c - h, row_max = pi.row_c + h;
+    int col_min = pi.col_c - h, col_max = pi.col_c + h;
+    int rs = 0, re = nc, cs = 0, ce = nc;
+    if (row_max + 1 > dom) { re -= row_max + 1 - dom; if (re < 0) re = 0; row_max = dom - 1; }
+    if (col_max + 1 > dom) { ce -= col_max + 1 - dom; if (ce < 0) ce = 0; col_max = dom - 1; }
+    if (row_min < 0) { rs -= row_min; if (rs < 0) rs = 0; row_min = 0; }
+    if (col_min < 0) { cs -= col_min; if (cs < 0) cs = 0; col_min = 0; }
+    const int Ar = py_slice_len(row_min, row_max + 1, dom), Ac = py_slice_len(col_min, col_max + 1, dom);
+    const int Br = py_slice_len(rs, re, nc), Bc = py_slice_len(cs, ce, nc);
+    const bool shape_err = (Br != Ar && Br != 1) || (Bc != Ac && Bc != 1);   // numpy ValueError (:547)
+    const bool clipped = rs > 0 || re < nc || cs > 0 || ce < nc;
+    if (shape_err || Ar == 0 || Ac == 0) {
+        // nothing lands in the domain: the whole period's mass is lost (:546,:558)
+        if (tid == 0) {
+            loss_t[(size_t)prob * periods + t] = hp;
+            if (shape_err) atomicOr(&meta[prob].status, PKB_ST_WARNED);
+        }
+        return;
+    }
+
+    double* A = reinterpret_cast<double*>(raw);   // standardised x corners
+    double* B = A + nmax;                         // standardised y corners
+    double* PA = B + nmax;                        // Phi(-a)
+    double* PB = PA + nmax;                       // Phi(-b)
+    double* HA = PB + nmax;                       // a^2/2
+    double* HB = HA + nmax;                       // b^2/2
+    double* U = HB + nmax;                        // corner lattice tile
+    const double cell = dp.cell, r = cell / 2;
+    for (int i = tid; i < n; i += T) {
+        // corner i <= 2h is `low` of cell i - h; the last corner is `upp` of the last cell (:354-355)
+        const double x = (i <= 2 * h) ? ((i - h) * cell - r) : ((h * cell - r) + cell);
+        const double a = (x - pi.mux) / bp.sx, b = (x - pi.muy) / bp.sy;
+        A[i] = a; B[i] = b;
+        PA[i] = phid(-a); PB[i] = phid(-b);
+        HA[i] = a * a / 2.0; HB[i] = b * b / 2.0;
+    }
+    __syncthreads();
+
+    const int rows_per_tile = PKB_LATTICE_CAP / n - 1;   // cell rows (y) per tile
+    const int shift = dp.rad_res - racc;                 // acc window origin in domain coords
+    const int W = 2 * racc + 1;
+    double* accp = acc + (size_t)prob * W * W;
+    double inside = 0.0;
+    for (int y0 = 0; y0 < nc; y0 += rows_per_tile) {
+        const int ny = (nc - y0 < rows_per_tile) ? (nc - y0) : rows_per_tile;   // cell rows in this tile
+        const int npts = (ny + 1) * n;
+        for (int q = tid; q < npts; q += T) {
+            const int iy = q / n, ix = q - iy * n;
+            const double a = A[ix], b = B[y0 + iy];
+            double u;
+            if (bp.high) u = bvu_high(bp, a, b);
+            else u = bvu_low_core(bp, a * b, HA[ix] + HB[y0 + iy], PA[ix] * PB[y0 + iy]);
+            U[q] = u;
+        }
+        __syncthreads();
+        const int ncell = ny * nc;
+        for (int q = tid; q < ncell; q += T) {
+            const int iy = q / nc, ix = q - iy * nc;
+            const double* u = U + iy * n + ix;
+            const double v = u[0] - u[1] - u[n] + u[n + 1];     // BVNMVN 4-term difference
+            const int jj = y0 + iy - h;                          // y index (up)
+            const int row = pi.row_c - jj;                       // rows run downwards (:377-378)
+            const int col = pi.col_c + (ix - h);
+            if (row >= 0 && row < dom && col >= 0 && col < dom) {
+                inside += v;
+                atomicAdd(&accp[(size_t)(row - shift) * W + (col - shift)], hp * v);   // (:539)
+            }
+        }
+        __syncthreads();
+    }
+    if (clipped) {
+        const double s = block_sum(inside, red);
+        if (tid == 0) loss_t[(size_t)prob * periods + t] = (1.0 - s) * hp;   // (:546)
+    } else if (tid == 0) {
+        loss_t[(size_t)prob * periods + t] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// grid = problems, block = 1024.  Works in place on the accumulation window.
+// pre (optional): receives the pre-threshold window (parity export).
+__global__ void k_day_finalize(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, int periods, double* __restrict__ acc,
+                               int racc, const double* __restrict__ loss_t, DayMeta* __restrict__ meta, double negval,
+                               double* __restrict__ pre) {
+    PKB_SHARED(double, red, 1024);
+    PKB_SHARED(double, sh, 4);
+    const int prob = blockIdx.x;
+    const DayParams dp = dps[prob];
+    const int P = dp.single ? 1 : periods;
+    const int W = 2 * racc + 1;
+    const int nel = W * W;
+    double* a = acc + (size_t)prob * nel;
+    const int tid = threadIdx.x, T = blockDim.x;
+    int status = 0;
+
+    if (tid == 0) {
+        double loss = 0.0;
+        for (int t = dp.start_indx; t < P; ++t) loss += loss_t[(size_t)prob * periods + t];   // same order as the loop (:546,558)
+        sh[0] = loss;
+    }
+    double s = 0.0, mn = 0.0;
+    for (int i = tid; i < nel; i += T) { const double v = a[i]; s += v; mn = fmin(mn, v); }
+    const double pmfsum = block_sum(s, red);
+    const double pmin = block_min(mn, red);
+    const double loss = sh[0];
+    double total = pmfsum + loss;
+    if (!(loss >= 0.0)) status |= PKB_ST_NEG_LOSS;
+    if (!(pmin >= -1e-8)) status |= PKB_ST_PMF_NEG;
+    if (!(pmfsum <= 1.00001)) status |= PKB_ST_PMF_GT1;
+    if (total < 0.99999) {
+        // wasps that did not fly diffuse locally around the release cell (:581-585)
+        const BvnPar& bl = bvn[dp.bvn_Sl];
+        const int hl = bl.h0;
+        const int ncl = 2 * hl + 1;
+        const double cell = dp.cell, r = cell / 2;
+        const double wgt = 1.0 - total;
+        for (int q = tid; q < ncl * ncl; q += T) {
+            const int iy = q / ncl, ix = q - iy * ncl;      // iy: y index + hl, ix: x index + hl
+            const double xl = (ix - hl) * cell - r, yl = (iy - hl) * cell - r;
+            const double v = mvn_rect(bl, xl, xl + cell, yl, yl + cell, 0.0, 0.0);
+            const int row = racc - (iy - hl), col = racc + (ix - hl);
+            a[(size_t)row * W + col] += wgt * v;
+        }
+        __syncthreads();
+        s = 0.0; mn = 0.0;
+        for (int i = tid; i < nel; i += T) { const double v = a[i]; s += v; mn = fmin(mn, v); }
+        const double sum2 = block_sum(s, red);
+        const double min2 = block_min(mn, red);
+        if (!(min2 >= -1e-8)) status |= PKB_ST_PMF_NEG2;
+        if (!(sum2 + loss <= 1.00001)) status |= PKB_ST_TOT_GT1;
+    }
+    // r_small_vals(coo(pmf), prob_model=True) (:605, CalcSol.py:112-136)
+    double ks = 0.0, kc = 0.0, kr = 0.0;
+    for (int i = tid; i < nel; i += T) {
+        const double v = a[i];
+        if (v != 0.0 && !(v < negval)) {
+            ks += v; kc += 1.0;
+            int rr = i / W - racc, cc = i % W - racc;
+            if (rr < 0) rr = -rr;
+            if (cc < 0) cc = -cc;
+            kr = fmax(kr, (double)(rr > cc ? rr : cc));
+        }
+    }
+    const double ksum = block_sum(ks, red);
+    const double kcnt = block_sum(kc, red);
+    const double krad = block_max(kr, red);
+    const double add = (1.0 - ksum) / kcnt;
+    for (int i = tid; i < nel; i += T) {
+        const double v = a[i];
+        if (pre) pre[(size_t)prob * nel + i] = v;
+        a[i] = (v != 0.0 && !(v < negval)) ? v + add : 0.0;
+    }
+    if (tid == 0) {
+        DayMeta& m = meta[prob];
+        m.loss = loss; m.pmfsum = pmfsum; m.total = total; m.kept_sum = ksum; m.add = add;
+        m.rad = (int)krad; m.nnz = (int)kcnt;
+    }
+    if (status && tid == 0) atomicOr(&meta[prob].status, status);
+}
+
+// ---------------------------------------------------------------------------
+// get_mvn_cdf_values for arbitrary mu: grid = 1, block = 256.
+// out: [cap] doubles, receives the (2h+1)^2 array in the reference orientation;
+// hout[0] = h, or -1 if (2h+1)^2 > cap or h >= 4096.
+__global__ void k_mvn_cdf(const BvnPar* __restrict__ bvn, double cell, double mux, double muy, double* __restrict__ out, int cap,
+                          int* __restrict__ hout) {
+    PKB_SHARED(int, okv, 256);
+    PKB_SHARED(int, found, 1);
+    const BvnPar& p = bvn[0];
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) found[0] = -1;
+    __syncthreads();
+    for (int base = 0; base < 4096; base += T) {
+        okv[tid] = (1.0 - square_prob(p, cell, base + tid, mux, muy) < PKB_CDF_EPS) ? 1 : 0;
+        __syncthreads();
+        if (tid == 0)
+            for (int t = 0; t < T; ++t)
+                if (okv[t]) { found[0] = base + t; break; }
+        __syncthreads();
+        if (found[0] >= 0) break;
+    }
+    const int h = found[0];
+    const int nc = 2 * h + 1;
+    if (h < 0 || (long long)nc * nc > cap) { if (tid == 0) hout[0] = -1; return; }
+    const double r = cell / 2;
+    for (int q = tid; q < nc * nc; q += T) {
+        const int row = q / nc, col = q - row * nc;
+        const int jj = h - row, ii = col - h;                   // [row, col] = (y = h - row, x = col - h) (:377-378)
+        const double xl = ii * cell - r, yl = jj * cell - r;
+        out[q] = mvn_rect(p, xl, xl + cell, yl, yl + cell, mux, muy);
+    }
+    if (tid == 0) hout[0] = h;
+}
+
+}  // namespace pkb

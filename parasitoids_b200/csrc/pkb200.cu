@@ -1,0 +1,1247 @@
+// libpkb200.so -- host side of the C ABI declared in include/pkb200.h.
+//
+// Orchestrates the sm_100a kernels of phase1.cuh (per-day dispersal kernels,
+// ParasitoidModel.py) and chain.cuh (daily convolution chain, CalcSol.py /
+// cuda_lib.py).  Everything runs on one CUDA stream per context; the only
+// host<->device synchronisations inside a solve are the two places where the
+// reference's algorithm is data dependent in *size*: the accumulation-window
+// radius after the drift pass and the crop radii (-> torus size) after phase 1.
+//
+// There is no CPU code path in this library.  (tests/emul builds these same
+// sources against a CPU fiber emulation of CUDA purely to unit-test indexing
+// logic in the GPU-less build container; see tests/emul/emul_cuda.h.)
+#include "../../include/pkb200.h"
+#include "phase1.cuh"
+#include "chain.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace pkb;
+
+static_assert(sizeof(pkb_day_meta) == sizeof(DayMeta), "pkb_day_meta layout");
+static_assert(sizeof(pkb_step_meta) == sizeof(StepMeta), "pkb_step_meta layout");
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return fail(PKB_ECUDA, "%s failed: %s (%s:%d)", #call,       \
+                                           cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+#define TRY(call)            \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+extern "C" const char* pkb_last_error(void) { return g_err.c_str(); }
+extern "C" int pkb_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------
+// context: stream, caching allocators, FFT plans
+// ---------------------------------------------------------------------------
+struct PlanRec {
+    FftPlan plan;
+    cplx* tw;
+    int* perm;
+};
+
+struct pkb_ctx {
+    int device;
+    cudaStream_t stream;
+    long long launches;
+    std::map<int, PlanRec> plans;
+    // size-bucketed free lists: repeated solves (MCMC proposals, bench steps)
+    // reuse their buffers instead of paying cudaMalloc/cudaMallocHost again
+    std::map<size_t, std::vector<void*> > dev_free, host_free;
+    std::map<void*, size_t> dev_live, host_live;
+    cudaEvent_t ev[5];
+    double timing[4];
+    int stencil_max_radius;
+    int fft_threads;
+    int max_smem;
+};
+
+static size_t bucket(size_t n) {
+    if (n < 4096) return 4096;
+    size_t p = 4096;
+    while (p < n) p <<= 1;          // next power of two ...
+    const size_t step = p >> 3;     // ... refined to eighths
+    return ((n + step - 1) / step) * step;
+}
+
+static int dev_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
+    const size_t b = bucket(bytes);
+    std::vector<void*>& fl = ctx->dev_free[b];
+    if (!fl.empty()) {
+        *out = fl.back();
+        fl.pop_back();
+    } else {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            // drop the cache and retry once
+            for (auto& kv : ctx->dev_free) {
+                for (void* q : kv.second) cudaFree(q);
+                kv.second.clear();
+            }
+            e = cudaMalloc(&p, b);
+            if (e != cudaSuccess) return fail(PKB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+        }
+        *out = p;
+    }
+    ctx->dev_live[*out] = b;
+    return 0;
+}
+static void dev_release(pkb_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->dev_live.find(p);
+    if (it == ctx->dev_live.end()) return;
+    ctx->dev_free[it->second].push_back(p);
+    ctx->dev_live.erase(it);
+}
+static int host_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
+    const size_t b = bucket(bytes);
+    std::vector<void*>& fl = ctx->host_free[b];
+    if (!fl.empty()) {
+        *out = fl.back();
+        fl.pop_back();
+    } else {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, b);
+        if (e != cudaSuccess) return fail(PKB_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+        *out = p;
+    }
+    ctx->host_live[*out] = b;
+    return 0;
+}
+static void host_release(pkb_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->host_live.find(p);
+    if (it == ctx->host_live.end()) return;
+    ctx->host_free[it->second].push_back(p);
+    ctx->host_live.erase(it);
+}
+
+// typed handle on a pooled device buffer
+template <class T>
+struct DBuf {
+    pkb_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(pkb_ctx* c, size_t count) {
+        release();
+        ctx = c;
+        void* q = nullptr;
+        int rc = dev_alloc(c, std::max<size_t>(count, 1) * sizeof(T), &q);
+        if (rc) return rc;
+        p = static_cast<T*>(q);
+        n = count;
+        return 0;
+    }
+    void release() {
+        if (p && ctx) dev_release(ctx, p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DBuf() { release(); }
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+};
+template <class T>
+struct HBuf {
+    pkb_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(pkb_ctx* c, size_t count) {
+        release();
+        ctx = c;
+        void* q = nullptr;
+        int rc = host_alloc(c, std::max<size_t>(count, 1) * sizeof(T), &q);
+        if (rc) return rc;
+        p = static_cast<T*>(q);
+        n = count;
+        return 0;
+    }
+    void release() {
+        if (p && ctx) host_release(ctx, p);
+        p = nullptr;
+        n = 0;
+    }
+    ~HBuf() { release(); }
+    HBuf() {}
+    HBuf(const HBuf&) = delete;
+    HBuf& operator=(const HBuf&) = delete;
+};
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                             \
+    do {                                                                      \
+        PKB_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);      \
+        (ctx)->launches++;                                                    \
+    } while (0)
+
+static int check_launches(pkb_ctx* ctx, const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PKB_ECUDA, "kernel launch failed in %s: %s", where, cudaGetErrorString(e));
+    (void)ctx;
+    return 0;
+}
+static int sync_check(pkb_ctx* ctx, const char* where) {
+    TRY(check_launches(ctx, where));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(PKB_ECUDA, "stream synchronize failed in %s: %s", where, cudaGetErrorString(e));
+    return 0;
+}
+
+static const int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+
+extern "C" int pkb_create(int device, pkb_ctx** out) {
+    if (!out) return fail(PKB_EINVAL, "pkb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(PKB_ECUDA, "pkb_create: no CUDA device available (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(PKB_EINVAL, "pkb_create: device %d out of range [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    pkb_ctx* ctx = new pkb_ctx();
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->stencil_max_radius = 3;
+    ctx->fft_threads = 256;
+    ctx->max_smem = kMaxSmem;
+    for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
+    CU(cudaStreamCreate(&ctx->stream));
+    for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&ctx->ev[i]));
+    CU(cudaFuncSetAttribute(k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_kernel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_fft_test, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_period, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_hprob, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_stencil, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int pkb_destroy(pkb_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->plans) {
+        cudaFree(kv.second.tw);
+        cudaFree(kv.second.perm);
+    }
+    for (auto& kv : ctx->dev_free)
+        for (void* p : kv.second) cudaFree(p);
+    for (auto& kv : ctx->dev_live) cudaFree(kv.first);
+    for (auto& kv : ctx->host_free)
+        for (void* p : kv.second) cudaFreeHost(p);
+    for (auto& kv : ctx->host_live) cudaFreeHost(kv.first);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int pkb_sync(pkb_ctx* ctx) {
+    if (!ctx) return fail(PKB_EINVAL, "pkb_sync: ctx is NULL");
+    return sync_check(ctx, "pkb_sync");
+}
+
+extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
+    if (!ctx || !key) return fail(PKB_EINVAL, "pkb_set_option: NULL argument");
+    if (!strcmp(key, "stencil_max_radius")) {
+        if (value < -1 || value > 24) return fail(PKB_EINVAL, "stencil_max_radius must be in [-1, 24]");
+        ctx->stencil_max_radius = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "fft_threads")) {
+        const int t = (int)value;
+        if (t < 32 || t > 1024 || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, 1024]");
+        ctx->fft_threads = t;
+        return 0;
+    }
+    return fail(PKB_EINVAL, "pkb_set_option: unknown key '%s'", key);
+}
+
+extern "C" int pkb_timing(pkb_ctx* ctx, double out_ms[4]) {
+    if (!ctx || !out_ms) return fail(PKB_EINVAL, "pkb_timing: NULL argument");
+    for (int i = 0; i < 4; ++i) out_ms[i] = ctx->timing[i];
+    return 0;
+}
+
+extern "C" long long pkb_launch_count(pkb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// ---------------------------------------------------------------------------
+// FFT plans
+// ---------------------------------------------------------------------------
+static bool is_smooth(int n) {
+    if (n < 1) return false;
+    const int pr[4] = {2, 3, 5, 7};
+    for (int p : pr)
+        while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+extern "C" int pkb_smooth_len(int n) {
+    if (n < 1) n = 1;
+    while (!is_smooth(n)) ++n;
+    return n;
+}
+
+static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
+    auto it = ctx->plans.find(N);
+    if (it != ctx->plans.end()) {
+        *out = it->second.plan;
+        return 0;
+    }
+    if (!is_smooth(N)) return fail(PKB_EINVAL, "FFT length %d is not 7-smooth", N);
+    PlanRec rec;
+    FftPlan& p = rec.plan;
+    p.N = N;
+    p.Npad = (N + 63) / 64 * 64;
+    p.nstage = 0;
+    int n = N;
+    // odd radices first (largest strides), powers of two last (unit strides)
+    const int odd[3] = {7, 5, 3};
+    for (int r : odd)
+        while (n % r == 0) { p.radix[p.nstage++] = r; n /= r; }
+    int l2 = 0;
+    while (n % 2 == 0) { ++l2; n /= 2; }
+    while (l2 >= 3 && l2 != 4) { p.radix[p.nstage++] = 8; l2 -= 3; }
+    while (l2 >= 2) { p.radix[p.nstage++] = 4; l2 -= 2; }
+    if (l2 == 1) p.radix[p.nstage++] = 2;
+    if (p.nstage > PKB_FFT_MAX_STAGES) return fail(PKB_ELIMIT, "FFT length %d needs too many stages", N);
+    std::vector<cplx> tw(N);
+    for (int j = 0; j < N; ++j) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
+        tw[j] = cmake((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<int> perm(N);
+    for (int k = 0; k < N; ++k) {
+        int f = k, M = N, pos = 0;
+        for (int s = 0; s < p.nstage; ++s) {
+            const int R = p.radix[s], Ms = M / R;
+            pos += (f % R) * Ms;
+            f /= R;
+            M = Ms;
+        }
+        perm[k] = pos;
+    }
+    CU(cudaMalloc((void**)&rec.tw, sizeof(cplx) * N));
+    CU(cudaMalloc((void**)&rec.perm, sizeof(int) * N));
+    CU(cudaMemcpy(rec.tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(rec.perm, perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    p.tw = rec.tw;
+    p.perm = rec.perm;
+    ctx->plans[N] = rec;
+    *out = p;
+    return 0;
+}
+
+extern "C" int pkb_debug_fft(pkb_ctx* ctx, int n, const double* in, double* out, int inverse) {
+    if (!ctx || !in || !out) return fail(PKB_EINVAL, "pkb_debug_fft: NULL argument");
+    if (n < 1 || !is_smooth(n)) return fail(PKB_EINVAL, "pkb_debug_fft: n = %d is not 7-smooth", n);
+    CU(cudaSetDevice(ctx->device));
+    FftPlan plan;
+    TRY(get_plan(ctx, n, &plan));
+    if ((size_t)plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "pkb_debug_fft: n = %d exceeds shared memory", n);
+    DBuf<cplx> a, b;
+    TRY(a.alloc(ctx, n));
+    TRY(b.alloc(ctx, n));
+    CU(cudaMemcpyAsync(a.p, in, sizeof(cplx) * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_fft_test, 1, ctx->fft_threads, plan.Npad * sizeof(cplx), a.p, b.p, inverse, plan);
+    CU(cudaMemcpyAsync(out, b.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_debug_fft");
+}
+
+// ---------------------------------------------------------------------------
+// phase 1
+// ---------------------------------------------------------------------------
+struct pkb_kset {
+    pkb_ctx* ctx;
+    int nprob, periods, racc, W, rad_res;
+    bool keep_pre;
+    DBuf<double> acc, pre, hprob, loss_t;
+    DBuf<PeriodInfo> pinfo;
+    DBuf<DayMeta> dmeta;
+    DBuf<DayParams> ddp;
+    DBuf<BvnPar> bvn;
+    std::vector<DayMeta> hmeta;
+    std::vector<DayParams> hdp;
+};
+
+static int check_dparams(const double d[3], const char* which) {
+    // Dmat's assertions (ParasitoidModel.py:276-278)
+    if (!(d[0] > 0)) return fail(PKB_EINVAL, "sig_x must be positive (%s)", which);
+    if (!(d[1] > 0)) return fail(PKB_EINVAL, "sig_y must be positive (%s)", which);
+    if (!(-1 <= d[2] && d[2] <= 1)) return fail(PKB_EINVAL, "correlation must be between -1 and 1 (%s)", which);
+    return 0;
+}
+
+// wind_dev: device pointer [nd_wind][periods][3]
+static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, int periods, const pkb_day_args* args, int nprob,
+                             int keep_pre, pkb_kset** out) {
+    if (nprob < 1 || periods < 1 || nd_wind < 1) return fail(PKB_EINVAL, "pkb_kernels_build: empty problem set");
+    pkb_kset* ks = new pkb_kset();
+    ks->ctx = ctx;
+    ks->nprob = nprob;
+    ks->periods = periods;
+    ks->keep_pre = keep_pre != 0;
+    ks->rad_res = args[0].rad_res;
+    struct Guard {
+        pkb_kset* k;
+        ~Guard() { delete k; }
+    } guard{ks};
+
+    std::vector<DayParams>& hdp = ks->hdp;
+    hdp.resize(nprob);
+    std::vector<double> dpar(6 * (size_t)nprob), cells(2 * (size_t)nprob);
+    for (int i = 0; i < nprob; ++i) {
+        const pkb_day_args& a = args[i];
+        if (a.rad_res != ks->rad_res) return fail(PKB_EINVAL, "pkb_kernels_build: all problems must share rad_res");
+        if (a.rad_res < 1 || !(a.rad_dist > 0)) return fail(PKB_EINVAL, "pkb_kernels_build: bad domain (rad_dist %g, rad_res %d)", a.rad_dist, a.rad_res);
+        if (a.n_periods < 1) return fail(PKB_EINVAL, "pkb_kernels_build: n_periods must be >= 1");
+        if (a.wind_day < 0 || a.wind_day >= nd_wind) return fail(PKB_EINVAL, "pkb_kernels_build: wind_day %d out of range", a.wind_day);
+        TRY(check_dparams(a.dparams, "Dparams"));
+        TRY(check_dparams(a.dlparams, "Dlparams"));
+        DayParams& d = hdp[i];
+        d.lam = a.hparams[0]; d.aw = a.hparams[1]; d.bw = a.hparams[2];
+        d.a1 = a.hparams[3]; d.b1 = a.hparams[4]; d.a2 = a.hparams[5]; d.b2 = a.hparams[6];
+        d.mu_r = a.mu_r;
+        d.cell = a.rad_dist / a.rad_res;                     // ParasitoidModel.py:411
+        d.n_periods = a.n_periods;
+        d.rad_res = a.rad_res;
+        d.single = a.single ? 1 : 0;
+        const int P = d.single ? 1 : periods;
+        d.start_indx = 0;
+        if (a.start_time >= 0) {
+            const double s = floor(a.start_time * P);         // :431-433
+            d.start_indx = s > P ? P : (int)s;
+        }
+        d.wind_day = a.wind_day;
+        d.has_next = (a.wind_day + 1 < nd_wind) ? 1 : 0;
+        d.bvn_S = 2 * i;
+        d.bvn_Sl = 2 * i + 1;
+        d.pad_ = 0;
+        for (int k = 0; k < 3; ++k) { dpar[6 * i + k] = a.dparams[k]; dpar[6 * i + 3 + k] = a.dlparams[k]; }
+        cells[2 * i] = cells[2 * i + 1] = d.cell;
+    }
+    DBuf<double> d_dpar, d_cells;
+    TRY(d_dpar.alloc(ctx, dpar.size()));
+    TRY(d_cells.alloc(ctx, cells.size()));
+    TRY(ks->bvn.alloc(ctx, 2 * (size_t)nprob));
+    TRY(ks->ddp.alloc(ctx, nprob));
+    TRY(ks->dmeta.alloc(ctx, nprob));
+    TRY(ks->hprob.alloc(ctx, (size_t)nprob * periods));
+    TRY(ks->loss_t.alloc(ctx, (size_t)nprob * periods));
+    TRY(ks->pinfo.alloc(ctx, (size_t)nprob * periods));
+    CU(cudaMemcpyAsync(d_dpar.p, dpar.data(), dpar.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_cells.p, cells.data(), cells.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ks->ddp.p, hdp.data(), sizeof(DayParams) * nprob, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ks->dmeta.p, 0, sizeof(DayMeta) * nprob, ctx->stream));
+    CU(cudaMemsetAsync(ks->loss_t.p, 0, sizeof(double) * (size_t)nprob * periods, ctx->stream));
+    CU(cudaMemsetAsync(ks->hprob.p, 0, sizeof(double) * (size_t)nprob * periods, ctx->stream));
+
+    LAUNCH(ctx, k_bvn_setup, 2 * nprob, 32, 0, ks->bvn.p, d_dpar.p, d_cells.p, 0);
+    if ((size_t)4 * periods * sizeof(double) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "too many periods per day (%d)", periods);
+    LAUNCH(ctx, k_hprob, nprob, 256, 4 * (size_t)periods * sizeof(double), ks->ddp.p, wind_dev, periods, ks->hprob.p, ks->dmeta.p,
+           (double*)nullptr, (double*)nullptr);
+    LAUNCH(ctx, k_drift, nprob, 256, 0, ks->ddp.p, ks->bvn.p, wind_dev, periods, ks->pinfo.p, ks->dmeta.p);
+
+    // size of the accumulation window: needs the drift extents (one small D2H)
+    ks->hmeta.resize(nprob);
+    std::vector<BvnPar> hbvn(2 * (size_t)nprob);
+    CU(cudaMemcpyAsync(ks->hmeta.data(), ks->dmeta.p, sizeof(DayMeta) * nprob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hbvn.data(), ks->bvn.p, sizeof(BvnPar) * 2 * nprob, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "phase 1 drift pass"));
+    int racc = 1, nmax = 4;
+    for (int i = 0; i < nprob; ++i) {
+        const int h0 = hbvn[2 * i].h0, hl = hbvn[2 * i + 1].h0;
+        if (h0 < 0 || hl < 0) return fail(PKB_ELIMIT, "BVN support half-width exceeds 4096 cells (problem %d)", i);
+        if (hl > ks->rad_res) return fail(PKB_ELIMIT, "local-diffusion blob (half-width %d) is larger than the domain (rad_res %d)", hl, ks->rad_res);
+        racc = std::max(racc, std::min(ks->rad_res, std::max(ks->hmeta[i].ext, hl)));
+        nmax = std::max(nmax, 2 * (h0 + 1) + 2);
+    }
+    if (nmax > PKB_LATTICE_CAP / 2) return fail(PKB_ELIMIT, "BVN support of %d cells per side exceeds the lattice tile", nmax);
+    ks->racc = racc;
+    ks->W = 2 * racc + 1;
+    const size_t nel = (size_t)ks->W * ks->W;
+    TRY(ks->acc.alloc(ctx, nel * nprob));
+    CU(cudaMemsetAsync(ks->acc.p, 0, sizeof(double) * nel * nprob, ctx->stream));
+    if (keep_pre) TRY(ks->pre.alloc(ctx, nel * nprob));
+
+    const size_t smem = (6 * (size_t)nmax + PKB_LATTICE_CAP) * sizeof(double);
+    LAUNCH(ctx, k_period, dim3(periods, nprob), 256, smem, ks->ddp.p, ks->bvn.p, ks->pinfo.p, ks->hprob.p, periods, nmax, ks->acc.p, racc,
+           ks->loss_t.p, ks->dmeta.p);
+    LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ks->ddp.p, ks->bvn.p, periods, ks->acc.p, racc, ks->loss_t.p, ks->dmeta.p, 1e-8,
+           keep_pre ? ks->pre.p : (double*)nullptr);
+    CU(cudaMemcpyAsync(ks->hmeta.data(), ks->dmeta.p, sizeof(DayMeta) * nprob, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "phase 1"));
+    guard.k = nullptr;
+    *out = ks;
+    return 0;
+}
+
+extern "C" int pkb_kernels_build(pkb_ctx* ctx, const double* wind, int nd_wind, int periods, const pkb_day_args* args, int nprob,
+                                 int keep_pre, pkb_kset** out) {
+    if (!ctx || !wind || !args || !out) return fail(PKB_EINVAL, "pkb_kernels_build: NULL argument");
+    *out = nullptr;
+    if (nd_wind < 1 || periods < 1) return fail(PKB_EINVAL, "pkb_kernels_build: empty wind array");
+    CU(cudaSetDevice(ctx->device));
+    DBuf<double> dw;
+    const size_t nw = (size_t)nd_wind * periods * 3;
+    TRY(dw.alloc(ctx, nw));
+    CU(cudaMemcpyAsync(dw.p, wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return kernels_build_dev(ctx, dw.p, nd_wind, periods, args, nprob, keep_pre, out);
+}
+
+extern "C" int pkb_kset_meta(pkb_kset* ks, int i, pkb_day_meta* out) {
+    if (!ks || !out || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_kset_meta: bad argument");
+    memcpy(out, &ks->hmeta[i], sizeof(DayMeta));
+    return 0;
+}
+
+extern "C" int pkb_kset_racc(pkb_kset* ks) { return ks ? ks->racc : -1; }
+
+// copy the centred (2r+1)^2 sub-window of a W x W device window to the host
+static int copy_window(pkb_ctx* ctx, const double* src, int W, int r, double* out) {
+    const int c = W / 2, k = 2 * r + 1;
+    for (int row = 0; row < k; ++row)
+        CU(cudaMemcpyAsync(out + (size_t)row * k, src + (size_t)(c - r + row) * W + (c - r), sizeof(double) * k, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    return sync_check(ctx, "copy_window");
+}
+
+extern "C" int pkb_kset_get(pkb_kset* ks, int i, double* out) {
+    if (!ks || !out || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_kset_get: bad argument");
+    CU(cudaSetDevice(ks->ctx->device));
+    const size_t nel = (size_t)ks->W * ks->W;
+    return copy_window(ks->ctx, ks->acc.p + nel * i, ks->W, ks->hmeta[i].rad, out);
+}
+
+extern "C" int pkb_kset_get_pre(pkb_kset* ks, int i, double* out) {
+    if (!ks || !out || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_kset_get_pre: bad argument");
+    if (!ks->keep_pre) return fail(PKB_ESTATE, "pkb_kset_get_pre: kernel set was built without keep_pre");
+    CU(cudaSetDevice(ks->ctx->device));
+    const size_t nel = (size_t)ks->W * ks->W;
+    CU(cudaMemcpyAsync(out, ks->pre.p + nel * i, sizeof(double) * nel, cudaMemcpyDeviceToHost, ks->ctx->stream));
+    return sync_check(ks->ctx, "pkb_kset_get_pre");
+}
+
+extern "C" int pkb_kset_periods(pkb_kset* ks, int i, int* rch, double* hprob) {
+    if (!ks || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_kset_periods: bad argument");
+    pkb_ctx* ctx = ks->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int P = ks->periods;
+    if (hprob) CU(cudaMemcpyAsync(hprob, ks->hprob.p + (size_t)i * P, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<PeriodInfo> pi(P);
+    if (rch) CU(cudaMemcpyAsync(pi.data(), ks->pinfo.p + (size_t)i * P, sizeof(PeriodInfo) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_kset_periods"));
+    if (rch) {
+        const DayParams& d = ks->hdp[i];
+        const int np = d.single ? 1 : P;
+        for (int t = 0; t < P; ++t) {
+            const bool live = t >= d.start_indx && t < np;
+            rch[3 * t] = live ? pi[t].row_c : -1;
+            rch[3 * t + 1] = live ? pi[t].col_c : -1;
+            rch[3 * t + 2] = live ? pi[t].h : -1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int pkb_kset_destroy(pkb_kset* ks) {
+    if (!ks) return 0;
+    cudaSetDevice(ks->ctx->device);
+    cudaStreamSynchronize(ks->ctx->stream);
+    delete ks;
+    return 0;
+}
+
+// h_flight_prob alone: a one-problem hprob launch
+extern "C" int pkb_hprob(pkb_ctx* ctx, const double* wind, int periods, int single, const double hparams[7], double* out,
+                         double* f_out, double* g_out) {
+    if (!ctx || !wind || !hparams || !out) return fail(PKB_EINVAL, "pkb_hprob: NULL argument");
+    if (periods < 1) return fail(PKB_EINVAL, "pkb_hprob: periods must be >= 1");
+    CU(cudaSetDevice(ctx->device));
+    if (single) periods = 1;
+    if ((size_t)4 * periods * sizeof(double) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "too many periods per day (%d)", periods);
+    DayParams d;
+    memset(&d, 0, sizeof d);
+    d.lam = hparams[0]; d.aw = hparams[1]; d.bw = hparams[2];
+    d.a1 = hparams[3]; d.b1 = hparams[4]; d.a2 = hparams[5]; d.b2 = hparams[6];
+    d.single = single ? 1 : 0;
+    d.start_indx = periods;   // no range check here: prob_mass asserts, h_flight_prob does not
+    DBuf<double> dw, dh, df, dg;
+    DBuf<DayParams> dd;
+    DBuf<DayMeta> dm;
+    TRY(dw.alloc(ctx, (size_t)periods * 3));
+    TRY(dh.alloc(ctx, periods));
+    TRY(df.alloc(ctx, periods));
+    TRY(dg.alloc(ctx, periods));
+    TRY(dd.alloc(ctx, 1));
+    TRY(dm.alloc(ctx, 1));
+    CU(cudaMemcpyAsync(dw.p, wind, sizeof(double) * 3 * periods, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dd.p, &d, sizeof d, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dm.p, 0, sizeof(DayMeta), ctx->stream));
+    LAUNCH(ctx, k_hprob, 1, 256, 4 * (size_t)periods * sizeof(double), dd.p, dw.p, periods, dh.p, dm.p, df.p, dg.p);
+    CU(cudaMemcpyAsync(out, dh.p, sizeof(double) * periods, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_out) CU(cudaMemcpyAsync(f_out, df.p, sizeof(double) * periods, cudaMemcpyDeviceToHost, ctx->stream));
+    if (g_out) CU(cudaMemcpyAsync(g_out, dg.p, sizeof(double) * periods, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_hprob");
+}
+
+extern "C" int pkb_mvn_cdf(pkb_ctx* ctx, double cell_length, const double mu[2], const double cov[3], double* out, int cap, int* h_out) {
+    if (!ctx || !mu || !cov || !out || !h_out) return fail(PKB_EINVAL, "pkb_mvn_cdf: NULL argument");
+    if (!(cell_length > 0) || !(cov[0] > 0) || !(cov[1] > 0)) return fail(PKB_EINVAL, "pkb_mvn_cdf: cell length and variances must be positive");
+    if (cap < 1) return fail(PKB_EINVAL, "pkb_mvn_cdf: cap must be positive");
+    CU(cudaSetDevice(ctx->device));
+    DBuf<BvnPar> bp;
+    DBuf<double> dpar, dcell, dout;
+    DBuf<int> dh;
+    TRY(bp.alloc(ctx, 1));
+    TRY(dpar.alloc(ctx, 3));
+    TRY(dcell.alloc(ctx, 1));
+    TRY(dout.alloc(ctx, cap));
+    TRY(dh.alloc(ctx, 1));
+    CU(cudaMemcpyAsync(dpar.p, cov, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dcell.p, &cell_length, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_bvn_setup, 1, 32, 0, bp.p, dpar.p, dcell.p, 1);
+    LAUNCH(ctx, k_mvn_cdf, 1, 256, 0, bp.p, cell_length, mu[0], mu[1], dout.p, cap, dh.p);
+    int h = -1;
+    CU(cudaMemcpyAsync(&h, dh.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_mvn_cdf"));
+    if (h < 0) return fail(PKB_ELIMIT, "pkb_mvn_cdf: support exceeds the output capacity (%d values)", cap);
+    const size_t n = (size_t)(2 * h + 1) * (2 * h + 1);
+    CU(cudaMemcpyAsync(out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_mvn_cdf"));
+    *h_out = h;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// phase 2: the chain
+// ---------------------------------------------------------------------------
+#define PKB_MAX_COHORTS 16
+
+struct pkb_chain {
+    pkb_ctx* ctx;
+    ChainDims d;
+    int mmax;
+    FftPlan plan;
+    DBuf<double> S[2];
+    int cur;
+    DBuf<cplx> Yt, Wt, Krt;
+    DBuf<RowStats> rstat;
+    DBuf<ChainCtrl> ctrl;   // [0] main state, [1 + j] cohort j
+    DBuf<StepMeta> meta;    // same indexing
+    DBuf<double> dout;      // D*D staging
+    DBuf<double> kup;       // uploaded filter window, (2*mmax+1)^2
+    DBuf<double> coh[PKB_MAX_COHORTS];
+    DBuf<cplx> kcache[PKB_MAX_COHORTS];   // cached row spectra of the release-day filters (fused solve)
+    int kcache_m[PKB_MAX_COHORTS];
+    double negval;          // threshold the row statistics were taken with
+    bool stats_valid;
+};
+
+static int roundup(int v, int q) { return (v + q - 1) / q * q; }
+
+static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
+    if (D < 1 || mmax < 0) return fail(PKB_EINVAL, "pkb_chain_create: bad sizes (dom_len %d, filter radius %d)", D, mmax);
+    pkb_chain* ch = new pkb_chain();
+    struct Guard {
+        pkb_chain* c;
+        ~Guard() { delete c; }
+    } guard{ch};
+    ch->ctx = ctx;
+    ch->mmax = mmax;
+    ChainDims& d = ch->d;
+    d.D = D;
+    d.P = D + mmax;                         // CalcSol.py:20-21 with max_shape = 2*mmax + 1
+    d.N = pkb_smooth_len(d.P + 2 * mmax);
+    d.Nc = d.N / 2 + 1;
+    d.ldS = roundup(d.P, 16);
+    d.ldY = roundup(d.P, 8);
+    d.ldW = roundup(d.N, 8);
+    d.ldK = roundup(2 * mmax + 1, 8);
+    TRY(get_plan(ctx, d.N, &ch->plan));
+    if ((size_t)2 * ch->plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem)
+        return fail(PKB_ELIMIT, "torus side %d (domain %d + filter radius %d) exceeds the shared-memory FFT limit of %d points", d.N, D,
+                    mmax, (int)(ctx->max_smem / (2 * sizeof(cplx))));
+    const size_t ns = (size_t)d.P * d.ldS;
+    TRY(ch->S[0].alloc(ctx, ns));
+    TRY(ch->S[1].alloc(ctx, ns));
+    TRY(ch->Yt.alloc(ctx, (size_t)d.Nc * d.ldY));
+    TRY(ch->Wt.alloc(ctx, (size_t)d.Nc * d.ldW));
+    TRY(ch->Krt.alloc(ctx, (size_t)d.Nc * d.ldK));
+    TRY(ch->rstat.alloc(ctx, d.P));
+    TRY(ch->ctrl.alloc(ctx, 1 + PKB_MAX_COHORTS));
+    TRY(ch->meta.alloc(ctx, 1 + PKB_MAX_COHORTS));
+    TRY(ch->dout.alloc(ctx, (size_t)D * D));
+    TRY(ch->kup.alloc(ctx, (size_t)(2 * mmax + 1) * (2 * mmax + 1)));
+    CU(cudaMemsetAsync(ch->S[0].p, 0, ns * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ch->ctrl.p, 0, sizeof(ChainCtrl) * (1 + PKB_MAX_COHORTS), ctx->stream));
+    CU(cudaMemsetAsync(ch->meta.p, 0, sizeof(StepMeta) * (1 + PKB_MAX_COHORTS), ctx->stream));
+    ch->cur = 0;
+    ch->negval = 1e-8;
+    ch->stats_valid = false;
+    for (int i = 0; i < PKB_MAX_COHORTS; ++i) ch->kcache_m[i] = -1;
+    guard.c = nullptr;
+    *out = ch;
+    return 0;
+}
+
+extern "C" int pkb_chain_create(pkb_ctx* ctx, int dom_len, int max_shape, pkb_chain** out) {
+    if (!ctx || !out) return fail(PKB_EINVAL, "pkb_chain_create: NULL argument");
+    *out = nullptr;
+    if (max_shape < 0) return fail(PKB_EINVAL, "pkb_chain_create: max_shape must be >= 0");
+    CU(cudaSetDevice(ctx->device));
+    return chain_create(ctx, dom_len, max_shape / 2, out);
+}
+
+extern "C" int pkb_chain_destroy(pkb_chain* ch) {
+    if (!ch) return 0;
+    cudaSetDevice(ch->ctx->device);
+    cudaStreamSynchronize(ch->ctx->stream);
+    delete ch;
+    return 0;
+}
+
+extern "C" int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N) {
+    if (!ch) return fail(PKB_EINVAL, "pkb_chain_dims: NULL chain");
+    if (D) *D = ch->d.D;
+    if (P) *P = ch->d.P;
+    if (N) *N = ch->d.N;
+    return 0;
+}
+
+// One convolution step: dst = src (*) K on the P torus.  K is a device window
+// Wk x Wk with support radius m.  krt: row spectra buffer to (re)use;
+// krt_ready: it already holds the spectra of K.  Leaves per-row statistics in
+// ch->rstat (taken with ch->negval).
+static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
+                     cplx* krt, bool krt_ready) {
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
+    if (2 * m > d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, d.P);
+    if (m <= ctx->stencil_max_radius) {
+        const size_t smem = ((size_t)(8 + 2 * m) * (32 + 2 * m) + (size_t)(2 * m + 1) * (2 * m + 1)) * sizeof(double);
+        LAUNCH(ctx, k_stencil, dim3((d.P + 31) / 32, (d.P + 7) / 8), dim3(32, 8), smem, src, K, Wk, m, d, src_ctrl, dst);
+        LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
+        return 0;
+    }
+    const int T = ctx->fft_threads;
+    const size_t sm1 = (size_t)ch->plan.Npad * sizeof(cplx);
+    if (!krt_ready) LAUNCH(ctx, k_kernel_rows, m + 1, T, sm1, K, Wk, m, d, krt, ch->plan);
+    LAUNCH(ctx, k_rows_fwd, (d.P + 1) / 2, T, sm1, src, d, src_ctrl, ch->Yt.p, ch->plan);
+    LAUNCH(ctx, k_cols, d.Nc, T, 2 * sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl, ch->Wt.p, ch->plan);
+    const int njobs = 2 * m + (d.P - 2 * m + 1) / 2;
+    LAUNCH(ctx, k_rows_inv, njobs, T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan);
+    return 0;
+}
+
+// flag / sums of the state whose row statistics are in ch->rstat -> ctrl[slot], meta[slot];
+// apply_trunc: also truncate a flagged state to the domain (CalcSol.py:200-201)
+static void finalize_step(pkb_chain* ch, double* state, int slot, int apply_trunc) {
+    pkb_ctx* ctx = ch->ctx;
+    LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, ch->d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
+    if (apply_trunc) LAUNCH(ctx, k_zero_pad, ch->d.P, 256, 0, state, ch->d, (const ChainCtrl*)(ch->ctrl.p + slot));
+}
+
+extern "C" int pkb_chain_set_state(pkb_chain* ch, const double* A) {
+    if (!ch || !A) return fail(PKB_EINVAL, "pkb_chain_set_state: NULL argument");
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    CU(cudaSetDevice(ctx->device));
+    double* S = ch->S[ch->cur].p;
+    CU(cudaMemsetAsync(S, 0, (size_t)d.P * d.ldS * sizeof(double), ctx->stream));
+    CU(cudaMemcpyAsync(ch->dout.p, A, (size_t)d.D * d.D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_load_state, d.D, 256, 0, (const double*)ch->dout.p, d, S);
+    LAUNCH(ctx, k_set_ctrl, 1, 32, 0, ch->ctrl.p, 1, 0);
+    ch->stats_valid = false;
+    return sync_check(ctx, "pkb_chain_set_state");
+}
+
+static int set_state_kernel_dev(pkb_chain* ch, const double* K, int Wk, int m) {
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    if (m > d.D / 2) return fail(PKB_ELIMIT, "kernel radius %d is larger than the domain radius %d", m, d.D / 2);
+    double* S = ch->S[ch->cur].p;
+    CU(cudaMemsetAsync(S, 0, (size_t)d.P * d.ldS * sizeof(double), ctx->stream));
+    LAUNCH(ctx, k_place_kernel, 2 * m + 1, 128, 0, K, Wk, m, d, S);
+    LAUNCH(ctx, k_set_ctrl, 1, 32, 0, ch->ctrl.p, 1, 0);
+    ch->stats_valid = false;
+    return 0;
+}
+
+extern "C" int pkb_chain_set_state_kernel(pkb_chain* ch, pkb_kset* ks, int i) {
+    if (!ch || !ks || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_chain_set_state_kernel: bad argument");
+    CU(cudaSetDevice(ch->ctx->device));
+    if (2 * ks->rad_res + 1 != ch->d.D) return fail(PKB_EINVAL, "kernel set domain (%d) does not match the chain (%d)", 2 * ks->rad_res + 1, ch->d.D);
+    TRY(set_state_kernel_dev(ch, ks->acc.p + (size_t)ks->W * ks->W * i, ks->W, ks->hmeta[i].rad));
+    return sync_check(ch->ctx, "pkb_chain_set_state_kernel");
+}
+
+// upload the support window of a host filter (k x k, odd) into ch->kup; returns its radius
+static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
+    pkb_ctx* ctx = ch->ctx;
+    if (k < 1 || !(k & 1)) return fail(PKB_EINVAL, "filters must be square with an odd side (got %d)", k);
+    const int c = k / 2;
+    int m = 0;
+    for (int r = 0; r < k; ++r)
+        for (int q = 0; q < k; ++q)
+            if (B[(size_t)r * k + q] != 0.0) m = std::max(m, std::max(std::abs(r - c), std::abs(q - c)));
+    if (m > ch->mmax) return fail(PKB_ELIMIT, "filter support radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
+    const int w = 2 * m + 1;
+    std::vector<double> win((size_t)w * w);
+    for (int r = 0; r < w; ++r) memcpy(&win[(size_t)r * w], B + (size_t)(c - m + r) * k + (c - m), sizeof(double) * w);
+    CU(cudaMemcpyAsync(ch->kup.p, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // `win` is pageable and about to go out of scope
+    *m_out = m;
+    return 0;
+}
+
+static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m) {
+    const int nxt = ch->cur ^ 1;
+    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, ch->Krt.p, false));
+    ch->cur = nxt;
+    return 0;
+}
+
+extern "C" int pkb_chain_conv(pkb_chain* ch, const double* B, int k) {
+    if (!ch || !B) return fail(PKB_EINVAL, "pkb_chain_conv: NULL argument");
+    CU(cudaSetDevice(ch->ctx->device));
+    int m = 0;
+    TRY(upload_filter(ch, B, k, &m));
+    TRY(chain_conv_main(ch, ch->kup.p, 2 * m + 1, m));
+    finalize_step(ch, ch->S[ch->cur].p, 0, 0);
+    ch->stats_valid = true;
+    return sync_check(ch->ctx, "pkb_chain_conv");
+}
+
+extern "C" int pkb_chain_conv_kernel(pkb_chain* ch, pkb_kset* ks, int i) {
+    if (!ch || !ks || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_chain_conv_kernel: bad argument");
+    CU(cudaSetDevice(ch->ctx->device));
+    TRY(chain_conv_main(ch, ks->acc.p + (size_t)ks->W * ks->W * i, ks->W, ks->hmeta[i].rad));
+    finalize_step(ch, ch->S[ch->cur].p, 0, 0);
+    ch->stats_valid = true;
+    return sync_check(ch->ctx, "pkb_chain_conv_kernel");
+}
+
+extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int apply_trunc, double* out, pkb_step_meta* meta) {
+    if (!ch) return fail(PKB_EINVAL, "pkb_chain_get_cursol: NULL chain");
+    if (mode < 0 || mode > 2) return fail(PKB_EINVAL, "pkb_chain_get_cursol: mode must be 0, 1 or 2");
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    CU(cudaSetDevice(ctx->device));
+    double* S = ch->S[ch->cur].p;
+    if (!ch->stats_valid || negval != ch->negval) {
+        ch->negval = negval;
+        LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)S, d, ch->rstat.p, negval);
+        finalize_step(ch, S, 0, 0);
+        ch->stats_valid = true;
+    }
+    if (out) {
+        if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p);
+        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, 0, ch->dout.p);
+        CU(cudaMemcpyAsync(out, ch->dout.p, (size_t)d.D * d.D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (apply_trunc) {
+        LAUNCH(ctx, k_apply_trunc, 1, 32, 0, ch->ctrl.p);
+        LAUNCH(ctx, k_zero_pad, d.P, 256, 0, S, d, (const ChainCtrl*)ch->ctrl.p);
+    }
+    StepMeta hm;
+    CU(cudaMemcpyAsync(&hm, ch->meta.p, sizeof hm, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_chain_get_cursol"));
+    if (meta) memcpy(meta, &hm, sizeof hm);
+    return 0;
+}
+
+// cohorts of earlier release days: cohort j = state (*) F[nf-1] (*) ... (*) F[j]
+// F[j]: device window (Wk[j], radius m[j]); krt[j]/ready[j]: optional cached spectra.
+static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, const int* m, int nf, cplx* const* krt, bool* ready) {
+    if (nf > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "at most %d earlier release days are supported", PKB_MAX_COHORTS);
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    const double* src = ch->S[ch->cur].p;
+    const ChainCtrl* src_ctrl = ch->ctrl.p;
+    for (int j = nf - 1; j >= 0; --j) {
+        if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
+        cplx* kr = krt ? krt[j] : ch->Krt.p;
+        const bool rdy = krt && ready && ready[j];
+        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, F[j], Wk[j], m[j], kr, rdy));
+        if (ready) ready[j] = true;
+        finalize_step(ch, ch->coh[j].p, 1 + j, 1);     // CalcSol.py:103-105 (same-shape re-FFT)
+        src = ch->coh[j].p;
+        src_ctrl = ch->ctrl.p + 1 + j;
+    }
+    return 0;
+}
+
+extern "C" int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters, const int* ks, int nf, double threshold, double* out,
+                                    int* flags) {
+    if (!ch || (nf > 0 && (!filters || !ks))) return fail(PKB_EINVAL, "pkb_chain_back_solve: NULL argument");
+    if (nf > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "at most %d earlier release days are supported", PKB_MAX_COHORTS);
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    CU(cudaSetDevice(ctx->device));
+    const double* src = ch->S[ch->cur].p;
+    const ChainCtrl* src_ctrl = ch->ctrl.p;
+    const size_t nd = (size_t)d.D * d.D;
+    for (int j = nf - 1; j >= 0; --j) {
+        if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
+        int m = 0;
+        TRY(upload_filter(ch, filters[j], ks[j], &m));
+        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false));
+        finalize_step(ch, ch->coh[j].p, 1 + j, 1);
+        if (out) {
+            if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p);
+            else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p);
+            CU(cudaMemcpyAsync(out + nd * j, ch->dout.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        src = ch->coh[j].p;
+        src_ctrl = ch->ctrl.p + 1 + j;
+    }
+    std::vector<StepMeta> hm(nf > 0 ? nf : 1);
+    if (nf > 0) CU(cudaMemcpyAsync(hm.data(), ch->meta.p + 1, sizeof(StepMeta) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_chain_back_solve"));
+    if (flags)
+        for (int j = 0; j < nf; ++j) flags[j] = hm[j].flag;
+    return 0;
+}
+
+// Population-model output from the cohorts of the last pkb_chain_back_solve
+// (cohorts 0..ncoh-2) plus the current state (cohort ncoh-1).
+extern "C" int pkb_chain_population(pkb_chain* ch, int ncoh, const double* weights, double r_number, double centre_extra, int add_centre,
+                                    double negval, int first_day, double* out, double* pre) {
+    if (!ch || !weights || !out) return fail(PKB_EINVAL, "pkb_chain_population: NULL argument");
+    if (ncoh < 1 || ncoh > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "pkb_chain_population: 1..%d cohorts are supported", PKB_MAX_COHORTS);
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    CU(cudaSetDevice(ctx->device));
+    CohortArgs ca;
+    memset(&ca, 0, sizeof ca);
+    ca.n = ncoh;
+    for (int c = 0; c < ncoh; ++c) {
+        if (c < ncoh - 1 && !ch->coh[c].p) return fail(PKB_ESTATE, "pkb_chain_population: cohort %d has not been computed (call pkb_chain_back_solve)", c);
+        ca.S[c] = c < ncoh - 1 ? ch->coh[c].p : ch->S[ch->cur].p;
+        ca.w[c] = weights[c];
+    }
+    DBuf<double> dpre;
+    const size_t nd = (size_t)d.D * d.D;
+    if (pre) TRY(dpre.alloc(ctx, nd));
+    LAUNCH(ctx, k_emit_population, d.D, 256, 0, ca, d, r_number, centre_extra, add_centre, negval, first_day, ch->dout.p,
+           pre ? dpre.p : (double*)nullptr);
+    CU(cudaMemcpyAsync(out, ch->dout.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pre) CU(cudaMemcpyAsync(pre, dpre.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_chain_population");
+}
+
+extern "C" int pkb_chain_get_state(pkb_chain* ch, double* out) {
+    if (!ch || !out) return fail(PKB_EINVAL, "pkb_chain_get_state: NULL argument");
+    pkb_ctx* ctx = ch->ctx;
+    const ChainDims& d = ch->d;
+    CU(cudaSetDevice(ctx->device));
+    const double* S = ch->S[ch->cur].p;
+    for (int r = 0; r < d.P; ++r)
+        CU(cudaMemcpyAsync(out + (size_t)r * d.P, S + (size_t)r * d.ldS, sizeof(double) * d.P, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_chain_get_state");
+}
+
+// ---------------------------------------------------------------------------
+// fused forward solve
+// ---------------------------------------------------------------------------
+struct pkb_result {
+    pkb_ctx* ctx;
+    int ndays, D, P, N, max_shape;
+    DBuf<double> dense;     // [ndays][D][D]
+    DBuf<double> pre;       // optional [ndays][D][D] un-thresholded (parity export)
+    std::vector<DayMeta> kmeta;
+    std::vector<StepMeta> smeta;
+    HBuf<long long> dayoff;
+    HBuf<int> rows, cols;
+    HBuf<double> vals;
+    bool have_coo;
+};
+
+static int build_coo(pkb_ctx* ctx, pkb_result* r) {
+    const int D = r->D, nd = r->ndays;
+    DBuf<int> rownnz;
+    DBuf<long long> rowoff, dayoff;
+    TRY(rownnz.alloc(ctx, (size_t)nd * D));
+    TRY(rowoff.alloc(ctx, (size_t)nd * D));
+    TRY(dayoff.alloc(ctx, nd + 1));
+    LAUNCH(ctx, k_row_nnz, nd * D, 256, 0, (const double*)r->dense.p, D, rownnz.p);
+    LAUNCH(ctx, k_row_scan, 1, 1024, 0, (const int*)rownnz.p, D, nd, rowoff.p, dayoff.p);
+    TRY(r->dayoff.alloc(ctx, nd + 1));
+    CU(cudaMemcpyAsync(r->dayoff.p, dayoff.p, sizeof(long long) * (nd + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "COO sizing"));
+    const long long total = r->dayoff.p[nd];
+    DBuf<int> drows, dcols;
+    DBuf<double> dvals;
+    TRY(drows.alloc(ctx, total));
+    TRY(dcols.alloc(ctx, total));
+    TRY(dvals.alloc(ctx, total));
+    LAUNCH(ctx, k_coo_write, nd * D, 256, 0, (const double*)r->dense.p, D, (const long long*)rowoff.p, drows.p, dcols.p, dvals.p);
+    TRY(r->rows.alloc(ctx, total));
+    TRY(r->cols.alloc(ctx, total));
+    TRY(r->vals.alloc(ctx, total));
+    if (total > 0) {
+        CU(cudaMemcpyAsync(r->rows.p, drows.p, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->cols.p, dcols.p, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->vals.p, dvals.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRY(sync_check(ctx, "COO copy"));
+    r->have_coo = true;
+    return 0;
+}
+
+extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out) {
+    if (!ctx || !a || !out || !a->wind) return fail(PKB_EINVAL, "pkb_solve: NULL argument");
+    *out = nullptr;
+    if (a->ndays < 1 || a->ndays > a->nd_wind) return fail(PKB_EINVAL, "pkb_solve: ndays %d must be in [1, %d]", a->ndays, a->nd_wind);
+    if (!a->prob_model) {
+        if (a->r_dur < 1 || a->r_dur > a->ndays) return fail(PKB_EINVAL, "pkb_solve: r_dur %d must be in [1, ndays]", a->r_dur);
+        if (a->r_dur > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "pkb_solve: r_dur is limited to %d days", PKB_MAX_COHORTS);
+        if (!a->r_dist) return fail(PKB_EINVAL, "pkb_solve: r_dist is NULL");
+    }
+    CU(cudaSetDevice(ctx->device));
+    const int nd = a->ndays;
+    const double negval = a->negval > 0 ? a->negval : 1e-8;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    // ---- phase 1 (Run.py:412-425) ------------------------------------------
+    DBuf<double> dwind;
+    const double* wind_dev = a->wind;
+    if (!a->wind_on_device) {
+        const size_t nw = (size_t)a->nd_wind * a->periods * 3;
+        TRY(dwind.alloc(ctx, nw));
+        CU(cudaMemcpyAsync(dwind.p, a->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        wind_dev = dwind.p;
+    }
+    std::vector<pkb_day_args> dargs(nd, a->day);
+    for (int i = 0; i < nd; ++i) {
+        dargs[i].wind_day = i;
+        dargs[i].single = 0;
+        dargs[i].start_time = (!a->prob_model && i == 0 && a->r_start >= 0) ? a->r_start : -1.0;   // Run.py:418-421
+    }
+    pkb_kset* ks = nullptr;
+    TRY(kernels_build_dev(ctx, wind_dev, a->nd_wind, a->periods, dargs.data(), nd, 0, &ks));
+    struct KGuard {
+        pkb_kset* k;
+        ~KGuard() { delete k; }
+    } kguard{ks};
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    int mmax = 0;
+    for (int i = 0; i < nd; ++i) mmax = std::max(mmax, ks->hmeta[i].rad);      // Run.py:426-429
+    const int D = 2 * ks->rad_res + 1;
+
+    pkb_result* res = new pkb_result();
+    struct RGuard {
+        pkb_result* r;
+        ~RGuard() { delete r; }
+    } rguard{res};
+    res->ctx = ctx;
+    res->ndays = nd;
+    res->D = D;
+    res->max_shape = 2 * mmax + 1;
+    res->have_coo = false;
+    res->kmeta = ks->hmeta;
+    res->smeta.assign(nd, StepMeta());
+    for (auto& sm : res->smeta) memset(&sm, 0, sizeof sm);
+
+    // ---- phase 2 -----------------------------------------------------------
+    pkb_chain* ch = nullptr;
+    TRY(chain_create(ctx, D, mmax, &ch));
+    struct CGuard {
+        pkb_chain* c;
+        ~CGuard() { delete c; }
+    } cguard{ch};
+    ch->negval = negval;
+    const ChainDims d = ch->d;
+    res->P = d.P;
+    res->N = d.N;
+    const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
+    TRY(res->dense.alloc(ctx, nD * nd));
+    DBuf<StepMeta> dsm;
+    TRY(dsm.alloc(ctx, nd));
+    CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
+    auto kern = [&](int i) { return (const double*)(ks->acc.p + nW * i); };
+    auto krad = [&](int i) { return ks->hmeta[i].rad; };
+
+    if (a->prob_model) {
+        // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
+        TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
+        LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
+        for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n)));
+            finalize_step(ch, ch->S[ch->cur].p, 0, 1);
+            LAUNCH(ctx, k_emit_dense, D, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)ch->meta.p, negval, 1, 0,
+                   res->dense.p + nD * n);
+            CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    } else {
+        const int rd = a->r_dur;
+        const double rn = a->r_number;
+        const double* F[PKB_MAX_COHORTS];
+        int Wk[PKB_MAX_COHORTS], mm[PKB_MAX_COHORTS];
+        cplx* krt[PKB_MAX_COHORTS];
+        bool ready[PKB_MAX_COHORTS];
+        for (int j = 0; j < rd; ++j) {
+            F[j] = kern(j); Wk[j] = ks->W; mm[j] = krad(j); ready[j] = false; krt[j] = nullptr;
+            if (krad(j) > D / 2) return fail(PKB_ELIMIT, "kernel radius %d is larger than the domain radius", krad(j));
+        }
+        for (int j = 0; j + 1 < rd; ++j) {
+            TRY(ch->kcache[j].alloc(ctx, (size_t)d.Nc * d.ldK));
+            krt[j] = ch->kcache[j].p;
+        }
+        // r_spread[j] as a state (Run.py:469-474); `spread` holds the latest one
+        DBuf<double> spread;
+        TRY(spread.alloc(ctx, (size_t)d.P * d.ldS));
+        CohortArgs ca;
+        memset(&ca, 0, sizeof ca);
+        // day 0 (CalcSol.py:236-237)
+        TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
+        ca.n = 1; ca.S[0] = ch->S[ch->cur].p; ca.w[0] = a->r_dist[0];
+        LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, rn * (1 - a->r_dist[0]), 1, negval, 1, res->dense.p, (double*)nullptr);
+        // release days (CalcSol.py:296-306)
+        for (int day = 1; day < rd; ++day) {
+            TRY(set_state_kernel_dev(ch, kern(day), ks->W, krad(day)));
+            TRY(back_solve_dev(ch, F, Wk, mm, day, krt, ready));
+            double wsum = 0.0;
+            for (int c = 0; c <= day; ++c) {
+                ca.S[c] = c < day ? ch->coh[c].p : ch->S[ch->cur].p;
+                ca.w[c] = a->r_dist[c];
+                wsum += a->r_dist[c];
+            }
+            ca.n = day + 1;
+            LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, (1 - wsum) * rn, 1, negval, 0, res->dense.p + nD * day, (double*)nullptr);
+        }
+        // post-release days (CalcSol.py:308-323)
+        for (int n = rd; n < nd; ++n) {
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n)));
+            finalize_step(ch, ch->S[ch->cur].p, 0, 1);
+            CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+            TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
+            for (int c = 0; c < rd; ++c) {
+                ca.S[c] = c < rd - 1 ? ch->coh[c].p : ch->S[ch->cur].p;
+                ca.w[c] = a->r_dist[c];
+            }
+            ca.n = rd;
+            LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, 0.0, 0, negval, 0, res->dense.p + nD * n, (double*)nullptr);
+        }
+    }
+    CU(cudaMemcpyAsync(res->smeta.data(), dsm.p, sizeof(StepMeta) * nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    TRY(sync_check(ctx, "pkb_solve chain"));
+
+    // ---- outputs -----------------------------------------------------------
+    if (a->want_coo) TRY(build_coo(ctx, res));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    TRY(sync_check(ctx, "pkb_solve outputs"));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->timing[0] = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->timing[1] = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing[2] = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3])); ctx->timing[3] = ms;
+    if (!a->keep_dense_device && !a->want_dense_host) res->dense.release();
+    rguard.r = nullptr;
+    *out = res;
+    return 0;
+}
+
+extern "C" int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape) {
+    if (!r) return fail(PKB_EINVAL, "pkb_result_info: NULL result");
+    if (ndays) *ndays = r->ndays;
+    if (dom_len) *dom_len = r->D;
+    if (P) *P = r->P;
+    if (N) *N = r->N;
+    if (max_shape) *max_shape = r->max_shape;
+    return 0;
+}
+
+extern "C" int pkb_result_day_meta(pkb_result* r, int day, pkb_day_meta* kmeta, pkb_step_meta* smeta) {
+    if (!r || day < 0 || day >= r->ndays) return fail(PKB_EINVAL, "pkb_result_day_meta: bad argument");
+    if (kmeta) memcpy(kmeta, &r->kmeta[day], sizeof(DayMeta));
+    if (smeta) memcpy(smeta, &r->smeta[day], sizeof(StepMeta));
+    return 0;
+}
+
+extern "C" int pkb_result_dense(pkb_result* r, int day, double* out) {
+    if (!r || !out || day < 0 || day >= r->ndays) return fail(PKB_EINVAL, "pkb_result_dense: bad argument");
+    if (!r->dense.p) return fail(PKB_ESTATE, "pkb_result_dense: dense solutions were not kept (want_dense_host / keep_dense_device)");
+    pkb_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t nD = (size_t)r->D * r->D;
+    CU(cudaMemcpyAsync(out, r->dense.p + nD * day, nD * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_result_dense");
+}
+
+extern "C" int pkb_result_coo(pkb_result* r, const long long** day_offsets, const int** rows, const int** cols, const double** vals) {
+    if (!r) return fail(PKB_EINVAL, "pkb_result_coo: NULL result");
+    if (!r->have_coo) return fail(PKB_ESTATE, "pkb_result_coo: solve was run without want_coo");
+    if (day_offsets) *day_offsets = r->dayoff.p;
+    if (rows) *rows = r->rows.p;
+    if (cols) *cols = r->cols.p;
+    if (vals) *vals = r->vals.p;
+    return 0;
+}
+
+extern "C" int pkb_result_sample(pkb_result* r, const int* cells, int K, double* out) {
+    if (!r || !cells || !out || K < 1) return fail(PKB_EINVAL, "pkb_result_sample: bad argument");
+    if (!r->dense.p) return fail(PKB_ESTATE, "pkb_result_sample: dense solutions were not kept");
+    pkb_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2 * K; ++k)
+        if (cells[k] < 0 || cells[k] >= r->D) return fail(PKB_EINVAL, "pkb_result_sample: cell index %d outside the domain", cells[k]);
+    DBuf<int> dc;
+    DBuf<double> dv;
+    TRY(dc.alloc(ctx, 2 * (size_t)K));
+    TRY(dv.alloc(ctx, (size_t)K * r->ndays));
+    CU(cudaMemcpyAsync(dc.p, cells, sizeof(int) * 2 * K, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_sample, r->ndays, 256, 0, (const double*)r->dense.p, r->D, (const int*)dc.p, K, dv.p);
+    CU(cudaMemcpyAsync(out, dv.p, sizeof(double) * K * r->ndays, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_result_sample");
+}
+
+extern "C" int pkb_result_device_ptr(pkb_result* r, void** dptr) {
+    if (!r || !dptr) return fail(PKB_EINVAL, "pkb_result_device_ptr: NULL argument");
+    if (!r->dense.p) return fail(PKB_ESTATE, "pkb_result_device_ptr: dense solutions were not kept");
+    *dptr = r->dense.p;
+    return 0;
+}
+
+extern "C" int pkb_result_destroy(pkb_result* r) {
+    if (!r) return 0;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    delete r;
+    return 0;
+}
