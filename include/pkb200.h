@@ -88,6 +88,16 @@ int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
 int pkb_timing(pkb_ctx* ctx, double out_ms[4]);
 /* number of kernel launches issued through this context so far */
 long long pkb_launch_count(pkb_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream: record mark `slot` (0..7);
+ * device time between two recorded marks (waits for the later one) */
+int pkb_mark(pkb_ctx* ctx, int slot);
+int pkb_elapsed_ms(pkb_ctx* ctx, int slot_a, int slot_b, double* ms);
+/* per-kernel device timing: while enabled every launch is bracketed by CUDA
+ * events on the context's stream; pkb_profile_get returns the launch count and
+ * summed duration of one kernel by name (e.g. "k_cols") since the last reset */
+int pkb_profile_enable(pkb_ctx* ctx, int on);
+int pkb_profile_reset(pkb_ctx* ctx);
+int pkb_profile_get(pkb_ctx* ctx, const char* kernel, long long* count, double* total_ms);
 
 /* ---- phase 1: ParasitoidModel.py ------------------------------------------ */
 /* h_flight_prob(day_wind, lam, aw, bw, a1, b1, a2, b2)  (ParasitoidModel.py:282-309)

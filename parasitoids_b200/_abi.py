@@ -60,6 +60,11 @@ _SIGS = {
     'pkb_set_option': (C.c_int, [_H, C.c_char_p, C.c_double]),
     'pkb_timing': (C.c_int, [_H, c_double_p]),
     'pkb_launch_count': (C.c_longlong, [_H]),
+    'pkb_mark': (C.c_int, [_H, C.c_int]),
+    'pkb_elapsed_ms': (C.c_int, [_H, C.c_int, C.c_int, c_double_p]),
+    'pkb_profile_enable': (C.c_int, [_H, C.c_int]),
+    'pkb_profile_reset': (C.c_int, [_H]),
+    'pkb_profile_get': (C.c_int, [_H, C.c_char_p, c_ll_p, c_double_p]),
     'pkb_hprob': (C.c_int, [_H, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     'pkb_mvn_cdf': (C.c_int, [_H, C.c_double, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p]),
     'pkb_kernels_build': (C.c_int, [_H, c_double_p, C.c_int, C.c_int, C.POINTER(DayArgs), C.c_int, C.c_int, _HP]),

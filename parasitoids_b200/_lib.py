@@ -74,6 +74,26 @@ class Context(object):
         check(lib().pkb_timing(self.h, out))
         return dict(phase1_ms=out[0], chain_ms=out[1], output_ms=out[2], total_ms=out[3])
 
+    def mark(self, slot):
+        check(lib().pkb_mark(self.h, int(slot)))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_double()
+        check(lib().pkb_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value
+
+    def profile(self, on):
+        check(lib().pkb_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        check(lib().pkb_profile_reset(self.h))
+
+    def profile_get(self, kernel):
+        """(launch count, total device ms) of one kernel since the last reset."""
+        n, ms = C.c_longlong(), C.c_double()
+        check(lib().pkb_profile_get(self.h, kernel.encode(), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
     def close(self):
         if self.h:
             lib().pkb_destroy(self.h)

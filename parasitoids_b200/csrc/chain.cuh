@@ -394,7 +394,7 @@ __global__ void k_row_nnz(const double* __restrict__ G, int D, int* __restrict__
 // global COO position of row r of that day; dayoff[day] the start of the day,
 // dayoff[ndays] the grand total.  grid = 1, block = 1024; each thread owns a
 // contiguous chunk of the ndays*D rows.
-__global__ void k_row_scan(const int* __restrict__ rownnz, int D, int ndays, long long* __restrict__ rowoff, long long* __restrict__ dayoff) {
+__global__ void __launch_bounds__(1024) k_row_scan(const int* __restrict__ rownnz, int D, int ndays, long long* __restrict__ rowoff, long long* __restrict__ dayoff) {
     PKB_SHARED(long long, part, 1024);
     const long long n = (long long)D * ndays;
     const int tid = threadIdx.x, T = blockDim.x;

@@ -343,7 +343,7 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
 // ---------------------------------------------------------------------------
 // grid = problems, block = 1024.  Works in place on the accumulation window.
 // pre (optional): receives the pre-threshold window (parity export).
-__global__ void k_day_finalize(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, int periods, double* __restrict__ acc,
+__global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, int periods, double* __restrict__ acc,
                                int racc, const double* __restrict__ loss_t, DayMeta* __restrict__ meta, double negval,
                                double* __restrict__ pre) {
     PKB_SHARED(double, red, 1024);

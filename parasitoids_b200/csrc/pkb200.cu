@@ -76,7 +76,14 @@ struct pkb_ctx {
     std::map<size_t, std::vector<void*> > dev_free, host_free;
     std::map<void*, size_t> dev_live, host_live;
     cudaEvent_t ev[5];
+    cudaEvent_t marks[8];
     double timing[4];
+    // optional per-kernel device timing (pkb_profile_*): event pairs around launches
+    bool prof_on;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    std::map<std::string, std::pair<long long, double> > prof_acc;
     int stencil_max_radius;
     int fft_threads;
     int max_smem;
@@ -195,9 +202,45 @@ struct HBuf {
     HBuf& operator=(const HBuf&) = delete;
 };
 
+static cudaEvent_t prof_event(pkb_ctx* ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->prof_pool.empty()) {
+        e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+static void prof_begin(pkb_ctx* ctx, const char* name) {
+    pkb_ctx::ProfRec r;
+    r.name = name;
+    r.a = prof_event(ctx);
+    r.b = prof_event(ctx);
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof_pending.push_back(r);
+}
+static void prof_end(pkb_ctx* ctx) { cudaEventRecord(ctx->prof_pending.back().b, ctx->stream); }
+// fold finished event pairs into the accumulators (call after a stream sync)
+static void prof_collect(pkb_ctx* ctx) {
+    for (auto& r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& acc = ctx->prof_acc[r.name];
+            acc.first += 1;
+            acc.second += ms;
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+}
+
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                             \
     do {                                                                      \
+        if ((ctx)->prof_on) prof_begin((ctx), #kern);                         \
         PKB_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);      \
+        if ((ctx)->prof_on) prof_end((ctx));                                  \
         (ctx)->launches++;                                                    \
     } while (0)
 
@@ -211,10 +254,21 @@ static int sync_check(pkb_ctx* ctx, const char* where) {
     TRY(check_launches(ctx, where));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(PKB_ECUDA, "stream synchronize failed in %s: %s", where, cudaGetErrorString(e));
+    if (!ctx->prof_pending.empty()) prof_collect(ctx);
     return 0;
 }
 
 static const int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+static const int kStaticSmemReserve = 8192 + 1024;   // largest static __shared__ use of any kernel here
+
+// allow a kernel the full opt-in dynamic shared memory (minus its static use)
+template <class F>
+static int opt_in_smem(F kern) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kern));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - (int)fa.sharedSizeBytes));
+    return 0;
+}
 
 extern "C" int pkb_create(int device, pkb_ctx** out) {
     if (!out) return fail(PKB_EINVAL, "pkb_create: out is NULL");
@@ -231,18 +285,20 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->launches = 0;
     ctx->stencil_max_radius = 3;
     ctx->fft_threads = 256;
-    ctx->max_smem = kMaxSmem;
+    ctx->max_smem = kMaxSmem - kStaticSmemReserve;
+    ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
     for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&ctx->ev[i]));
-    CU(cudaFuncSetAttribute(k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_kernel_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_fft_test, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_period, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_hprob, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_stencil, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&ctx->marks[i]));
+    TRY(opt_in_smem(k_rows_fwd));
+    TRY(opt_in_smem(k_kernel_rows));
+    TRY(opt_in_smem(k_cols));
+    TRY(opt_in_smem(k_rows_inv));
+    TRY(opt_in_smem(k_fft_test));
+    TRY(opt_in_smem(k_period));
+    TRY(opt_in_smem(k_hprob));
+    TRY(opt_in_smem(k_stencil));
     *out = ctx;
     return 0;
 }
@@ -262,6 +318,9 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
         for (void* p : kv.second) cudaFreeHost(p);
     for (auto& kv : ctx->host_live) cudaFreeHost(kv.first);
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->marks[i]);
+    for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -281,7 +340,7 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fft_threads")) {
         const int t = (int)value;
-        if (t < 32 || t > 1024 || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, 1024]");
+        if (t < 32 || t > 512 || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, 512]");
         ctx->fft_threads = t;
         return 0;
     }
@@ -295,6 +354,46 @@ extern "C" int pkb_timing(pkb_ctx* ctx, double out_ms[4]) {
 }
 
 extern "C" long long pkb_launch_count(pkb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int pkb_mark(pkb_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return fail(PKB_EINVAL, "pkb_mark: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return 0;
+}
+
+extern "C" int pkb_elapsed_ms(pkb_ctx* ctx, int slot_a, int slot_b, double* ms) {
+    if (!ctx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return fail(PKB_EINVAL, "pkb_elapsed_ms: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->marks[slot_b]));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, ctx->marks[slot_a], ctx->marks[slot_b]));
+    *ms = f;
+    return 0;
+}
+
+extern "C" int pkb_profile_enable(pkb_ctx* ctx, int on) {
+    if (!ctx) return fail(PKB_EINVAL, "pkb_profile_enable: NULL context");
+    TRY(sync_check(ctx, "pkb_profile_enable"));
+    ctx->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int pkb_profile_reset(pkb_ctx* ctx) {
+    if (!ctx) return fail(PKB_EINVAL, "pkb_profile_reset: NULL context");
+    TRY(sync_check(ctx, "pkb_profile_reset"));
+    ctx->prof_acc.clear();
+    return 0;
+}
+
+extern "C" int pkb_profile_get(pkb_ctx* ctx, const char* kernel, long long* count, double* total_ms) {
+    if (!ctx || !kernel) return fail(PKB_EINVAL, "pkb_profile_get: NULL argument");
+    TRY(sync_check(ctx, "pkb_profile_get"));
+    auto it = ctx->prof_acc.find(kernel);
+    if (count) *count = it == ctx->prof_acc.end() ? 0 : it->second.first;
+    if (total_ms) *total_ms = it == ctx->prof_acc.end() ? 0.0 : it->second.second;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------
 // FFT plans

@@ -1,0 +1,287 @@
+"""Phase 2 (CalcSol / cuda_lib drop-in and the fused solve) against the
+reference's known-answer tests, its golden vectors and the oracle.  Runs on
+the emulated backend in the CPU container and on the real library with -m gpu."""
+import warnings
+
+import numpy as np
+import pytest
+from scipy import signal, sparse
+
+from oracle import cs_oracle as CO
+import helpers as H
+
+
+# ---- the reference's own tests (tests/test_CalcSol.py), restated -------------
+def _two_arrays():
+    A = np.outer(range(10), range(1, 11))
+    B = np.outer(range(4, -1, -1), range(8, -1, -2))
+    return A, B
+
+
+def _many_arrays():
+    out = []
+    for data in (np.outer(range(5), np.arange(.1, .6, .1)), np.outer(np.arange(0, 2.5, 0.5), np.ones(5)),
+                 np.outer(range(5, 0, -1), np.arange(.1, .6, .1)), np.outer(np.arange(1, 0, -.2), np.arange(0, 2.5, 0.5))):
+        M = np.zeros((55, 55))
+        M[25:30, 25:30] = data
+        out.append(M)
+    return out
+
+
+def test_fftconv2(pkb):
+    """tests/test_CalcSol.py:75-83."""
+    CS = pkb.CS
+    A, B = _two_arrays()
+    A0, B0 = A.copy(), B.copy()
+    A_hat = CS.fft2(sparse.coo_matrix(A), np.array(B.shape))
+    before, _ = CS.ifft2(A_hat, A.shape)
+    CS.fftconv2(A_hat, sparse.csr_matrix(B))
+    after, _ = CS.ifft2(A_hat, A.shape)
+    assert not np.all(before.toarray() == after.toarray())
+    assert np.all(B == B0) and np.all(A == A0)
+    assert np.allclose(after.toarray(), signal.convolve2d(A, B, 'same'), rtol=1e-12, atol=1e-10)
+
+
+def test_convolve_same(pkb):
+    """tests/test_CalcSol.py:85-98."""
+    CS = pkb.CS
+    A, B = _two_arrays()
+    A_hat = CS.fft2(sparse.coo_matrix(A), np.array([A.shape[0] + 6, A.shape[1] + 6]))
+    CS.fftconv2(A_hat, sparse.csr_matrix(B))
+    C, flag = CS.ifft2(A_hat, A.shape)
+    C = C.toarray()
+    assert not np.iscomplexobj(C)
+    assert np.allclose(C, signal.fftconvolve(A, B, 'same'), rtol=1e-12, atol=1e-10)
+
+
+def test_cuda_convolve(pkb):
+    """tests/test_CalcSol.py:100-113 (fp64, so without the float32 tolerance)."""
+    A, B = _two_arrays()
+    solver = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(A), np.array(A.shape) + 6)
+    solver.fftconv2(sparse.csr_matrix(B))
+    C = solver.get_cursol(A.shape)
+    assert sparse.isspmatrix_coo(C)
+    assert np.allclose(C.toarray(), signal.fftconvolve(A, B, 'same'), rtol=1e-12, atol=1e-10)
+
+
+def _abcd_reference():
+    A, B, C, D = _many_arrays()
+    B_hat = CO.fft2(sparse.coo_matrix(B), A.shape)
+    CO.fftconv2(B_hat, sparse.csr_matrix(C))
+    CO.fftconv2(B_hat, sparse.csr_matrix(D))
+    BCD = CO.ifft2(B_hat, B.shape)[0].toarray()
+    A_hat = CO.fft2(sparse.coo_matrix(A), A.shape)
+    for M in (B, C, D):
+        CO.fftconv2(A_hat, sparse.csr_matrix(M))
+    ABCD = CO.ifft2(A_hat, A.shape)[0].toarray()
+    return BCD, ABCD
+
+
+def test_back_solve(pkb):
+    """tests/test_CalcSol.py:115-139."""
+    CS = pkb.CS
+    A, B, C, D = _many_arrays()
+    C_hat = CS.fft2(sparse.coo_matrix(C), A.shape)
+    CS.fftconv2(C_hat, sparse.csr_matrix(D))
+    bck = CS.back_solve([sparse.csr_matrix(A), sparse.csr_matrix(B)], C_hat, A.shape)
+    BCD, ABCD = _abcd_reference()
+    assert np.allclose(bck[1].toarray(), BCD, rtol=1e-12, atol=1e-10)
+    assert np.allclose(bck[0].toarray(), ABCD, rtol=1e-12, atol=1e-10)
+
+
+def test_cuda_back_solve(pkb):
+    """tests/test_CalcSol.py:141-171 (fp64: tolerances 1e-4/1e-3 -> 1e-10)."""
+    A, B, C, D = _many_arrays()
+    solver = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(C), A.shape)
+    solver.fftconv2(sparse.csr_matrix(D))
+    bck = solver.back_solve([sparse.csr_matrix(A), sparse.csr_matrix(B)], A.shape)
+    BCD, ABCD = _abcd_reference()
+    # cuda_lib thresholds each cohort at 1e-8 (cuda_lib.py:195-197)
+    assert np.allclose(bck[1].toarray(), np.where(BCD > 1e-8, BCD, 0), rtol=1e-12, atol=1e-10)
+    assert np.allclose(bck[0].toarray(), np.where(ABCD > 1e-8, ABCD, 0), rtol=1e-12, atol=1e-10)
+
+
+def test_stencil_path_matches_fft_path(pkb):
+    """Small-support filters go through the direct shared-memory stencil; both
+    paths must agree with the oracle's circular convolution."""
+    rng = np.random.default_rng(3)
+    A = rng.random((40, 40))
+    B = rng.random((5, 5))
+    ref_hat = CO.fft2(sparse.coo_matrix(A), (21, 21))
+    CO.fftconv2(ref_hat, sparse.csr_matrix(B))
+    ref, _ = CO.ifft2_dense(ref_hat, A.shape)
+    for radius in (-1, 3):
+        pkb._lib.ctx().set_option('stencil_max_radius', radius)
+        solver = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(A), (21, 21))
+        solver.fftconv2(sparse.csr_matrix(B))
+        assert np.abs(solver.state() - ref).max() < 1e-12, radius
+        solver.close()
+    pkb._lib.ctx().set_option('stencil_max_radius', 3)
+
+
+def test_filter_limits(pkb):
+    A = np.ones((9, 9))
+    solver = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(A), (5, 5))
+    with pytest.raises(pkb._lib.PkbError):
+        solver.fftconv2(sparse.csr_matrix(np.ones((9, 9))))          # support radius 4 > max_shape//2 = 2
+    with pytest.raises(ValueError):
+        solver.fftconv2(sparse.csr_matrix(np.ones((1, 1))))
+    with pytest.raises(ValueError):
+        pkb.cuda_lib.CudaSolve(sparse.coo_matrix(np.ones((4, 5))), (3, 3))
+
+
+# ---- golden chains (reference get_solutions / get_populations) ---------------
+def _small_pmfs():
+    z = H.load('pm_small')
+    days = [int(d) for d in z['days']]
+    return z, days, [H.coo(z, 'd%d_pmf' % d) for d in days]
+
+
+def test_get_solutions_small(pkb):
+    z, days, pmfs = _small_pmfs()
+    g = H.load('chain_small')
+    n = 10
+    rr, D, ms = int(z['rad_res']), int(g['dom_len']), g['max_shape']
+    sol = [H.recentre(pmfs[0], rr)]
+    det = {'want_pre': True}
+    pkb.CS.get_solutions(sol, pmfs[:n], days[:n], n, D, ms, details=det)
+    assert len(sol) == n
+    assert det['flags'] == [bool(f) for f in g['prob_flags']]
+    for i in range(1, n):
+        H.assert_parity(det['pre'][i - 1], g['prob_pre'][i - 1], 'pre-threshold day %d' % i)
+        assert sparse.isspmatrix_coo(sol[i])
+        H.assert_thresholded_parity(sol[i].toarray(), H.coo(g, 'prob%d' % i).toarray(), what='prob day %d' % i)
+        assert abs(sol[i].sum() - 1) < H.MASS
+
+
+def test_get_populations_small(pkb):
+    z, days, pmfs = _small_pmfs()
+    g = H.load('chain_small')
+    n = 10
+    rr, D, ms = int(z['rad_res']), int(g['dom_len']), g['max_shape']
+    pop = pkb.CS.get_populations([H.recentre(pmfs[0], rr).tocsr()], pmfs[:n], days[:n], n, D, ms, 1, 130000,
+                                 lambda d: 1.0)
+    assert len(pop) == n
+    for i in range(n):
+        assert sparse.isspmatrix_csr(pop[i])
+        H.assert_thresholded_parity(pop[i].toarray(), H.coo(g, 'pop1_%d' % i).toarray(), what='pop1 day %d' % i)
+    r_dur = 3
+    r_spread = [H.recentre(pmfs[i], rr).tocsr() for i in range(r_dur)]
+    det = {}
+    pop = pkb.CS.get_populations(r_spread, pmfs[:n], days[:n], n, D, ms, r_dur, 40000, lambda d: 1. / r_dur, details=det)
+    for i in range(n):
+        H.assert_thresholded_parity(pop[i].toarray(), H.coo(g, 'pop3_%d' % i).toarray(), what='pop3 day %d' % i)
+
+
+# ---- fused solve (Run.main's hot path) ---------------------------------------
+def _fused_small(pkb, tmp_path, **kw):
+    z = H.load('pm_small')
+    wind, days = pkb.PM.get_wind_data(H.write_wind_file(tmp_path, 'kalbar'), int(z['interp']), '00:00')
+    n = 10
+    w = pkb.Run.stack_wind(wind, days)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        res = pkb.Run.solve(w, n, H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, int(z['n_periods']), float(z['rad_dist']),
+                            int(z['rad_res']), want_coo=True, want_dense=True, **kw)
+    return res
+
+
+def test_fused_solve_prob_small(pkb, tmp_path):
+    g = H.load('chain_small')
+    res = _fused_small(pkb, tmp_path, prob_model=True)
+    assert res.ndays == 10 and res.dom_len == int(g['dom_len']) and res.max_shape == int(g['max_shape'][0])
+    assert res.flags()[1:] == [bool(f) for f in g['prob_flags']]
+    sols = res.coo_list()
+    for i in range(10):
+        ref = H.coo(g, 'prob%d' % i).toarray()
+        H.assert_thresholded_parity(res.dense(i), ref, what='fused prob day %d' % i)
+        H.assert_thresholded_parity(sols[i].toarray(), ref, what='fused prob COO day %d' % i)
+        assert np.array_equal(sols[i].toarray(), res.dense(i))
+        assert abs(sols[i].sum() - 1) < H.MASS
+        # scipy.sparse.coo_matrix(dense) ordering: row-major
+        order = np.lexsort((sols[i].col, sols[i].row))
+        assert np.array_equal(order, np.arange(sols[i].nnz))
+    cells = np.array([[40, 40], [0, 0], [41, 39], [80, 80]])
+    smp = res.sample(cells)
+    for i in range(10):
+        assert np.array_equal(smp[i], res.dense(i)[cells[:, 0], cells[:, 1]])
+    res.close()
+
+
+def test_fused_solve_pop_small(pkb, tmp_path):
+    g = H.load('chain_small')
+    res = _fused_small(pkb, tmp_path, prob_model=False, r_dur=1, r_number=130000, r_dist=[1.0])
+    for i in range(10):
+        H.assert_thresholded_parity(res.dense(i), H.coo(g, 'pop1_%d' % i).toarray(), what='fused pop1 day %d' % i)
+    res.close()
+    res = _fused_small(pkb, tmp_path, prob_model=False, r_dur=3, r_number=40000, r_dist=[1. / 3] * 3)
+    for i in range(10):
+        H.assert_thresholded_parity(res.dense(i), H.coo(g, 'pop3_%d' % i).toarray(), what='fused pop3 day %d' % i)
+    res.close()
+
+
+def test_run_main_small(pkb, tmp_path, monkeypatch):
+    """Params / main drop-in: output file format of Run.py:490-516."""
+    monkeypatch.chdir(tmp_path)
+    prefix = H.write_wind_file(tmp_path, 'kalbar')
+    params = pkb.Run.Params()
+    params.cmd_line_chg(['--kalbar', 'site_name=' + prefix, 'interp_num=2', 'n_periods=2', 'domain_info=(2000.0,40)',
+                         'ndays=4', 'outfile=' + str(tmp_path / 'out' / 'run')])
+    assert params.get_model_params() == (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, 2000.0, 40)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        sol = pkb.Run.main(params)
+    g = H.load('chain_small')
+    assert len(sol) == 4
+    for i in range(4):
+        H.assert_thresholded_parity(sol[i].toarray(), H.coo(g, 'prob%d' % i).toarray(), what='main day %d' % i)
+    saved = np.load(str(tmp_path / 'out' / 'run.npz'))
+    assert list(saved['days']) == [13, 14, 15, 16]
+    csr = sparse.csr_matrix((saved['14_data'], saved['14_ind'], saved['14_indptr']), shape=(81, 81))
+    assert np.array_equal(csr.toarray(), sol[1].toarray())
+    params.cmd_line_chg(['--pop'])
+    assert params.PROB_MODEL is False and '_pop' in params.outfile
+
+
+# ---- full-size configurations (GPU only) --------------------------------------
+def _check_stats(g, prefix, sols, tol_nnz=3):
+    for i, s in enumerate(sols):
+        s = sparse.coo_matrix(s)
+        assert abs(s.nnz - g[prefix + '_nnz'][i]) <= tol_nnz, (prefix, i, s.nnz, g[prefix + '_nnz'][i])
+        scale = max(1.0, abs(g[prefix + '_sum'][i]))
+        assert abs(s.data.sum() - g[prefix + '_sum'][i]) < 1e-10 * scale
+        assert abs((s.data ** 2).sum() - g[prefix + '_sumsq'][i]) < 1e-10 * scale ** 2
+        assert abs(s.data.max() - g[prefix + '_max'][i]) < 1e-10 * scale
+        a = int(np.argmax(s.data))
+        assert [s.row[a], s.col[a]] == list(g[prefix + '_argmax'][i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('site', ['kalbar', 'carnarvon'])
+def test_full_configs(gpu, tmp_path, site):
+    """Configs 1-3: Kalbar / Carnarvon at default resolution, probability and
+    population model, against statistics and full rows of the reference output."""
+    g = H.load(site + '_full')
+    wind, days = gpu.PM.get_wind_data(H.write_wind_file(tmp_path, site), 30, H.SITES[site])
+    w = gpu.Run.stack_wind(wind, days)
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 30, 10000.0, 400)
+    res = gpu.Run.solve(w, len(days), *args, prob_model=True, want_coo=True, want_dense=True)
+    assert res.max_shape == int(g['max_shape'][0])
+    assert res.flags()[1:] == [bool(f) for f in g['prob_flags']]
+    sols = res.coo_list()
+    _check_stats(g, 'prob', sols)
+    for s in sols:
+        assert abs(s.sum() - 1) < H.MASS
+    last = res.dense(len(days) - 1)
+    H.assert_thresholded_parity(last[400, :], g['prob_last_row400'], what='last day row 400')
+    H.assert_thresholded_parity(last[:, 380], g['prob_last_col380'], what='last day col 380')
+    res.close()
+    r_dur, r_number, r_start = (1, 130000, None) if site == 'kalbar' else (5, 40000, 0.354)
+    res = gpu.Run.solve(w, len(days), *args, prob_model=False, r_dur=r_dur, r_number=r_number,
+                        r_dist=[1. / r_dur] * r_dur, r_start=r_start, want_coo=True, want_dense=True)
+    assert res.max_shape == int(g['max_shape_pop'][0])
+    _check_stats(g, 'pop', res.coo_list(), tol_nnz=6)
+    last = res.dense(len(days) - 1)
+    H.assert_thresholded_parity(last[400, :], g['pop_last_row400'], what='pop last day row 400', max_abs=1e-10)
+    H.assert_thresholded_parity(last[:, 380], g['pop_last_col380'], what='pop last day col 380', max_abs=1e-10)
+    res.close()
