@@ -52,9 +52,17 @@ struct StepMeta {   // one per emitted solution
 };
 
 // ---------------------------------------------------------------------------
+// Hermitian split of the transform of z = a + i b (a, b real rows) at bin k
+__device__ __forceinline__ void unpack_pair(const cplx* x, const FftPlan& plan, int N, int k, cplx& A, cplx& B) {
+    const cplx zk = x[swz(__ldg(&plan.perm[k]))];
+    const cplx zn = x[swz(__ldg(&plan.perm[k == 0 ? 0 : N - k]))];
+    A = cmake(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+    B = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
+}
+
 // grid = ceil(P/2), block = T, dyn smem = Npad complex
-__global__ void k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Yt,
-                           FftPlan plan) {
+__global__ void __launch_bounds__(256) k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
+                                                 cplx* __restrict__ Yt, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     const int lim = ctrl->trunc ? d.D : d.P;
@@ -64,20 +72,18 @@ __global__ void k_rows_fwd(const double* __restrict__ S, ChainDims d, const Chai
     const int tid = threadIdx.x, T = blockDim.x;
     const double* s0 = S + (size_t)r0 * d.ldS;
     const double* s1 = S + (size_t)(r1 >= 0 ? r1 : r0) * d.ldS;
-    for (int j = tid; j < plan.Npad; j += T) {
-        double re = 0.0, im = 0.0;
-        if (j < lim) { re = s0[j]; if (r1 >= 0) im = s1[j]; }
-        x[swz(j)] = cmake(re, im);
-    }
-    __syncthreads();
-    fft_dif(x, 1, 0, plan, tid, T);
+    auto ld = [&](int j) -> cplx {
+        if (j >= lim) return cmake(0.0, 0.0);
+        return cmake(s0[j], r1 >= 0 ? s1[j] : 0.0);
+    };
+    fft_dif_from(x, plan, tid, T, ld);
     const int N = d.N;
     for (int k = tid; k < d.Nc; k += T) {
-        const cplx zk = x[swz(__ldg(&plan.perm[k]))];
-        const cplx zn = x[swz(__ldg(&plan.perm[k == 0 ? 0 : N - k]))];
+        cplx A, B;
+        unpack_pair(x, plan, N, k, A, B);
         cplx* dst = Yt + (size_t)k * d.ldY + r0;
-        dst[0] = cmake(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
-        if (r1 >= 0) dst[1] = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
+        dst[0] = A;
+        if (r1 >= 0) dst[1] = B;
     }
 }
 
@@ -85,7 +91,8 @@ __global__ void k_rows_fwd(const double* __restrict__ S, ChainDims d, const Chai
 // K: dense (Wk x Wk) window centred on the release cell, support radius m.
 // Krt[kc][q], q = dy for dy in [0,m], q = dy + 2m+1 for dy in [-m,-1].
 // grid = m+1 (row pairs), block = T, dyn smem = Npad complex
-__global__ void k_kernel_rows(const double* __restrict__ K, int Wk, int m, ChainDims d, cplx* __restrict__ Krt, FftPlan plan) {
+__global__ void __launch_bounds__(256) k_kernel_rows(const double* __restrict__ K, int Wk, int m, ChainDims d, cplx* __restrict__ Krt,
+                                                    FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     const int nq = 2 * m + 1;
@@ -99,56 +106,156 @@ __global__ void k_kernel_rows(const double* __restrict__ K, int Wk, int m, Chain
     const double* k0 = K + (size_t)(ck + dy0) * Wk + ck;
     const double* k1 = K + (size_t)(ck + dy1) * Wk + ck;
     const int N = d.N;
-    for (int j = tid; j < plan.Npad; j += T) {
-        int dx = 0;
-        bool on = false;
-        if (j <= m) { dx = j; on = true; }
-        else if (j >= N - m && j < N) { dx = j - N; on = true; }
-        double re = 0.0, im = 0.0;
-        if (on) { re = k0[dx]; if (q1 >= 0) im = k1[dx]; }
-        x[swz(j)] = cmake(re, im);
-    }
-    __syncthreads();
-    fft_dif(x, 1, 0, plan, tid, T);
+    auto ld = [&](int j) -> cplx {
+        int dx;
+        if (j <= m) dx = j;
+        else if (j >= N - m) dx = j - N;
+        else return cmake(0.0, 0.0);
+        return cmake(k0[dx], q1 >= 0 ? k1[dx] : 0.0);
+    };
+    fft_dif_from(x, plan, tid, T, ld);
     for (int k = tid; k < d.Nc; k += T) {
-        const cplx zk = x[swz(__ldg(&plan.perm[k]))];
-        const cplx zn = x[swz(__ldg(&plan.perm[k == 0 ? 0 : N - k]))];
+        cplx A, B;
+        unpack_pair(x, plan, N, k, A, B);
         cplx* dst = Krt + (size_t)k * d.ldK;
-        dst[q0] = cmake(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
-        if (q1 >= 0) dst[q1] = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
+        dst[q0] = A;
+        if (q1 >= 0) dst[q1] = B;
     }
 }
 
 // ---------------------------------------------------------------------------
-// grid = Nc, block = T, dyn smem = 2*Npad complex.
-__global__ void k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
-                       const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, FftPlan plan) {
+// Last forward stage of a column, fused with the spectral multiply and the
+// first inverse stage.  Thread t owns the final-stage blocks t, t + T, ... (KB of
+// them, R_last points each): the filter's spectrum of those blocks stays in
+// registers (K) while the same shared-memory buffer is reused for the state
+// column, so the filter spectrum and the product never touch shared memory.
+#define PKB_COLS_KMAX 32   // KB * R_last <= 32 complex registers
+
+template <int RL, int KB>
+__device__ __forceinline__ void cols_final_filter(const cplx* x, int tid, int T, int nbl, cplx (&K)[PKB_COLS_KMAX]) {
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        const int j = tid + kb * T;
+        if (j < nbl) {
+            cplx v[RL];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) v[q] = x[swz(j * RL + q)];
+            dft<RL>(v);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) K[kb * RL + q] = v[q];
+        }
+    }
+}
+template <int RL, int KB>
+__device__ __forceinline__ void cols_final_state(cplx* x, int tid, int T, int nbl, const cplx (&K)[PKB_COLS_KMAX]) {
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        const int j = tid + kb * T;
+        if (j < nbl) {
+            cplx v[RL];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) v[q] = x[swz(j * RL + q)];
+            dft<RL>(v);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) v[q] = cmul_f(v[q], K[kb * RL + q]);
+            idft<RL>(v);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) x[swz(j * RL + q)] = v[q];
+        }
+    }
+}
+
+// the (R_last, KB) pairs the planner may pick (pkb200.cu: plan_cols)
+#define PKB_COLS_SWITCH(RL, KB, CALL)                                                                     \
+    switch ((RL) * 8 + (KB)) {                                                                            \
+        case 2 * 8 + 1: { CALL(2, 1); } break;  case 2 * 8 + 2: { CALL(2, 2); } break;                    \
+        case 2 * 8 + 3: { CALL(2, 3); } break;  case 2 * 8 + 4: { CALL(2, 4); } break;                    \
+        case 3 * 8 + 1: { CALL(3, 1); } break;  case 3 * 8 + 2: { CALL(3, 2); } break;                    \
+        case 3 * 8 + 3: { CALL(3, 3); } break;  case 3 * 8 + 4: { CALL(3, 4); } break;                    \
+        case 4 * 8 + 1: { CALL(4, 1); } break;  case 4 * 8 + 2: { CALL(4, 2); } break;                    \
+        case 4 * 8 + 3: { CALL(4, 3); } break;  case 4 * 8 + 4: { CALL(4, 4); } break;                    \
+        case 5 * 8 + 1: { CALL(5, 1); } break;  case 5 * 8 + 2: { CALL(5, 2); } break;                    \
+        case 5 * 8 + 3: { CALL(5, 3); } break;  case 5 * 8 + 4: { CALL(5, 4); } break;                    \
+        case 7 * 8 + 1: { CALL(7, 1); } break;  case 7 * 8 + 2: { CALL(7, 2); } break;                    \
+        case 7 * 8 + 3: { CALL(7, 3); } break;  case 7 * 8 + 4: { CALL(7, 4); } break;                    \
+        case 8 * 8 + 1: { CALL(8, 1); } break;  case 8 * 8 + 2: { CALL(8, 2); } break;                    \
+        case 8 * 8 + 3: { CALL(8, 3); } break;  case 8 * 8 + 4: { CALL(8, 4); } break;                    \
+        case 9 * 8 + 1: { CALL(9, 1); } break;  case 9 * 8 + 2: { CALL(9, 2); } break;                    \
+        default: { CALL(9, 3); } break;                                                                   \
+    }
+
+// grid = Nc, block = plan.cols_threads, dyn smem = Npad complex, 2 CTAs/SM.
+// Per spectral column: forward FFT of the filter column (inputs straight from
+// Krt, only 2m+1 of them non-zero), forward FFT of the state column (inputs
+// straight from Yt), product, inverse FFT, rows needed by the fold straight to Wt.
+__global__ void __maxnreg__(144) k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
+                                                const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, FftPlan plan) {
     PKB_DYN_SMEM(raw);
-    cplx* xs = reinterpret_cast<cplx*>(raw);
-    cplx* xk = xs + plan.Npad;
+    cplx* x = reinterpret_cast<cplx*>(raw);
     const int c = blockIdx.x;
     const int lim = ctrl->trunc ? d.D : d.P;
     const int tid = threadIdx.x, T = blockDim.x;
     const int N = d.N, nq = 2 * m + 1;
     const cplx* ycol = Yt + (size_t)c * d.ldY;
     const cplx* kcol = Krt + (size_t)c * d.ldK;
-    const cplx zero = cmake(0.0, 0.0);
-    for (int i = tid; i < plan.Npad; i += T) {
-        xs[swz(i)] = (i < lim) ? ycol[i] : zero;
-        cplx kv = zero;
-        if (i <= m) kv = kcol[i];
-        else if (i >= N - m && i < N) kv = kcol[i - (N - nq)];
-        xk[swz(i)] = kv;
-    }
-    __syncthreads();
-    fft_dif(xs, 2, plan.Npad, plan, tid, T);
-    for (int i = tid; i < plan.Npad; i += T) xs[i] = cmul(xs[i], xk[i]);   // same permuted/swizzled slot in both
-    __syncthreads();
-    fft_dit_inv(xs, 1, 0, plan, tid, T);
     cplx* wcol = Wt + (size_t)c * d.ldW;
+    const int L = plan.nstage, RL = plan_radix(plan, L - 1), nbl = N / RL, KB = plan.cols_kb;
     const int hi = d.P + m;   // rows [0, P+m) and [N-m, N) are needed by the fold
-    for (int i = tid; i < N; i += T)
-        if (i < hi || i >= N - m) wcol[i] = xs[swz(i)];
+    auto ld_filter = [&](int i) -> cplx {
+        if (i <= m) return kcol[i];
+        if (i >= N - m) return kcol[i - (N - nq)];
+        return cmake(0.0, 0.0);
+    };
+    auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[i] : cmake(0.0, 0.0); };
+    auto st_out = [&](int i, cplx v) {
+        if (i < hi || i >= N - m) wcol[i] = v;
+    };
+    cplx K[PKB_COLS_KMAX];
+    const int R0 = plan_radix(plan, 0);
+
+    // phase 0: filter column spectrum -> K registers; phase 1: state column
+    // forward, product, inverse (one copy of the stage code serves both)
+    for (int phase = 0; phase < 2; ++phase) {
+        auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
+        if (L == 1) {
+            for (int i = tid; i < N; i += T) x[swz(i)] = ld(i);
+        } else {
+            fft_stage_first_dispatch(x, R0, N, plan.tw, tid, T, ld);
+            int M = N / R0, off = 0;
+            for (int s = 1; s < L - 1; ++s) {
+                __syncthreads();
+                const int R = plan_radix(plan, s);
+                plan_stage_fwd(x, plan, R, M, off, tid, T);
+                off += stage_tw_size(R, M);
+                M /= R;
+            }
+        }
+        __syncthreads();
+        if (phase == 0) {
+#define PKB_CALL_(RR, KK) cols_final_filter<RR, KK>(x, tid, T, nbl, K)
+            PKB_COLS_SWITCH(RL, KB, PKB_CALL_)
+#undef PKB_CALL_
+        } else {
+#define PKB_CALL_(RR, KK) cols_final_state<RR, KK>(x, tid, T, nbl, K)
+            PKB_COLS_SWITCH(RL, KB, PKB_CALL_)
+#undef PKB_CALL_
+        }
+        __syncthreads();
+    }
+    if (L == 1) {
+        for (int i = tid; i < N; i += T) st_out(i, x[swz(i)]);
+    } else {
+        int M = RL;
+        int off = plan_tw_offset(plan, L - 2);
+        for (int s = L - 2; s >= 1; --s) {
+            const int R = plan_radix(plan, s);
+            M *= R;
+            off -= stage_tw_size(R, M);
+            plan_stage_inv(x, plan, R, M, off, tid, T);
+            __syncthreads();
+        }
+        fft_stage_last_inv_dispatch(x, R0, N, plan.tw, tid, T, st_out);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -168,7 +275,7 @@ __device__ __forceinline__ double fold_col(const cplx* x, int c, int P, int N, i
 }
 
 // grid = 2m + ceil((P-2m)/2), block = T, dyn smem = Npad complex
-__global__ void k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout, RowStats* __restrict__ rstat,
+__global__ void __launch_bounds__(256) k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout, RowStats* __restrict__ rstat,
                            double negval, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(double, red, 1024);
@@ -200,7 +307,7 @@ __global__ void k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, doub
         }
     }
     __syncthreads();
-    fft_dit_inv(x, 1, 0, plan, tid, T);
+    fft_dit_inv(x, plan, tid, T);
     const double scale = 1.0 / ((double)N * (double)N);
     const int nout = (fold || out_b < 0) ? 1 : 2;
     for (int o = 0; o < nout; ++o) {
@@ -361,7 +468,7 @@ __global__ void k_sample(const double* __restrict__ G, int D, const int* __restr
 
 // Single-vector transform through the shared-memory FFT (diagnostics).
 // grid = 1, block = T, dyn smem = Npad complex
-__global__ void k_fft_test(const cplx* __restrict__ in, cplx* __restrict__ out, int inverse, FftPlan plan) {
+__global__ void __launch_bounds__(256) k_fft_test(const cplx* __restrict__ in, cplx* __restrict__ out, int inverse, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     const int tid = threadIdx.x, T = blockDim.x, N = plan.N;
@@ -370,12 +477,12 @@ __global__ void k_fft_test(const cplx* __restrict__ in, cplx* __restrict__ out, 
     if (!inverse) {
         for (int i = tid; i < N; i += T) x[swz(i)] = in[i];
         __syncthreads();
-        fft_dif(x, 1, 0, plan, tid, T);
+        fft_dif(x, plan, tid, T);
         for (int k = tid; k < N; k += T) out[k] = x[swz(__ldg(&plan.perm[k]))];
     } else {
         for (int k = tid; k < N; k += T) x[swz(__ldg(&plan.perm[k]))] = in[k];
         __syncthreads();
-        fft_dit_inv(x, 1, 0, plan, tid, T);
+        fft_dit_inv(x, plan, tid, T);
         for (int i = tid; i < N; i += T) out[i] = x[swz(i)];
     }
 }

@@ -63,6 +63,7 @@ extern "C" int pkb_version(void) { return 100; }
 struct PlanRec {
     FftPlan plan;
     cplx* tw;
+    cplx* twm;
     int* perm;
 };
 
@@ -86,6 +87,7 @@ struct pkb_ctx {
     std::map<std::string, std::pair<long long, double> > prof_acc;
     int stencil_max_radius;
     int fft_threads;
+    int cols_variant;
     int max_smem;
 };
 
@@ -284,7 +286,8 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->device = device;
     ctx->launches = 0;
     ctx->stencil_max_radius = 3;
-    ctx->fft_threads = 256;
+    ctx->fft_threads = 128;
+    ctx->cols_variant = 1;
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
@@ -309,6 +312,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->plans) {
         cudaFree(kv.second.tw);
+        cudaFree(kv.second.twm);
         cudaFree(kv.second.perm);
     }
     for (auto& kv : ctx->dev_free)
@@ -342,6 +346,11 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
         const int t = (int)value;
         if (t < 32 || t > 512 || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, 512]");
         ctx->fft_threads = t;
+        return 0;
+    }
+    if (!strcmp(key, "cols_variant")) {
+        if (value != 1) return fail(PKB_EINVAL, "cols_variant must be 1");
+        ctx->cols_variant = (int)value;
         return 0;
     }
     return fail(PKB_EINVAL, "pkb_set_option: unknown key '%s'", key);
@@ -412,6 +421,28 @@ extern "C" int pkb_smooth_len(int n) {
     return n;
 }
 
+// fewest factors of n from the register radices (iterative deepening; n is 7-smooth)
+static const int kRadices[] = {12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+static bool factor_depth(int n, int depth, int max_r, std::vector<int>& out) {
+    if (n == 1) return true;
+    if (depth == 0) return false;
+    for (int r : kRadices) {
+        if (r > max_r || n % r) continue;
+        out.push_back(r);
+        if (factor_depth(n / r, depth - 1, r, out)) return true;
+        out.pop_back();
+    }
+    return false;
+}
+static bool min_factor(int n, std::vector<int>& out) {
+    if (n == 1) { out.assign(1, 2); return false; }
+    for (int depth = 1; depth <= PKB_FFT_MAX_STAGES; ++depth) {
+        out.clear();
+        if (factor_depth(n, depth, 12, out)) return true;
+    }
+    return false;
+}
+
 static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     auto it = ctx->plans.find(N);
     if (it != ctx->plans.end()) {
@@ -424,16 +455,49 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     p.N = N;
     p.Npad = (N + 63) / 64 * 64;
     p.nstage = 0;
-    int n = N;
-    // odd radices first (largest strides), powers of two last (unit strides)
-    const int odd[3] = {7, 5, 3};
-    for (int r : odd)
-        while (n % r == 0) { p.radix[p.nstage++] = r; n /= r; }
-    int l2 = 0;
-    while (n % 2 == 0) { ++l2; n /= 2; }
-    while (l2 >= 3 && l2 != 4) { p.radix[p.nstage++] = 8; l2 -= 3; }
-    while (l2 >= 2) { p.radix[p.nstage++] = 4; l2 -= 2; }
-    if (l2 == 1) p.radix[p.nstage++] = 2;
+    // fewest passes over shared memory: factor N into the fewest register
+    // radices; the last one (whose blocks stay in registers in k_cols) is the
+    // largest odd radix that keeps N / R_last threads per transform <= 512
+    std::vector<int> fac;
+    if (!min_factor(N, fac)) return fail(PKB_EINVAL, "FFT length %d cannot be factored into the supported radices", N);
+    std::sort(fac.begin(), fac.end(), [](int a, int b) { return a > b; });
+    // last radix: the largest odd one k_cols has a fused final stage for
+    // (conflict-free per-thread stride); else the largest even one
+    int last = -1;
+    for (size_t i = 0; i < fac.size() && last < 0; ++i)
+        if (fac[i] == 9 || fac[i] == 7 || fac[i] == 5 || fac[i] == 3) last = (int)i;
+    for (size_t i = 0; i < fac.size() && last < 0; ++i)
+        if (fac[i] == 8 || fac[i] == 4 || fac[i] == 2) last = (int)i;
+    if (last < 0) {
+        // only 6 / 10 / 12 present: split one of them so that a supported last radix exists
+        const int r = fac.back();
+        fac.pop_back();
+        fac.push_back(r / 2);
+        fac.push_back(2);
+        std::sort(fac.begin(), fac.end(), [](int a, int b) { return a > b; });
+        for (size_t i = 0; i < fac.size() && last < 0; ++i)
+            if (fac[i] == 9 || fac[i] == 7 || fac[i] == 5 || fac[i] == 3) last = (int)i;
+        for (size_t i = 0; i < fac.size() && last < 0; ++i)
+            if (fac[i] == 8 || fac[i] == 4 || fac[i] == 2) last = (int)i;
+    }
+    const int rl = fac[last];
+    fac.erase(fac.begin() + last);
+    fac.push_back(rl);
+    // k_cols geometry: KB final-stage blocks per thread, KB * R_last <= 32, threads <= 224
+    {
+        const int nbl = N / rl;
+        const int kbmax = std::min(4, 32 / rl);
+        int best_t = 0, best_kb = 0;
+        for (int kb = 1; kb <= kbmax; ++kb) {
+            int t = ((nbl + kb - 1) / kb + 31) / 32 * 32;
+            if (t > 224) continue;
+            if (!best_t || t * kb < best_t * best_kb) { best_t = t; best_kb = kb; }
+        }
+        if (!best_t) return fail(PKB_ELIMIT, "FFT length %d is too long for the column kernel (last radix %d)", N, rl);
+        p.cols_threads = best_t;
+        p.cols_kb = best_kb;
+    }
+    for (int r : fac) p.radix[p.nstage++] = r;
     if (p.nstage > PKB_FFT_MAX_STAGES) return fail(PKB_ELIMIT, "FFT length %d needs too many stages", N);
     std::vector<cplx> tw(N);
     for (int j = 0; j < N; ++j) {
@@ -451,6 +515,28 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         }
         perm[k] = pos;
     }
+    // inner-stage tables [q-1][k] (fft_smem.cuh: FftPlan::twm)
+    std::vector<cplx> twm;
+    p.rpack = 0;
+    {
+        int M = N;
+        for (int s = 0; s < p.nstage; ++s) {
+            const int R = p.radix[s], Ms = M / R;
+            p.rpack |= (unsigned long long)R << (4 * s);
+            if (s > 0 && s < p.nstage - 1) {
+                for (int q = 1; q < R; ++q)
+                    for (int k = 0; k < Ms; ++k) {
+                        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((long long)k * q % M) / (long double)M;
+                        twm.push_back(cmake((double)cosl(a), (double)sinl(a)));
+                    }
+            }
+            M = Ms;
+        }
+    }
+    if (twm.empty()) twm.push_back(cmake(1.0, 0.0));
+    CU(cudaMalloc((void**)&rec.twm, sizeof(cplx) * twm.size()));
+    CU(cudaMemcpy(rec.twm, twm.data(), sizeof(cplx) * twm.size(), cudaMemcpyHostToDevice));
+    p.twm = rec.twm;
     CU(cudaMalloc((void**)&rec.tw, sizeof(cplx) * N));
     CU(cudaMalloc((void**)&rec.perm, sizeof(int) * N));
     CU(cudaMemcpy(rec.tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice));
@@ -782,16 +868,16 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ChainDims& d = ch->d;
     d.D = D;
     d.P = D + mmax;                         // CalcSol.py:20-21 with max_shape = 2*mmax + 1
-    d.N = pkb_smooth_len(d.P + 2 * mmax);
+    d.N = pkb_smooth_len(std::max(2, d.P + 2 * mmax));
     d.Nc = d.N / 2 + 1;
     d.ldS = roundup(d.P, 16);
     d.ldY = roundup(d.P, 8);
     d.ldW = roundup(d.N, 8);
     d.ldK = roundup(2 * mmax + 1, 8);
     TRY(get_plan(ctx, d.N, &ch->plan));
-    if ((size_t)2 * ch->plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem)
+    if ((size_t)ch->plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem)
         return fail(PKB_ELIMIT, "torus side %d (domain %d + filter radius %d) exceeds the shared-memory FFT limit of %d points", d.N, D,
-                    mmax, (int)(ctx->max_smem / (2 * sizeof(cplx))));
+                    mmax, (int)(ctx->max_smem / sizeof(cplx)));
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
@@ -859,7 +945,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     const size_t sm1 = (size_t)ch->plan.Npad * sizeof(cplx);
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, m + 1, T, sm1, K, Wk, m, d, krt, ch->plan);
     LAUNCH(ctx, k_rows_fwd, (d.P + 1) / 2, T, sm1, src, d, src_ctrl, ch->Yt.p, ch->plan);
-    LAUNCH(ctx, k_cols, d.Nc, T, 2 * sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl, ch->Wt.p, ch->plan);
+    LAUNCH(ctx, k_cols, d.Nc, ch->plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl, ch->Wt.p, ch->plan);
     const int njobs = 2 * m + (d.P - 2 * m + 1) / 2;
     LAUNCH(ctx, k_rows_inv, njobs, T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan);
     return 0;

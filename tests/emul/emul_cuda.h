@@ -28,6 +28,7 @@
 #define __forceinline__ inline
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __align__(n) alignas(n)
 
 struct dim3 {
@@ -76,6 +77,7 @@ inline unsigned char* dyn_smem() { return tl_block->dyn; }
 #define __syncthreads() emu::sync()
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 static inline double atomicAdd(double* addr, double val) {
