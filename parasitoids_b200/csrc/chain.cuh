@@ -25,6 +25,23 @@
 #pragma once
 #include "fft_smem.cuh"
 
+// launch-bound knobs (tools/chainbench.cu builds variants with -D)
+#ifndef PKB_ROWS_T
+#define PKB_ROWS_T 256
+#endif
+#ifndef PKB_ROWS_B
+#define PKB_ROWS_B 1
+#endif
+#ifndef PKB_COLS_T
+#define PKB_COLS_T 224
+#endif
+#ifndef PKB_COLS_B
+#define PKB_COLS_B 1
+#endif
+#define PKB_ROWS_LB __launch_bounds__(PKB_ROWS_T, PKB_ROWS_B)
+#define PKB_COLS_LB __launch_bounds__(PKB_COLS_T, PKB_COLS_B)
+#define PKB_COLS_TMAX PKB_COLS_T
+
 namespace pkb {
 
 struct ChainDims {
@@ -61,7 +78,7 @@ __device__ __forceinline__ void unpack_pair(const cplx* x, const FftPlan& plan, 
 }
 
 // grid = ceil(P/2), block = T, dyn smem = Npad complex
-__global__ void __launch_bounds__(256) k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
+__global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
                                                  cplx* __restrict__ Yt, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
@@ -188,7 +205,7 @@ __device__ __forceinline__ void cols_final_state(cplx* x, int tid, int T, int nb
 // Per spectral column: forward FFT of the filter column (inputs straight from
 // Krt, only 2m+1 of them non-zero), forward FFT of the state column (inputs
 // straight from Yt), product, inverse FFT, rows needed by the fold straight to Wt.
-__global__ void __maxnreg__(144) k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
+__global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
                                                 const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
@@ -275,7 +292,7 @@ __device__ __forceinline__ double fold_col(const cplx* x, int c, int P, int N, i
 }
 
 // grid = 2m + ceil((P-2m)/2), block = T, dyn smem = Npad complex
-__global__ void __launch_bounds__(256) k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout, RowStats* __restrict__ rstat,
+__global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout, RowStats* __restrict__ rstat,
                            double negval, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(double, red, 1024);

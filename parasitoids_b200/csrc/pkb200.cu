@@ -269,6 +269,9 @@ static int opt_in_smem(F kern) {
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kern));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - (int)fa.sharedSizeBytes));
+    // always configure the full shared-memory carveout: left to its default the
+    // driver sized it for ONE resident CTA of k_cols (ncu: 102 KB config)
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
 
@@ -490,7 +493,7 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         int best_t = 0, best_kb = 0;
         for (int kb = 1; kb <= kbmax; ++kb) {
             int t = ((nbl + kb - 1) / kb + 31) / 32 * 32;
-            if (t > 224) continue;
+            if (t > PKB_COLS_TMAX) continue;
             if (!best_t || t * kb < best_t * best_kb) { best_t = t; best_kb = kb; }
         }
         if (!best_t) return fail(PKB_ELIMIT, "FFT length %d is too long for the column kernel (last radix %d)", N, rl);

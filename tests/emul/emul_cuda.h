@@ -109,7 +109,7 @@ typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
 static inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emulated failure" : "no error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
