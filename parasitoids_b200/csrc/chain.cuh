@@ -30,13 +30,13 @@
 #define PKB_ROWS_T 256
 #endif
 #ifndef PKB_ROWS_B
-#define PKB_ROWS_B 1
+#define PKB_ROWS_B 2
 #endif
 #ifndef PKB_COLS_T
-#define PKB_COLS_T 224
+#define PKB_COLS_T 256
 #endif
 #ifndef PKB_COLS_B
-#define PKB_COLS_B 1
+#define PKB_COLS_B 2
 #endif
 #define PKB_ROWS_LB __launch_bounds__(PKB_ROWS_T, PKB_ROWS_B)
 #define PKB_COLS_LB __launch_bounds__(PKB_COLS_T, PKB_COLS_B)
@@ -69,209 +69,204 @@ struct StepMeta {   // one per emitted solution
 };
 
 // ---------------------------------------------------------------------------
-// Hermitian split of the transform of z = a + i b (a, b real rows) at bin k
-__device__ __forceinline__ void unpack_pair(const cplx* x, const FftPlan& plan, int N, int k, cplx& A, cplx& B) {
-    const cplx zk = x[swz(__ldg(&plan.perm[k]))];
-    const cplx zn = x[swz(__ldg(&plan.perm[k == 0 ? 0 : N - k]))];
+// The three FFT kernels are PERSISTENT: the grid is (resident CTAs per SM) x
+// (SM count) and every CTA loops over its jobs, so the base twiddles are staged
+// in shared memory once per CTA and k_cols' per-CTA scratch stays L2 resident.
+//
+// Dynamic shared memory of each: fft_smem_bytes(plan) = (N + ntw) complex.
+
+// Hermitian split of the transform of z = a + i b (a, b real rows):
+//   A_k = (Z_k + conj(Z_{N-k})) / 2,  B_k = (Z_k - conj(Z_{N-k})) / (2i)
+__device__ __forceinline__ void hermitian_split(cplx zk, cplx zn, cplx& A, cplx& B) {
     A = cmake(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
     B = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
 }
 
-// grid = ceil(P/2), block = T, dyn smem = Npad complex
+#define PKB_UNPACK_U 4   // independent gathers in flight per thread in the pack / unpack loops
+
+// x holds the digit-reversed transform of two packed real rows; write their
+// half spectra transposed: dst[k * ld + 0] = A_k, dst[k * ld + 1] = B_k (B only if two).
+// dst and ld are even (32-byte aligned pairs).
+__device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan, int Nc, cplx* __restrict__ dst, size_t ld, bool two,
+                                             int tid, int T) {
+    for (int k0 = tid; k0 < Nc; k0 += PKB_UNPACK_U * T) {
+        int2 pr[PKB_UNPACK_U];
+#pragma unroll
+        for (int u = 0; u < PKB_UNPACK_U; ++u) {
+            const int k = k0 + u * T;
+            pr[u] = k < Nc ? __ldg(&plan.pair[k]) : make_int2(0, 0);
+        }
+        cplx zk[PKB_UNPACK_U], zn[PKB_UNPACK_U];
+#pragma unroll
+        for (int u = 0; u < PKB_UNPACK_U; ++u) {
+            zk[u] = x[pr[u].x];
+            zn[u] = x[pr[u].y];
+        }
+#pragma unroll
+        for (int u = 0; u < PKB_UNPACK_U; ++u) {
+            const int k = k0 + u * T;
+            if (k < Nc) {
+                cplx A, B;
+                hermitian_split(zk[u], zn[u], A, B);
+                cplx* o = dst + (size_t)k * ld;
+                if (two) st_pair(o, A, B);
+                else o[0] = A;
+            }
+        }
+    }
+}
+
+// grid = persistent, block = T
 __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
-                                                 cplx* __restrict__ Yt, FftPlan plan) {
+                                       cplx* __restrict__ Yt, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
-    const int lim = ctrl->trunc ? d.D : d.P;
-    const int r0 = 2 * blockIdx.x;
-    if (r0 >= lim) return;
-    const int r1 = (r0 + 1 < lim) ? r0 + 1 : -1;
+    cplx* tws = x + plan.N;
     const int tid = threadIdx.x, T = blockDim.x;
-    const double* s0 = S + (size_t)r0 * d.ldS;
-    const double* s1 = S + (size_t)(r1 >= 0 ? r1 : r0) * d.ldS;
-    auto ld = [&](int j) -> cplx {
-        if (j >= lim) return cmake(0.0, 0.0);
-        return cmake(s0[j], r1 >= 0 ? s1[j] : 0.0);
-    };
-    fft_dif_from(x, plan, tid, T, ld);
-    const int N = d.N;
-    for (int k = tid; k < d.Nc; k += T) {
-        cplx A, B;
-        unpack_pair(x, plan, N, k, A, B);
-        cplx* dst = Yt + (size_t)k * d.ldY + r0;
-        dst[0] = A;
-        if (r1 >= 0) dst[1] = B;
+    fft_load_twiddles(tws, plan, tid, T);
+    __syncthreads();
+    const int lim = ctrl->trunc ? d.D : d.P;
+    const int njobs = (lim + 1) / 2;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int r0 = 2 * job;
+        const bool two = r0 + 1 < lim;
+        const double* s0 = S + (size_t)r0 * d.ldS;
+        const double* s1 = s0 + (two ? d.ldS : 0);
+        auto ld = [&](int j) -> cplx {
+            if (j >= lim) return cmake(0.0, 0.0);
+            return cmake(s0[j], two ? s1[j] : 0.0);
+        };
+        fft_forward_from(x, tws, plan, tid, T, ld);
+        unpack_store(x, plan, d.Nc, Yt + r0, (size_t)d.ldY, two, tid, T);
+        __syncthreads();
     }
 }
 
 // Row spectra of the wrap-shifted kernel (CalcSol.py:58-64 on the N torus).
 // K: dense (Wk x Wk) window centred on the release cell, support radius m.
 // Krt[kc][q], q = dy for dy in [0,m], q = dy + 2m+1 for dy in [-m,-1].
-// grid = m+1 (row pairs), block = T, dyn smem = Npad complex
-__global__ void __launch_bounds__(256) k_kernel_rows(const double* __restrict__ K, int Wk, int m, ChainDims d, cplx* __restrict__ Krt,
-                                                    FftPlan plan) {
+// grid = persistent over the m+1 row pairs, block = T
+__global__ void PKB_ROWS_LB k_kernel_rows(const double* __restrict__ K, int Wk, int m, ChainDims d, cplx* __restrict__ Krt,
+                                          FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
-    const int nq = 2 * m + 1;
-    const int q0 = 2 * blockIdx.x;
-    if (q0 >= nq) return;
-    const int q1 = (q0 + 1 < nq) ? q0 + 1 : -1;
+    cplx* tws = x + plan.N;
     const int tid = threadIdx.x, T = blockDim.x;
+    fft_load_twiddles(tws, plan, tid, T);
+    __syncthreads();
+    const int nq = 2 * m + 1;
     const int ck = Wk / 2;
-    const int dy0 = q0 <= m ? q0 : q0 - nq;
-    const int dy1 = q1 < 0 ? 0 : (q1 <= m ? q1 : q1 - nq);
-    const double* k0 = K + (size_t)(ck + dy0) * Wk + ck;
-    const double* k1 = K + (size_t)(ck + dy1) * Wk + ck;
     const int N = d.N;
-    auto ld = [&](int j) -> cplx {
-        int dx;
-        if (j <= m) dx = j;
-        else if (j >= N - m) dx = j - N;
-        else return cmake(0.0, 0.0);
-        return cmake(k0[dx], q1 >= 0 ? k1[dx] : 0.0);
-    };
-    fft_dif_from(x, plan, tid, T, ld);
-    for (int k = tid; k < d.Nc; k += T) {
-        cplx A, B;
-        unpack_pair(x, plan, N, k, A, B);
-        cplx* dst = Krt + (size_t)k * d.ldK;
-        dst[q0] = A;
-        if (q1 >= 0) dst[q1] = B;
+    for (int job = blockIdx.x; 2 * job < nq; job += gridDim.x) {
+        const int q0 = 2 * job;
+        const bool two = q0 + 1 < nq;
+        const int dy0 = q0 <= m ? q0 : q0 - nq;
+        const int dy1 = !two ? 0 : (q0 + 1 <= m ? q0 + 1 : q0 + 1 - nq);
+        const double* k0 = K + (size_t)(ck + dy0) * Wk + ck;
+        const double* k1 = K + (size_t)(ck + dy1) * Wk + ck;
+        auto ld = [&](int j) -> cplx {
+            int dx;
+            if (j <= m) dx = j;
+            else if (j >= N - m) dx = j - N;
+            else return cmake(0.0, 0.0);
+            return cmake(k0[dx], two ? k1[dx] : 0.0);
+        };
+        fft_forward_from(x, tws, plan, tid, T, ld);
+        unpack_store(x, plan, d.Nc, Krt + q0, (size_t)d.ldK, two, tid, T);
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------
-// Last forward stage of a column, fused with the spectral multiply and the
-// first inverse stage.  Thread t owns the final-stage blocks t, t + T, ... (KB of
-// them, R_last points each): the filter's spectrum of those blocks stays in
-// registers (K) while the same shared-memory buffer is reused for the state
-// column, so the filter spectrum and the product never touch shared memory.
-#define PKB_COLS_KMAX 32   // KB * R_last <= 32 complex registers
-
-template <int RL, int KB>
-__device__ __forceinline__ void cols_final_filter(const cplx* x, int tid, int T, int nbl, cplx (&K)[PKB_COLS_KMAX]) {
+// Last forward stage of a column fused with the spectral product and the first
+// inverse stage.  Thread t owns the final-stage blocks t, t + T, ... (R_last
+// contiguous points each).  Phase 0 (filter column): DFT of each block, result
+// parked in the CTA's global scratch (L2 resident; each thread re-reads only
+// what it wrote, laid out [kb][q][tid] so that both directions coalesce).
+// Phase 1 (state column): DFT, product with the parked filter spectrum,
+// inverse DFT, back to the same shared-memory slots.
+template <int RL>
+__device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, int tid, int T, int nbl, int phase) {
+    int slot = tid;
+#pragma unroll 1
+    for (int j = tid; j < nbl; j += T, slot += RL * T) {
+        cplx v[RL];
+        if (phase == 0) {
 #pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-        const int j = tid + kb * T;
-        if (j < nbl) {
-            cplx v[RL];
-#pragma unroll
-            for (int q = 0; q < RL; ++q) v[q] = x[swz(j * RL + q)];
+            for (int q = 0; q < RL; ++q) v[q] = x[j * RL + q];
             dft<RL>(v);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) K[kb * RL + q] = v[q];
-        }
-    }
-}
-template <int RL, int KB>
-__device__ __forceinline__ void cols_final_state(cplx* x, int tid, int T, int nbl, const cplx (&K)[PKB_COLS_KMAX]) {
+            for (int q = 0; q < RL; ++q) scr[slot + q * T] = v[q];
+        } else {
+            cplx kf[RL];
 #pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-        const int j = tid + kb * T;
-        if (j < nbl) {
-            cplx v[RL];
+            for (int q = 0; q < RL; ++q) kf[q] = scr[slot + q * T];
 #pragma unroll
-            for (int q = 0; q < RL; ++q) v[q] = x[swz(j * RL + q)];
+            for (int q = 0; q < RL; ++q) v[q] = x[j * RL + q];
             dft<RL>(v);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) v[q] = cmul_f(v[q], K[kb * RL + q]);
+            for (int q = 0; q < RL; ++q) v[q] = cmul_f(v[q], kf[q]);
             idft<RL>(v);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) x[swz(j * RL + q)] = v[q];
+            for (int q = 0; q < RL; ++q) x[j * RL + q] = v[q];
         }
     }
 }
 
-// the (R_last, KB) pairs the planner may pick (pkb200.cu: plan_cols)
-#define PKB_COLS_SWITCH(RL, KB, CALL)                                                                     \
-    switch ((RL) * 8 + (KB)) {                                                                            \
-        case 2 * 8 + 1: { CALL(2, 1); } break;  case 2 * 8 + 2: { CALL(2, 2); } break;                    \
-        case 2 * 8 + 3: { CALL(2, 3); } break;  case 2 * 8 + 4: { CALL(2, 4); } break;                    \
-        case 3 * 8 + 1: { CALL(3, 1); } break;  case 3 * 8 + 2: { CALL(3, 2); } break;                    \
-        case 3 * 8 + 3: { CALL(3, 3); } break;  case 3 * 8 + 4: { CALL(3, 4); } break;                    \
-        case 4 * 8 + 1: { CALL(4, 1); } break;  case 4 * 8 + 2: { CALL(4, 2); } break;                    \
-        case 4 * 8 + 3: { CALL(4, 3); } break;  case 4 * 8 + 4: { CALL(4, 4); } break;                    \
-        case 5 * 8 + 1: { CALL(5, 1); } break;  case 5 * 8 + 2: { CALL(5, 2); } break;                    \
-        case 5 * 8 + 3: { CALL(5, 3); } break;  case 5 * 8 + 4: { CALL(5, 4); } break;                    \
-        case 7 * 8 + 1: { CALL(7, 1); } break;  case 7 * 8 + 2: { CALL(7, 2); } break;                    \
-        case 7 * 8 + 3: { CALL(7, 3); } break;  case 7 * 8 + 4: { CALL(7, 4); } break;                    \
-        case 8 * 8 + 1: { CALL(8, 1); } break;  case 8 * 8 + 2: { CALL(8, 2); } break;                    \
-        case 8 * 8 + 3: { CALL(8, 3); } break;  case 8 * 8 + 4: { CALL(8, 4); } break;                    \
-        case 9 * 8 + 1: { CALL(9, 1); } break;  case 9 * 8 + 2: { CALL(9, 2); } break;                    \
-        default: { CALL(9, 3); } break;                                                                   \
-    }
-
-// grid = Nc, block = plan.cols_threads, dyn smem = Npad complex, 2 CTAs/SM.
+// grid = persistent, block = plan.cols_threads.
+// scr: gridDim.x slices of plan.cols_kb * R_last * blockDim.x complex.
 // Per spectral column: forward FFT of the filter column (inputs straight from
 // Krt, only 2m+1 of them non-zero), forward FFT of the state column (inputs
 // straight from Yt), product, inverse FFT, rows needed by the fold straight to Wt.
 __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
-                                                const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, FftPlan plan) {
+                                   const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
-    const int c = blockIdx.x;
-    const int lim = ctrl->trunc ? d.D : d.P;
+    cplx* tws = x + plan.N;
     const int tid = threadIdx.x, T = blockDim.x;
+    fft_load_twiddles(tws, plan, tid, T);
+    __syncthreads();
+    const int lim = ctrl->trunc ? d.D : d.P;
     const int N = d.N, nq = 2 * m + 1;
-    const cplx* ycol = Yt + (size_t)c * d.ldY;
-    const cplx* kcol = Krt + (size_t)c * d.ldK;
-    cplx* wcol = Wt + (size_t)c * d.ldW;
-    const int L = plan.nstage, RL = plan_radix(plan, L - 1), nbl = N / RL, KB = plan.cols_kb;
+    const int L = plan.nstage, R0 = plan_radix(plan, 0), RL = plan_radix(plan, L - 1), nbl = N / RL;
     const int hi = d.P + m;   // rows [0, P+m) and [N-m, N) are needed by the fold
-    auto ld_filter = [&](int i) -> cplx {
-        if (i <= m) return kcol[i];
-        if (i >= N - m) return kcol[i - (N - nq)];
-        return cmake(0.0, 0.0);
-    };
-    auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[i] : cmake(0.0, 0.0); };
-    auto st_out = [&](int i, cplx v) {
-        if (i < hi || i >= N - m) wcol[i] = v;
-    };
-    cplx K[PKB_COLS_KMAX];
-    const int R0 = plan_radix(plan, 0);
-
-    // phase 0: filter column spectrum -> K registers; phase 1: state column
-    // forward, product, inverse (one copy of the stage code serves both)
-    for (int phase = 0; phase < 2; ++phase) {
-        auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
-        if (L == 1) {
-            for (int i = tid; i < N; i += T) x[swz(i)] = ld(i);
-        } else {
-            fft_stage_first_dispatch(x, R0, N, plan.tw, tid, T, ld);
-            int M = N / R0, off = 0;
-            for (int s = 1; s < L - 1; ++s) {
+    cplx* myscr = scr + (size_t)blockIdx.x * ((size_t)plan.cols_kb * RL * T);
+    const int off_last = plan.ntw - 1;   // table offset of the last stage (one entry)
+    for (int c = blockIdx.x; c < d.Nc; c += gridDim.x) {
+        const cplx* ycol = Yt + (size_t)c * d.ldY;
+        const cplx* kcol = Krt + (size_t)c * d.ldK;
+        cplx* wcol = Wt + (size_t)c * d.ldW;
+        auto ld_filter = [&](int i) -> cplx {
+            if (i <= m) return kcol[i];
+            if (i >= N - m) return kcol[i - (N - nq)];
+            return cmake(0.0, 0.0);
+        };
+        auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[i] : cmake(0.0, 0.0); };
+        auto st_out = [&](int i, cplx v) {
+            if (i < hi || i >= N - m) wcol[i] = v;
+        };
+        for (int phase = 0; phase < 2; ++phase) {
+            auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
+            if (L == 1) {
+                for (int i = tid; i < N; i += T) x[i] = ld(i);
                 __syncthreads();
-                const int R = plan_radix(plan, s);
-                plan_stage_fwd(x, plan, R, M, off, tid, T);
-                off += stage_tw_size(R, M);
-                M /= R;
+            } else {
+                fft_stage_dispatch<false>(R0, N, N, tws, tid, T, ld, SmemStore{x});
+                __syncthreads();
+                fft_fwd_stages(x, tws, plan, 1, L - 1, N / R0, N / R0, tid, T);
             }
-        }
-        __syncthreads();
-        if (phase == 0) {
-#define PKB_CALL_(RR, KK) cols_final_filter<RR, KK>(x, tid, T, nbl, K)
-            PKB_COLS_SWITCH(RL, KB, PKB_CALL_)
+#define PKB_CALL_(RR) cols_final<RR>(x, myscr, tid, T, nbl, phase)
+            PKB_RADIX_SWITCH(RL, PKB_CALL_)
 #undef PKB_CALL_
-        } else {
-#define PKB_CALL_(RR, KK) cols_final_state<RR, KK>(x, tid, T, nbl, K)
-            PKB_COLS_SWITCH(RL, KB, PKB_CALL_)
-#undef PKB_CALL_
-        }
-        __syncthreads();
-    }
-    if (L == 1) {
-        for (int i = tid; i < N; i += T) st_out(i, x[swz(i)]);
-    } else {
-        int M = RL;
-        int off = plan_tw_offset(plan, L - 2);
-        for (int s = L - 2; s >= 1; --s) {
-            const int R = plan_radix(plan, s);
-            M *= R;
-            off -= stage_tw_size(R, M);
-            plan_stage_inv(x, plan, R, M, off, tid, T);
             __syncthreads();
         }
-        fft_stage_last_inv_dispatch(x, R0, N, plan.tw, tid, T, st_out);
+        if (L == 1) {
+            for (int i = tid; i < N; i += T) st_out(i, x[i]);
+        } else {
+            fft_inv_stages(x, tws, plan, L - 1, 1, RL, off_last, tid, T);
+            fft_stage_dispatch<true>(R0, N, N, tws, tid, T, SmemLoad{x}, st_out);
+        }
+        __syncthreads();
     }
 }
 
@@ -283,76 +278,143 @@ struct RowStats {
     int pad_;
 };
 
-__device__ __forceinline__ double fold_col(const cplx* x, int c, int P, int N, int m, bool imag) {
-    cplx a = x[swz(c)];
-    double v = imag ? a.y : a.x;
-    if (c < m) { cplx b = x[swz(c + P)]; v += imag ? b.y : b.x; }
-    if (c >= P - m) { cplx b = x[swz(c - P + N)]; v += imag ? b.y : b.x; }
-    return v;
-}
-
-// grid = 2m + ceil((P-2m)/2), block = T, dyn smem = Npad complex
-__global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout, RowStats* __restrict__ rstat,
-                           double negval, FftPlan plan) {
-    PKB_DYN_SMEM(raw);
-    PKB_SHARED(double, red, 1024);
-    cplx* x = reinterpret_cast<cplx*>(raw);
-    const int P = d.P, N = d.N, D = d.D;
-    const int job = blockIdx.x;
-    int ra, rb, out_a, out_b;
-    bool fold;
-    if (job < m) { fold = true; out_a = job; out_b = -1; ra = job; rb = job + P; }
-    else if (job < 2 * m) { const int t = job - m; fold = true; out_a = P - m + t; out_b = -1; ra = out_a; rb = N - m + t; }
-    else {
-        const int r = m + 2 * (job - 2 * m);
-        fold = false; out_a = r; ra = r;
-        out_b = (r + 1 < P - m) ? r + 1 : -1; rb = out_b;
-    }
-    const int tid = threadIdx.x, T = blockDim.x;
-    const cplx zero = cmake(0.0, 0.0);
-    // zero the padding slots, then scatter the Hermitian pair Z = A + iB
-    for (int i = N + tid; i < plan.Npad; i += T) x[swz(i)] = zero;
-    for (int k = tid; k < d.Nc; k += T) {
-        const cplx a = Wt[(size_t)k * d.ldW + ra];
-        const cplx b = rb >= 0 ? Wt[(size_t)k * d.ldW + rb] : zero;
-        const int nk = N - k;
-        if (k == 0 || nk == k) {
-            x[swz(__ldg(&plan.perm[k]))] = cmake(a.x, b.x);        // self-conjugate bins are real
-        } else {
-            x[swz(__ldg(&plan.perm[k]))] = cmake(a.x - b.y, a.y + b.x);    // A + iB
-            x[swz(__ldg(&plan.perm[nk]))] = cmake(a.x + b.y, b.x - a.y);   // conj(A) + i conj(B)
+// Block reduction of 8 per-thread values: entries with (i & 3) == 0 or 3 by max, the
+// others by sum.  Result valid in thread i (i < 8) of warp 0.  red: 8 * 32 doubles.
+__device__ __forceinline__ double block_reduce8(double (&v)[8], double* red, int tid, int T) {
+    const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool ismax = (i & 3) == 0 || (i & 3) == 3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_down_sync(0xffffffffu, v[i], o);
+            v[i] = ismax ? fmax(v[i], t) : v[i] + t;
         }
+        if (lane == 0) red[i * 32 + wid] = v[i];
     }
     __syncthreads();
-    fft_dit_inv(x, plan, tid, T);
+    double r = 0.0;
+    if (tid < 8) {
+        const bool ismax = (tid & 3) == 0 || (tid & 3) == 3;
+        r = red[tid * 32];
+        for (int w = 1; w < nw; ++w) r = ismax ? fmax(r, red[tid * 32 + w]) : r + red[tid * 32 + w];
+    }
+    return r;
+}
+
+// number of inverse-row jobs: 2m fold jobs, an unpaired row m if m is odd, then row pairs
+__host__ __device__ __forceinline__ int rows_inv_jobs(int P, int m) {
+    if (P - 2 * m <= 0) return 2 * m;
+    const int lo = m + (m & 1);
+    const int rest = P - m - lo;
+    return 2 * m + (m & 1) + (rest > 0 ? (rest + 1) / 2 : 0);
+}
+
+// grid = persistent over rows_inv_jobs(P, m) jobs, block = T
+// A job is one inverse transform.  "Pair" jobs carry two interior output rows as
+// real and imaginary part; "fold" jobs carry the two linear-convolution rows that
+// fold onto the same output row mod P (their sum is re + im).
+__global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
+                                       RowStats* __restrict__ rstat, double negval, FftPlan plan) {
+    PKB_DYN_SMEM(raw);
+    PKB_SHARED(double, red, 264);
+    cplx* x = reinterpret_cast<cplx*>(raw);
+    cplx* tws = x + plan.N;
+    const int tid = threadIdx.x, T = blockDim.x;
+    fft_load_twiddles(tws, plan, tid, T);
+    __syncthreads();
+    const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
+    const int njobs = rows_inv_jobs(P, m);
     const double scale = 1.0 / ((double)N * (double)N);
-    const int nout = (fold || out_b < 0) ? 1 : 2;
-    for (int o = 0; o < nout; ++o) {
-        const int r = o ? out_b : out_a;
-        double* dst = Sout + (size_t)r * d.ldS;
-        double pmax = -INFINITY, ks = 0.0, vmn = INFINITY;
-        int kc = 0;
-        for (int c = tid; c < P; c += T) {
-            double v;
-            if (fold) v = fold_col(x, c, P, N, m, false) + fold_col(x, c, P, N, m, true);
-            else v = fold_col(x, c, P, N, m, o == 1);
-            v *= scale;
-            dst[c] = v;
-            if (r >= D || c >= D) pmax = fmax(pmax, v);
-            else {
-                vmn = fmin(vmn, v);
-                if (!(v < negval)) { ks += v; kc += 1; }
+    const cplx zero = cmake(0.0, 0.0);
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        int ra, rb, out_a, out_b;
+        bool fold;
+        if (job < m) { fold = true; out_a = job; out_b = -1; ra = job; rb = job + P; }
+        else if (job < 2 * m) { const int t = job - m; fold = true; out_a = P - m + t; out_b = -1; ra = out_a; rb = N - m + t; }
+        else {
+            // interior rows [m, P-m): pairs start on even rows (32-byte aligned loads)
+            int j = job - 2 * m, r;
+            if (m & 1) { r = j == 0 ? m : m + 1 + 2 * (j - 1); out_b = (j > 0 && r + 1 < P - m) ? r + 1 : -1; }
+            else { r = m + 2 * j; out_b = (r + 1 < P - m) ? r + 1 : -1; }
+            fold = false; out_a = r; ra = r; rb = out_b;
+        }
+        const bool pair_ld = !fold && out_b >= 0;
+        // scatter the Hermitian pair Z = A + iB into digit-reversed order
+        for (int k0 = tid; k0 < Nc; k0 += PKB_UNPACK_U * T) {
+            int2 pr[PKB_UNPACK_U];
+            cplx a[PKB_UNPACK_U], b[PKB_UNPACK_U];
+#pragma unroll
+            for (int u = 0; u < PKB_UNPACK_U; ++u) {
+                const int k = k0 + u * T;
+                if (k < Nc) {
+                    pr[u] = __ldg(&plan.pair[k]);
+                    const cplx* w = Wt + (size_t)k * d.ldW;
+                    if (pair_ld) ld_pair(w + ra, a[u], b[u]);
+                    else {
+                        a[u] = w[ra];
+                        b[u] = rb >= 0 ? w[rb] : zero;
+                    }
+                } else {
+                    pr[u] = make_int2(0, 0); a[u] = zero; b[u] = zero;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PKB_UNPACK_U; ++u) {
+                const int k = k0 + u * T;
+                if (k < Nc) {
+                    if (k == 0 || N - k == k) {
+                        x[pr[u].x] = cmake(a[u].x, b[u].x);        // self-conjugate bins are real
+                    } else {
+                        x[pr[u].x] = cmake(a[u].x - b[u].y, a[u].y + b[u].x);    // A + iB
+                        x[pr[u].y] = cmake(a[u].x + b[u].y, b[u].x - a[u].y);    // conj(A) + i conj(B)
+                    }
+                }
             }
         }
-        const double bpmax = block_max(pmax, red);
-        const double bks = block_sum(ks, red);
-        const double bkc = block_sum((double)kc, red);
-        const double bmn = block_min(vmn, red);
-        if (tid == 0) {
-            RowStats rs;
-            rs.padmax = bpmax; rs.ksum = bks; rs.vmin = bmn; rs.kcnt = (int)bkc; rs.pad_ = 0;
-            rstat[r] = rs;
+        __syncthreads();
+        fft_inverse_to(x, tws, plan, tid, T, SmemStore{x});
+        __syncthreads();
+        // fold the columns mod P in place (2m <= P, so the two ranges are disjoint)
+        for (int c = tid; c < m; c += T) {
+            x[c] = cadd(x[c], x[c + P]);
+            x[P - m + c] = cadd(x[P - m + c], x[N - m + c]);
         }
+        __syncthreads();
+        double* dst_a = Sout + (size_t)out_a * d.ldS;
+        double* dst_b = Sout + (size_t)(out_b >= 0 ? out_b : out_a) * d.ldS;
+        // st[0..3]: row a (pad max, kept sum, kept count, -min); st[4..7]: row b
+        double st[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
+        const bool pad_a = out_a >= D, pad_b = out_b >= D;
+        for (int c = tid; c < P; c += T) {
+            const cplx z = x[c];
+            const double va = (fold ? z.x + z.y : z.x) * scale;
+            dst_a[c] = va;
+            if (pad_a || c >= D) st[0] = fmax(st[0], va);
+            else {
+                st[3] = fmax(st[3], -va);
+                if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
+            }
+            if (out_b >= 0) {
+                const double vb = z.y * scale;
+                dst_b[c] = vb;
+                if (pad_b || c >= D) st[4] = fmax(st[4], vb);
+                else {
+                    st[7] = fmax(st[7], -vb);
+                    if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
+                }
+            }
+        }
+        const double r = block_reduce8(st, red, tid, T);
+        if (tid < 8) red[256 + tid] = r;
+        __syncthreads();
+        if (tid == 0 || (tid == 1 && out_b >= 0)) {
+            const double* q = red + 256 + 4 * tid;
+            RowStats rs;
+            rs.padmax = q[0]; rs.ksum = q[1]; rs.kcnt = (int)q[2]; rs.vmin = -q[3]; rs.pad_ = 0;
+            rstat[tid ? out_b : out_a] = rs;
+        }
+        __syncthreads();
     }
 }
 
@@ -484,23 +546,21 @@ __global__ void k_sample(const double* __restrict__ G, int D, const int* __restr
 }
 
 // Single-vector transform through the shared-memory FFT (diagnostics).
-// grid = 1, block = T, dyn smem = Npad complex
-__global__ void __launch_bounds__(256) k_fft_test(const cplx* __restrict__ in, cplx* __restrict__ out, int inverse, FftPlan plan) {
+// grid = 1, block = T, dyn smem = fft_smem_bytes(plan)
+__global__ void PKB_ROWS_LB k_fft_test(const cplx* __restrict__ in, cplx* __restrict__ out, int inverse, FftPlan plan) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
+    cplx* tws = x + plan.N;
     const int tid = threadIdx.x, T = blockDim.x, N = plan.N;
-    for (int i = tid; i < plan.Npad; i += T) x[swz(i)] = cmake(0.0, 0.0);
+    fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
     if (!inverse) {
-        for (int i = tid; i < N; i += T) x[swz(i)] = in[i];
-        __syncthreads();
-        fft_dif(x, plan, tid, T);
-        for (int k = tid; k < N; k += T) out[k] = x[swz(__ldg(&plan.perm[k]))];
+        fft_forward_from(x, tws, plan, tid, T, [&](int i) -> cplx { return in[i]; });
+        for (int k = tid; k < N; k += T) out[k] = x[__ldg(&plan.perm[k])];
     } else {
-        for (int k = tid; k < N; k += T) x[swz(__ldg(&plan.perm[k]))] = in[k];
+        for (int k = tid; k < N; k += T) x[__ldg(&plan.perm[k])] = in[k];
         __syncthreads();
-        fft_dit_inv(x, plan, tid, T);
-        for (int i = tid; i < N; i += T) out[i] = x[swz(i)];
+        fft_inverse_to(x, tws, plan, tid, T, [&](int i, cplx v) { out[i] = v; });
     }
 }
 

@@ -1,47 +1,41 @@
-// Shared-memory mixed-radix complex128 FFT with register radices up to 21, sm_100a.
+// Shared-memory mixed-radix complex128 FFT, register radices 2..12, sm_100a.
 //
 // Replaces the pocketfft/ducc complex FFT the reference reaches through
 // scipy.fftpack (CalcSol.py:24,35,65,99) and the Reikna FFT of cuda_lib.py:42-54.
 //
 // Formulation: decimation-in-frequency, in place, natural-order input ->
-// digit-reversed output (fft_dif); the inverse is the exact transpose,
-// decimation-in-time, digit-reversed input -> natural-order output (fft_dit_inv).
-// Pointwise products are taken in the permuted domain, so the convolution
-// pipeline never un-permutes; only the two-real-rows pack/unpack steps look up
-// `perm` to pair bin k with bin N-k.
+// digit-reversed output (forward); the inverse is the exact transpose,
+// decimation-in-time, digit-reversed input -> natural-order output.  Pointwise
+// products are taken in the permuted domain, so the convolution pipeline never
+// un-permutes; only the two-real-rows pack/unpack steps look up the `pair`
+// table to pair bin k with bin N-k.
 //
-// A length-N transform is 2-4 passes over shared memory; each pass is a
-// radix-R butterfly (R in {2..21}) held entirely in registers.  Composite
-// radices (9, 10, 12, 14, 15, 16, 18, 20, 21) are Cooley-Tukey products of the
-// base codelets with compile-time twiddles, so fp64 instruction count -- the
-// real ceiling of these kernels on B200 (36 TFLOP/s fp64) -- stays close to
-// the split-radix count while shared-memory traffic drops to 3 round trips.
-//
-// One transform lives in one shared-memory buffer of Npad = roundup(N, 64)
-// complex128, addressed through an XOR swizzle so that power-of-two strides do
-// not serialise on the 16-byte bank groups.
+// A length-N transform is 2-5 passes over ONE shared-memory buffer of N
+// complex128; each pass is a radix-R butterfly held entirely in registers.
+// The two scarce per-SM resources of these kernels are shared-memory bandwidth
+// (128 B/clk) and fp64 issue (64 lanes/clk): a pass moves 32 B per point
+// through shared memory, so twiddle factors are NOT read as tables -- each
+// butterfly reads one base twiddle w = exp(-2 pi i k / M) from a small
+// shared-memory table (sum of M_s / R_s entries over the stages, 7 KB at
+// N = 4704) and forms w^2 .. w^(R-1) by a depth-4 product tree.
 #pragma once
 #include "pkb_platform.cuh"
 #include "fft_tables.cuh"
 
 namespace pkb {
 
-#define PKB_FFT_MAX_STAGES 16
+#define PKB_FFT_MAX_STAGES 8
 
 struct FftPlan {
     int N;
-    int Npad;
     int nstage;
-    int radix[PKB_FFT_MAX_STAGES];
-    const cplx* tw;   // device: tw[j] = exp(-2 pi i j / N), j in [0, N)
-    const int* perm;  // device: perm[k] = position of frequency k after fft_dif
-    int cols_threads; // k_cols launch: threads per column and last-stage blocks per thread
-    int cols_kb;
-    // twm: twiddles of the inner stages s = 1 .. nstage-2, stage after stage; stage s
-    // holds (R_s - 1) * Ms_s entries laid out [q-1][k] = exp(-2 pi i k q / M_s), so that
-    // consecutive threads (consecutive k) read consecutive entries
-    const cplx* twm;
-    unsigned long long rpack;   // radix[s] in 4-bit fields (register-friendly copy of radix[])
+    int ntw;                    // entries of twb (all stages)
+    int cols_threads, cols_kb;  // k_cols geometry: threads per column, last-stage blocks per thread
+    unsigned long long rpack;   // radix of stage s in bits [4s, 4s+4)
+    // device tables
+    const cplx* twb;            // stage after stage: exp(-2 pi i k / M_s), k in [0, M_s / R_s)
+    const int2* pair;           // pair[k] = (pos(k), pos((N - k) mod N)), pos = index of bin k after the forward pass
+    const int* perm;            // perm[k] = pos(k)
 };
 
 __host__ __device__ __forceinline__ int plan_radix(const FftPlan& p, int s) { return (int)((p.rpack >> (4 * s)) & 15ull); }
@@ -50,11 +44,8 @@ __host__ __device__ __forceinline__ int plan_radix(const FftPlan& p, int s) { re
 __device__ __forceinline__ int fast_div(int j, int d, unsigned magic) { return d == 1 ? j : (int)__umulhi((unsigned)j, magic); }
 __device__ __forceinline__ unsigned div_magic(int d) { return d == 1 ? 0u : 0xFFFFFFFFu / (unsigned)d + 1u; }
 
-// Shared-memory index map.  Identity: every pass either has consecutive threads on
-// consecutive elements or (last stage) a per-thread stride equal to the last
-// radix, which the planner keeps odd whenever N has an odd factor -- both are
-// conflict-free for 16-byte accesses.
-__host__ __device__ __forceinline__ int swz(int i) { return i; }
+// shared-memory footprint (bytes) of one transform: data + base twiddles
+__host__ __device__ __forceinline__ size_t fft_smem_bytes(const FftPlan& p) { return (size_t)(p.N + p.ntw) * sizeof(cplx); }
 
 // ---- compile-time twiddles -----------------------------------------------------
 // a * exp(-2 pi i J / R)
@@ -178,12 +169,6 @@ template <> __device__ __forceinline__ void dft<8>(cplx (&v)[8]) { dft_ct<2, 4>(
 template <> __device__ __forceinline__ void dft<9>(cplx (&v)[9]) { dft_ct<3, 3>(v); }
 template <> __device__ __forceinline__ void dft<10>(cplx (&v)[10]) { dft_ct<2, 5>(v); }
 template <> __device__ __forceinline__ void dft<12>(cplx (&v)[12]) { dft_ct<4, 3>(v); }
-template <> __device__ __forceinline__ void dft<14>(cplx (&v)[14]) { dft_ct<2, 7>(v); }
-template <> __device__ __forceinline__ void dft<15>(cplx (&v)[15]) { dft_ct<3, 5>(v); }
-template <> __device__ __forceinline__ void dft<16>(cplx (&v)[16]) { dft_ct<4, 4>(v); }
-template <> __device__ __forceinline__ void dft<18>(cplx (&v)[18]) { dft_ct<2, 9>(v); }
-template <> __device__ __forceinline__ void dft<20>(cplx (&v)[20]) { dft_ct<4, 5>(v); }
-template <> __device__ __forceinline__ void dft<21>(cplx (&v)[21]) { dft_ct<3, 7>(v); }
 
 template <int R>
 __device__ __forceinline__ void swap_reim(cplx (&v)[R]) {
@@ -202,106 +187,70 @@ __device__ __forceinline__ void idft(cplx (&v)[R]) {
     swap_reim<R>(v);
 }
 
-// a * w, a * conj(w) with fused multiply-adds
+// a * w, a * conj(w), w * w with fused multiply-adds
 __device__ __forceinline__ cplx cmul_f(cplx a, cplx w) {
     return cmake(fma(-a.y, w.y, a.x * w.x), fma(a.x, w.y, a.y * w.x));
 }
 __device__ __forceinline__ cplx cmulc_f(cplx a, cplx w) {
     return cmake(fma(a.y, w.y, a.x * w.x), fma(-a.x, w.y, a.y * w.x));
 }
+__device__ __forceinline__ cplx csqr_f(cplx w) {
+    return cmake(fma(-w.y, w.y, w.x * w.x), (w.x + w.x) * w.y);
+}
 
-// ---- twiddles of the outermost stage (M = N) ------------------------------------
-// w_N^(k q), q = 1..R-1, from ONE table load per butterfly: successive products
-// w^q = w^(q-1) w.  The outermost stage would otherwise gather R-1 entries of a
-// table as large as the transform itself (75 KB at N = 4704); rounding grows to
-// ~R ulp on these factors, far below the 1e-10 parity bar.
+// v[q] *= w^q (forward) or conj(w)^q (inverse), q = 1 .. R-1, powers by a product
+// tree of depth <= 4 (w^q = w^ceil(q/2) * w^floor(q/2)); rounding of the
+// derived factors stays at a few ulp, far below the 1e-10 parity bar
 template <int R, bool CONJ>
-__device__ __forceinline__ void twiddle_chain(cplx (&v)[R], cplx w1) {
-    cplx w = w1;
+__device__ __forceinline__ void twiddle_apply(cplx (&v)[R], cplx w1) {
+    if constexpr (R > 1) {
+        cplx w[R];
+        w[0] = w1;   // unused
+        w[1] = w1;
 #pragma unroll
-    for (int q = 1; q < R; ++q) {
-        v[q] = CONJ ? cmulc_f(v[q], w) : cmul_f(v[q], w);
-        if (q + 1 < R) w = cmul_f(w, w1);
+        for (int q = 2; q < R; ++q) w[q] = (q & 1) ? cmul_f(w[q / 2 + 1], w[q / 2]) : csqr_f(w[q / 2]);
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = CONJ ? cmulc_f(v[q], w[q]) : cmul_f(v[q], w[q]);
     }
 }
 
-// ---- one in-place stage over a block decomposition of size M -----------------
+// ---- one stage over a block decomposition of size M -----------------------------
 // INV = false: DIF forward stage (DFT_R then twiddle on outputs)
 // INV = true : DIT inverse stage (conj twiddle on inputs then inverse DFT_R)
-// CHAIN: outermost stage (M == N), twiddles by twiddle_chain
-template <int R, bool INV, bool CHAIN>
-__device__ __forceinline__ void fft_stage(cplx* x, int N, int M, const cplx* __restrict__ tw, int tid, int T) {
-    // tw: CHAIN -> the length-N table (entry k); else this stage's [q-1][k] table
+// twk: this stage's base twiddles exp(-2 pi i k / M), k in [0, M/R)  (shared memory)
+// Inputs come from ld(index) and outputs go to st(index, value): shared memory for
+// inner stages, global memory for the first forward / last inverse stage.
+template <int R, bool INV, class Load, class Store>
+__device__ __forceinline__ void fft_stage(int N, int M, const cplx* twk, int tid, int T, Load ld, Store st) {
     const int Ms = M / R;
     const int nb = N / R;
     const unsigned magic = div_magic(Ms);
+#pragma unroll 1
     for (int j = tid; j < nb; j += T) {
         const int b = fast_div(j, Ms, magic);
         const int k = j - b * Ms;
         const int base = b * M + k;
-        cplx w1;
-        if (CHAIN) w1 = __ldg(&tw[k]);
         cplx v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = x[swz(base + q * Ms)];
-        if (!INV) {
-            dft<R>(v);
-            if (k > 0) {
-                if (CHAIN) twiddle_chain<R, false>(v, w1);
-                else {
-#pragma unroll
-                    for (int q = 1; q < R; ++q) v[q] = cmul_f(v[q], __ldg(&tw[(q - 1) * Ms + k]));
-                }
+        for (int q = 0; q < R; ++q) v[q] = ld(base + q * Ms);
+        if (Ms > 1) {
+            const cplx w1 = twk[k];
+            if (!INV) {
+                dft<R>(v);
+                twiddle_apply<R, false>(v, w1);
+            } else {
+                twiddle_apply<R, true>(v, w1);
+                idft<R>(v);
             }
         } else {
-            if (k > 0) {
-                if (CHAIN) twiddle_chain<R, true>(v, w1);
-                else {
-#pragma unroll
-                    for (int q = 1; q < R; ++q) v[q] = cmulc_f(v[q], __ldg(&tw[(q - 1) * Ms + k]));
-                }
-            }
-            idft<R>(v);
+            if (!INV) dft<R>(v);
+            else idft<R>(v);
         }
 #pragma unroll
-        for (int q = 0; q < R; ++q) x[swz(base + q * Ms)] = v[q];
+        for (int q = 0; q < R; ++q) st(base + q * Ms, v[q]);
     }
 }
 
-// First forward stage (M = N) with inputs supplied by `ld(index)` instead of
-// shared memory, and last inverse stage with outputs consumed by `st(index, value)`.
-template <int R, class Load>
-__device__ __forceinline__ void fft_stage_first(cplx* x, int N, const cplx* __restrict__ tw, int tid, int T, Load ld) {
-    const int Ms = N / R;
-    for (int k = tid; k < Ms; k += T) {
-        const cplx w1 = __ldg(&tw[k]);
-        cplx v[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = ld(k + q * Ms);
-        dft<R>(v);
-        if (k > 0) twiddle_chain<R, false>(v, w1);
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[swz(k + q * Ms)] = v[q];
-    }
-}
-template <int R, class Store>
-__device__ __forceinline__ void fft_stage_last_inv(const cplx* x, int N, const cplx* __restrict__ tw, int tid, int T, Store st) {
-    const int Ms = N / R;
-    for (int k = tid; k < Ms; k += T) {
-        const cplx w1 = __ldg(&tw[k]);
-        cplx v[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = x[swz(k + q * Ms)];
-        if (k > 0) twiddle_chain<R, true>(v, w1);
-        idft<R>(v);
-#pragma unroll
-        for (int q = 0; q < R; ++q) st(k + q * Ms, v[q]);
-    }
-}
-
-// radices a plan may use (pkb200.cu: kRadices); larger composite codelets exist
-// above but cost registers -- and therefore resident warps -- for no gain in
-// fp64 instruction count
 #define PKB_RADIX_SWITCH(R, CALL)            \
     switch (R) {                             \
         case 2: { CALL(2); } break;          \
@@ -316,102 +265,82 @@ __device__ __forceinline__ void fft_stage_last_inv(const cplx* x, int N, const c
         default: { CALL(12); } break;        \
     }
 
-// tw: the length-N table when M == N (outermost stage), else the stage's own table
-template <bool INV>
-__device__ __forceinline__ void fft_stage_dispatch(cplx* x, int R, int N, int M, const cplx* tw, int tid, int T) {
-    if (M == N) {
-#define PKB_CALL_(RR) fft_stage<RR, INV, true>(x, N, M, tw, tid, T)
-        PKB_RADIX_SWITCH(R, PKB_CALL_)
-#undef PKB_CALL_
-    } else {
-#define PKB_CALL_(RR) fft_stage<RR, INV, false>(x, N, M, tw, tid, T)
-        PKB_RADIX_SWITCH(R, PKB_CALL_)
-#undef PKB_CALL_
-    }
-}
-template <class Load>
-__device__ __forceinline__ void fft_stage_first_dispatch(cplx* x, int R, int N, const cplx* tw, int tid, int T, Load ld) {
-#define PKB_CALL_(RR) fft_stage_first<RR>(x, N, tw, tid, T, ld)
-    PKB_RADIX_SWITCH(R, PKB_CALL_)
-#undef PKB_CALL_
-}
-template <class Store>
-__device__ __forceinline__ void fft_stage_last_inv_dispatch(const cplx* x, int R, int N, const cplx* tw, int tid, int T, Store st) {
-#define PKB_CALL_(RR) fft_stage_last_inv<RR>(x, N, tw, tid, T, st)
+template <bool INV, class Load, class Store>
+__device__ __forceinline__ void fft_stage_dispatch(int R, int N, int M, const cplx* twk, int tid, int T, Load ld, Store st) {
+#define PKB_CALL_(RR) fft_stage<RR, INV>(N, M, twk, tid, T, ld, st)
     PKB_RADIX_SWITCH(R, PKB_CALL_)
 #undef PKB_CALL_
 }
 
-// Twiddle table of inner stage s, and the running offset bookkeeping
-__device__ __forceinline__ int stage_tw_size(int R, int M) { return (R - 1) * (M / R); }
+// shared-memory accessors of the in-place stages
+struct SmemLoad {
+    const cplx* x;
+    __device__ __forceinline__ cplx operator()(int i) const { return x[i]; }
+};
+struct SmemStore {
+    cplx* x;
+    __device__ __forceinline__ void operator()(int i, cplx v) const { x[i] = v; }
+};
 
-// One forward stage s (block size M) of a plan: outermost stage uses the chain
-// on plan.tw, inner stages their [q-1][k] table at twm + off.
-__device__ __forceinline__ void plan_stage_fwd(cplx* x, const FftPlan& p, int R, int M, int off, int tid, int T) {
-    fft_stage_dispatch<false>(x, R, p.N, M, M == p.N ? p.tw : p.twm + off, tid, T);
-}
-__device__ __forceinline__ void plan_stage_inv(cplx* x, const FftPlan& p, int R, int M, int off, int tid, int T) {
-    fft_stage_dispatch<true>(x, R, p.N, M, M == p.N ? p.tw : p.twm + off, tid, T);
+// copy the plan's base twiddles into shared memory (visible after the next barrier)
+__device__ __forceinline__ void fft_load_twiddles(cplx* tws, const FftPlan& p, int tid, int T) {
+    for (int i = tid; i < p.ntw; i += T) tws[i] = p.twb[i];
 }
 
-// Forward transform of one buffer filled (and synchronised) by the caller; returns synchronised.
-__device__ __forceinline__ void fft_dif(cplx* x, const FftPlan& p, int tid, int T) {
+// offset of stage s's base table inside twb
+__device__ __forceinline__ int fft_tw_offset(const FftPlan& p, int s) {
     int M = p.N, off = 0;
-    for (int s = 0; s < p.nstage; ++s) {
-        const int R = plan_radix(p, s);
-        plan_stage_fwd(x, p, R, M, off, tid, T);
-        if (s > 0) off += stage_tw_size(R, M);
-        M /= R;
-        __syncthreads();
-    }
-}
-
-// Forward transform of one buffer whose inputs come from `ld(index)` (global
-// memory): the first stage reads them straight into registers.  Returns synchronised.
-template <class Load>
-__device__ __forceinline__ void fft_dif_from(cplx* x, const FftPlan& p, int tid, int T, Load ld) {
-    const int R0 = plan_radix(p, 0);
-    if (p.nstage == 1) {
-        for (int i = tid; i < p.N; i += T) x[swz(i)] = ld(i);
-        __syncthreads();
-        plan_stage_fwd(x, p, R0, p.N, 0, tid, T);
-        __syncthreads();
-        return;
-    }
-    fft_stage_first_dispatch(x, R0, p.N, p.tw, tid, T, ld);
-    __syncthreads();
-    int M = p.N / R0, off = 0;
-    for (int s = 1; s < p.nstage; ++s) {
-        const int R = plan_radix(p, s);
-        plan_stage_fwd(x, p, R, M, off, tid, T);
-        off += stage_tw_size(R, M);
-        M /= R;
-        __syncthreads();
-    }
-}
-
-// total size of the inner-stage tables up to and including stage `upto`
-__device__ __forceinline__ int plan_tw_offset(const FftPlan& p, int upto) {
-    int M = p.N / plan_radix(p, 0), off = 0;
-    for (int s = 1; s <= upto; ++s) {
-        const int R = plan_radix(p, s);
-        off += stage_tw_size(R, M);
+    for (int t = 0; t < s; ++t) {
+        const int R = plan_radix(p, t);
+        off += M / R;
         M /= R;
     }
     return off;
 }
 
-// Unnormalised inverse (result = N * ifft).  Same synchronisation contract.
-__device__ __forceinline__ void fft_dit_inv(cplx* x, const FftPlan& p, int tid, int T) {
-    int M = 1;
-    int off = plan_tw_offset(p, p.nstage - 1);
-    for (int s = p.nstage - 1; s >= 0; --s) {
+// Forward stages s0 .. s1-1 in shared memory (x holds the data on entry; M0 / off0 are the
+// block size and table offset of stage s0).  A barrier follows every stage.
+__device__ __forceinline__ void fft_fwd_stages(cplx* x, const cplx* tws, const FftPlan& p, int s0, int s1, int M0, int off0, int tid, int T) {
+    int M = M0, off = off0;
+    for (int s = s0; s < s1; ++s) {
         const int R = plan_radix(p, s);
-        M *= R;
-        if (s > 0) off -= stage_tw_size(R, M);
-        plan_stage_inv(x, p, R, M, off, tid, T);
+        fft_stage_dispatch<false>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
+        off += M / R;
+        M /= R;
         __syncthreads();
     }
+}
+// Inverse stages s1-1 down to s0 in shared memory; M1 = block size AFTER stage s1-1 has been
+// undone is M1 * R_{s1-1}..., so pass the block size of stage s1 (1 when s1 == nstage) and the
+// table offset of stage s1.  A barrier follows every stage.
+__device__ __forceinline__ void fft_inv_stages(cplx* x, const cplx* tws, const FftPlan& p, int s1, int s0, int Mnext, int offnext, int tid, int T) {
+    int M = Mnext, off = offnext;
+    for (int s = s1 - 1; s >= s0; --s) {
+        const int R = plan_radix(p, s);
+        M *= R;
+        off -= M / R;
+        fft_stage_dispatch<true>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
+        __syncthreads();
+    }
+}
+
+// Whole forward transform with the first stage fed by ld(index) (global memory).
+// tws must be loaded; the caller guarantees x is free.  Returns synchronised.
+template <class Load>
+__device__ __forceinline__ void fft_forward_from(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Load ld) {
+    const int R0 = plan_radix(p, 0);
+    fft_stage_dispatch<false>(R0, p.N, p.N, tws, tid, T, ld, SmemStore{x});
+    __syncthreads();
+    fft_fwd_stages(x, tws, p, 1, p.nstage, p.N / R0, p.N / R0, tid, T);
+}
+
+// Whole inverse transform (unnormalised, result = N * ifft) with the last stage
+// delivering to st(index, value).  x holds digit-reversed input, synchronised.
+template <class Store>
+__device__ __forceinline__ void fft_inverse_to(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Store st) {
+    const int R0 = plan_radix(p, 0);
+    fft_inv_stages(x, tws, p, p.nstage, 1, 1, p.ntw, tid, T);
+    fft_stage_dispatch<true>(R0, p.N, p.N, tws, tid, T, SmemLoad{x}, st);
 }
 
 }  // namespace pkb

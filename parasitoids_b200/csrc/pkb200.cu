@@ -62,8 +62,8 @@ extern "C" int pkb_version(void) { return 100; }
 // ---------------------------------------------------------------------------
 struct PlanRec {
     FftPlan plan;
-    cplx* tw;
-    cplx* twm;
+    cplx* twb;
+    int2* pair;
     int* perm;
 };
 
@@ -87,7 +87,7 @@ struct pkb_ctx {
     std::map<std::string, std::pair<long long, double> > prof_acc;
     int stencil_max_radius;
     int fft_threads;
-    int cols_variant;
+    int sm_count;
     int max_smem;
 };
 
@@ -289,8 +289,8 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->device = device;
     ctx->launches = 0;
     ctx->stencil_max_radius = 3;
-    ctx->fft_threads = 128;
-    ctx->cols_variant = 1;
+    ctx->fft_threads = PKB_ROWS_T;
+    CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
@@ -314,8 +314,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->plans) {
-        cudaFree(kv.second.tw);
-        cudaFree(kv.second.twm);
+        cudaFree(kv.second.twb);
+        cudaFree(kv.second.pair);
         cudaFree(kv.second.perm);
     }
     for (auto& kv : ctx->dev_free)
@@ -347,13 +347,8 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fft_threads")) {
         const int t = (int)value;
-        if (t < 32 || t > 512 || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, 512]");
+        if (t < 32 || t > PKB_ROWS_T || (t & 31)) return fail(PKB_EINVAL, "fft_threads must be a multiple of 32 in [32, %d]", PKB_ROWS_T);
         ctx->fft_threads = t;
-        return 0;
-    }
-    if (!strcmp(key, "cols_variant")) {
-        if (value != 1) return fail(PKB_EINVAL, "cols_variant must be 1");
-        ctx->cols_variant = (int)value;
         return 0;
     }
     return fail(PKB_EINVAL, "pkb_set_option: unknown key '%s'", key);
@@ -456,95 +451,74 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     PlanRec rec;
     FftPlan& p = rec.plan;
     p.N = N;
-    p.Npad = (N + 63) / 64 * 64;
     p.nstage = 0;
-    // fewest passes over shared memory: factor N into the fewest register
-    // radices; the last one (whose blocks stay in registers in k_cols) is the
-    // largest odd radix that keeps N / R_last threads per transform <= 512
+    // fewest passes over shared memory: factor N into the fewest register radices
     std::vector<int> fac;
     if (!min_factor(N, fac)) return fail(PKB_EINVAL, "FFT length %d cannot be factored into the supported radices", N);
     std::sort(fac.begin(), fac.end(), [](int a, int b) { return a > b; });
-    // last radix: the largest odd one k_cols has a fused final stage for
-    // (conflict-free per-thread stride); else the largest even one
+    // last radix (k_cols keeps whole last-stage blocks per thread, stride R_last
+    // complex between threads): the largest odd one is bank-conflict free
     int last = -1;
     for (size_t i = 0; i < fac.size() && last < 0; ++i)
-        if (fac[i] == 9 || fac[i] == 7 || fac[i] == 5 || fac[i] == 3) last = (int)i;
-    for (size_t i = 0; i < fac.size() && last < 0; ++i)
-        if (fac[i] == 8 || fac[i] == 4 || fac[i] == 2) last = (int)i;
-    if (last < 0) {
-        // only 6 / 10 / 12 present: split one of them so that a supported last radix exists
-        const int r = fac.back();
-        fac.pop_back();
-        fac.push_back(r / 2);
-        fac.push_back(2);
-        std::sort(fac.begin(), fac.end(), [](int a, int b) { return a > b; });
-        for (size_t i = 0; i < fac.size() && last < 0; ++i)
-            if (fac[i] == 9 || fac[i] == 7 || fac[i] == 5 || fac[i] == 3) last = (int)i;
-        for (size_t i = 0; i < fac.size() && last < 0; ++i)
-            if (fac[i] == 8 || fac[i] == 4 || fac[i] == 2) last = (int)i;
-    }
+        if (fac[i] & 1) last = (int)i;
+    if (last < 0) last = 0;
     const int rl = fac[last];
     fac.erase(fac.begin() + last);
     fac.push_back(rl);
-    // k_cols geometry: KB final-stage blocks per thread, KB * R_last <= 32, threads <= 224
+    if ((int)fac.size() > PKB_FFT_MAX_STAGES) return fail(PKB_ELIMIT, "FFT length %d needs too many stages", N);
+    // k_cols geometry: threads per column and last-stage blocks per thread
     {
         const int nbl = N / rl;
-        const int kbmax = std::min(4, 32 / rl);
         int best_t = 0, best_kb = 0;
-        for (int kb = 1; kb <= kbmax; ++kb) {
-            int t = ((nbl + kb - 1) / kb + 31) / 32 * 32;
-            if (t > PKB_COLS_TMAX) continue;
-            if (!best_t || t * kb < best_t * best_kb) { best_t = t; best_kb = kb; }
+        for (int t = 32; t <= PKB_COLS_TMAX; t += 32) {
+            const int kb = (nbl + t - 1) / t;
+            // least idle work first, then the most threads
+            if (!best_t || t * kb < best_t * best_kb || (t * kb == best_t * best_kb && t > best_t)) { best_t = t; best_kb = kb; }
         }
-        if (!best_t) return fail(PKB_ELIMIT, "FFT length %d is too long for the column kernel (last radix %d)", N, rl);
         p.cols_threads = best_t;
         p.cols_kb = best_kb;
     }
-    for (int r : fac) p.radix[p.nstage++] = r;
-    if (p.nstage > PKB_FFT_MAX_STAGES) return fail(PKB_ELIMIT, "FFT length %d needs too many stages", N);
-    std::vector<cplx> tw(N);
-    for (int j = 0; j < N; ++j) {
-        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
-        tw[j] = cmake((double)cosl(a), (double)sinl(a));
+    p.rpack = 0;
+    for (int r : fac) {
+        p.rpack |= (unsigned long long)r << (4 * p.nstage);
+        ++p.nstage;
     }
+    // base twiddles of every stage: exp(-2 pi i k / M_s), k < M_s / R_s
+    const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+    std::vector<cplx> twb;
+    {
+        int M = N;
+        for (int s = 0; s < p.nstage; ++s) {
+            const int Ms = M / fac[s];
+            for (int k = 0; k < Ms; ++k) {
+                const long double a = -twopi * (long double)k / (long double)M;
+                twb.push_back(cmake((double)cosl(a), (double)sinl(a)));
+            }
+            M = Ms;
+        }
+    }
+    p.ntw = (int)twb.size();
     std::vector<int> perm(N);
     for (int k = 0; k < N; ++k) {
         int f = k, M = N, pos = 0;
         for (int s = 0; s < p.nstage; ++s) {
-            const int R = p.radix[s], Ms = M / R;
+            const int R = fac[s], Ms = M / R;
             pos += (f % R) * Ms;
             f /= R;
             M = Ms;
         }
         perm[k] = pos;
     }
-    // inner-stage tables [q-1][k] (fft_smem.cuh: FftPlan::twm)
-    std::vector<cplx> twm;
-    p.rpack = 0;
-    {
-        int M = N;
-        for (int s = 0; s < p.nstage; ++s) {
-            const int R = p.radix[s], Ms = M / R;
-            p.rpack |= (unsigned long long)R << (4 * s);
-            if (s > 0 && s < p.nstage - 1) {
-                for (int q = 1; q < R; ++q)
-                    for (int k = 0; k < Ms; ++k) {
-                        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((long long)k * q % M) / (long double)M;
-                        twm.push_back(cmake((double)cosl(a), (double)sinl(a)));
-                    }
-            }
-            M = Ms;
-        }
-    }
-    if (twm.empty()) twm.push_back(cmake(1.0, 0.0));
-    CU(cudaMalloc((void**)&rec.twm, sizeof(cplx) * twm.size()));
-    CU(cudaMemcpy(rec.twm, twm.data(), sizeof(cplx) * twm.size(), cudaMemcpyHostToDevice));
-    p.twm = rec.twm;
-    CU(cudaMalloc((void**)&rec.tw, sizeof(cplx) * N));
+    std::vector<int2> pair(N);
+    for (int k = 0; k < N; ++k) pair[k] = make_int2(perm[k], perm[(N - k) % N]);
+    CU(cudaMalloc((void**)&rec.twb, sizeof(cplx) * twb.size()));
+    CU(cudaMalloc((void**)&rec.pair, sizeof(int2) * N));
     CU(cudaMalloc((void**)&rec.perm, sizeof(int) * N));
-    CU(cudaMemcpy(rec.tw, tw.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(rec.twb, twb.data(), sizeof(cplx) * twb.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(rec.pair, pair.data(), sizeof(int2) * N, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(rec.perm, perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-    p.tw = rec.tw;
+    p.twb = rec.twb;
+    p.pair = rec.pair;
     p.perm = rec.perm;
     ctx->plans[N] = rec;
     *out = p;
@@ -557,12 +531,12 @@ extern "C" int pkb_debug_fft(pkb_ctx* ctx, int n, const double* in, double* out,
     CU(cudaSetDevice(ctx->device));
     FftPlan plan;
     TRY(get_plan(ctx, n, &plan));
-    if ((size_t)plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "pkb_debug_fft: n = %d exceeds shared memory", n);
+    if (fft_smem_bytes(plan) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "pkb_debug_fft: n = %d exceeds shared memory", n);
     DBuf<cplx> a, b;
     TRY(a.alloc(ctx, n));
     TRY(b.alloc(ctx, n));
     CU(cudaMemcpyAsync(a.p, in, sizeof(cplx) * n, cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_fft_test, 1, ctx->fft_threads, plan.Npad * sizeof(cplx), a.p, b.p, inverse, plan);
+    LAUNCH(ctx, k_fft_test, 1, ctx->fft_threads, fft_smem_bytes(plan), a.p, b.p, inverse, plan);
     CU(cudaMemcpyAsync(out, b.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx, "pkb_debug_fft");
 }
@@ -845,6 +819,8 @@ struct pkb_chain {
     DBuf<double> S[2];
     int cur;
     DBuf<cplx> Yt, Wt, Krt;
+    DBuf<cplx> cscr;        // k_cols: per-CTA parking space for the filter column spectrum
+    int grid_rows, grid_cols;
     DBuf<RowStats> rstat;
     DBuf<ChainCtrl> ctrl;   // [0] main state, [1 + j] cohort j
     DBuf<StepMeta> meta;    // same indexing
@@ -878,9 +854,22 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     d.ldW = roundup(d.N, 8);
     d.ldK = roundup(2 * mmax + 1, 8);
     TRY(get_plan(ctx, d.N, &ch->plan));
-    if ((size_t)ch->plan.Npad * sizeof(cplx) > (size_t)ctx->max_smem)
+    if (fft_smem_bytes(ch->plan) > (size_t)ctx->max_smem)
         return fail(PKB_ELIMIT, "torus side %d (domain %d + filter radius %d) exceeds the shared-memory FFT limit of %d points", d.N, D,
                     mmax, (int)(ctx->max_smem / sizeof(cplx)));
+    {
+        // resident CTAs per SM of the persistent kernels at this plan's footprint
+        const size_t sm1 = fft_smem_bytes(ch->plan);
+        int occ_r = 0, occ_i = 0, occ_c = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, ctx->fft_threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, ctx->fft_threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols, ch->plan.cols_threads, sm1));
+        if (occ_r < 1 || occ_i < 1 || occ_c < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
+        ch->grid_rows = std::min(occ_r, occ_i) * ctx->sm_count;
+        ch->grid_cols = occ_c * ctx->sm_count;
+        const int rl = plan_radix(ch->plan, ch->plan.nstage - 1);
+        TRY(ch->cscr.alloc(ctx, (size_t)ch->grid_cols * ch->plan.cols_kb * rl * ch->plan.cols_threads));
+    }
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
@@ -944,13 +933,15 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
         return 0;
     }
+    // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
     const int T = ctx->fft_threads;
-    const size_t sm1 = (size_t)ch->plan.Npad * sizeof(cplx);
-    if (!krt_ready) LAUNCH(ctx, k_kernel_rows, m + 1, T, sm1, K, Wk, m, d, krt, ch->plan);
-    LAUNCH(ctx, k_rows_fwd, (d.P + 1) / 2, T, sm1, src, d, src_ctrl, ch->Yt.p, ch->plan);
-    LAUNCH(ctx, k_cols, d.Nc, ch->plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl, ch->Wt.p, ch->plan);
-    const int njobs = 2 * m + (d.P - 2 * m + 1) / 2;
-    LAUNCH(ctx, k_rows_inv, njobs, T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan);
+    const size_t sm1 = fft_smem_bytes(ch->plan);
+    if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, ch->grid_rows), T, sm1, K, Wk, m, d, krt, ch->plan);
+    LAUNCH(ctx, k_rows_fwd, std::min((d.P + 1) / 2, ch->grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, ch->plan);
+    LAUNCH(ctx, k_cols, std::min(d.Nc, ch->grid_cols), ch->plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
+           ch->Wt.p, ch->cscr.p, ch->plan);
+    const int njobs = rows_inv_jobs(d.P, m);
+    LAUNCH(ctx, k_rows_inv, std::min(njobs, ch->grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan);
     return 0;
 }
 

@@ -37,6 +37,26 @@ __host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
 }
 __host__ __device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
 
+// Two adjacent complex128 values as ONE 256-bit global access (sm_100 LDG/STG.256):
+// the transposed spectra are written / read as 32-byte row pairs, one L1 wavefront
+// per pair instead of two.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_pair(cplx* p, cplx a, cplx b) {
+#if PKB_IS_EMUL
+    p[0] = a;
+    p[1] = b;
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+#endif
+}
+__device__ __forceinline__ void ld_pair(const cplx* p, cplx& a, cplx& b) {
+#if PKB_IS_EMUL
+    a = p[0];
+    b = p[1];
+#else
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#endif
+}
+
 // Block-wide reductions through shared memory (scratch >= blockDim.x doubles).
 // Fixed tree => deterministic results for a given launch shape.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {

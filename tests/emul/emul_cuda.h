@@ -98,6 +98,19 @@ static inline int atomicMax(int* addr, int val) {
     while (old < val && !__atomic_compare_exchange_n(addr, &old, val, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return old;
 }
+// warp shuffle for block-uniform call sites (every thread of the block calls it the
+// same number of times): exchange through a per-block buffer between two fiber barriers
+static inline double __shfl_down_sync(unsigned, double v, int delta) {
+    static thread_local double ex[1024];
+    const unsigned t = threadIdx.x;
+    ex[t] = v;
+    emu::sync();
+    const unsigned lane = t & 31u;
+    const double r = (lane + (unsigned)delta < 32u && t + (unsigned)delta < blockDim.x) ? ex[t + delta] : v;
+    emu::sync();
+    return r;
+}
+static inline int2 make_int2(int a, int b) { int2 r; r.x = a; r.y = b; return r; }
 static inline void sincospi(double x, double* s, double* c) {
     *s = sin(M_PI * x);
     *c = cos(M_PI * x);
@@ -138,5 +151,8 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) {
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
 struct cudaFuncAttributes { size_t sharedSizeBytes; };
 template <class F> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) { a->sharedSizeBytes = 0; return cudaSuccess; }

@@ -285,3 +285,19 @@ def test_full_configs(gpu, tmp_path, site):
     H.assert_thresholded_parity(last[400, :], g['pop_last_row400'], what='pop last day row 400', max_abs=1e-10)
     H.assert_thresholded_parity(last[:, 380], g['pop_last_col380'], what='pop last day col 380', max_abs=1e-10)
     res.close()
+
+
+@pytest.mark.parametrize('n', [2, 3, 5, 7, 8, 12, 14, 30, 49, 64, 210, 360, 1000, 1764, 4704])
+def test_debug_fft_matches_numpy(pkb, n):
+    """The shared-memory FFT behind every chain kernel against numpy's pocketfft
+    (the transform CalcSol.py:24,35 reaches through scipy.fftpack)."""
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    z = rng.normal(size=n) + 1j * rng.normal(size=n)
+    zin = np.ascontiguousarray(z.view(np.float64))
+    lib, ctx = pkb._lib.lib(), pkb._lib.ctx()
+    for inverse, ref in ((0, np.fft.fft(z)), (1, np.fft.ifft(z) * n)):
+        out = np.empty(2 * n)
+        pkb._lib.check(lib.pkb_debug_fft(ctx.h, n, pkb._lib.dptr(zin), pkb._lib.dptr(out), inverse))
+        got = out.view(np.complex128)
+        assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()) * np.log2(n + 1)
