@@ -249,6 +249,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        # launched bare: re-launch as one process per GPU (the driver does this itself)
+        os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+                                   '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29541'),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -279,34 +284,40 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from parasitoids_b200 import Run, _lib
+    from parasitoids_b200 import Run, _lib, batch
     ctx = _lib.ctx(local)
 
-    # one parameter proposal per rank (rank 0 = the defaults)
-    dparams = (DPARAMS[0] * (1 + 0.01 * rank), DPARAMS[1] * (1 - 0.005 * rank), DPARAMS[2])
-    model = (HPARAMS, dparams, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res)
+    # N > 1: a likelihood batch of one parameter proposal per rank (proposal 0 = the defaults),
+    # sharded by parasitoids_b200.batch.solve_batch; the only collective is its all_gather
+    model = (HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res)
+    proposals = np.tile(np.array([HPARAMS[1], HPARAMS[2], HPARAMS[3], HPARAMS[4], HPARAMS[5], HPARAMS[6], *DPARAMS, *DLPARAMS,
+                                  HPARAMS[0], N_PERIODS, MU_R]), (world, 1))
+    proposals[:, 6] *= 1 + 0.01 * np.arange(world)
+    proposals[:, 7] *= 1 - 0.005 * np.arange(world)
     wind_dev = torch.from_numpy(wind).cuda(local)
     wind_pinned = torch.from_numpy(wind).pin_memory()
     rng = np.random.default_rng(7)
     cells = rng.integers(0, 2 * rad_res + 1, (1024, 2)).astype(np.int32)
-    gather_buf = [torch.empty((ndays, cells.shape[0]), dtype=torch.float64, device='cuda') for _ in range(world)] if world > 1 else None
+
+    class _Info(object):
+        pass
 
     def step_device():
-        res = Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
-                        wind_shape=wind.shape, device=local)
         if world > 1:
-            mine = torch.from_numpy(res.sample(cells)).cuda(local)
-            dist.all_gather(gather_buf, mine)
-        return res
+            batch.solve_batch(None, proposals, cells, ndays, rad_dist, rad_res, prob_model=True, device=local,
+                              wind_device_ptr=wind_dev.data_ptr(), wind_shape=wind.shape)
+            return None
+        return Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
+                         wind_shape=wind.shape, device=local)
 
     def step_e2e():
+        if world > 1:
+            # host wind in, sampled cells of every proposal out (what the likelihood consumes)
+            out = batch.solve_batch(wind_pinned.numpy(), proposals, cells, ndays, rad_dist, rad_res, prob_model=True, device=local)
+            return None, out.size // 2        # counted below as 16 bytes per entry
         res = Run.solve(wind_pinned.numpy(), ndays, *model, want_coo=True, device=local)
         off, rows, cols, vals = res.coo_arrays()
-        nnz = int(off[-1])
-        if world > 1:
-            # the likelihood only needs the sampled cells from every proposal
-            pass
-        return res, nnz
+        return res, int(off[-1])
 
     def barrier():
         if world > 1:
@@ -315,8 +326,17 @@ def main():
         ctx.sync()
 
     # ---- device-resident measurement -------------------------------------------
+    def close(r):
+        if r is not None:
+            r.close()
+
+    # geometry of the workload (one untimed solve on every rank)
+    r = Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
+                  wind_shape=wind.shape, device=local)
+    info = (r.P, r.N, r.dom_len, r.flags(), r.radii())
+    r.close()
     for _ in range(args.warmup):
-        step_device().close()
+        close(step_device())
     barrier()
     ctx.profile_reset()
     ctx.profile(True)
@@ -327,11 +347,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     ctx.mark(0)
-    info = None
     for _ in range(args.steps):
-        res = step_device()
-        info = (res.P, res.N, res.dom_len, res.flags(), res.radii())
-        res.close()
+        close(step_device())
     ctx.mark(1)
     barrier()
     t1 = time.perf_counter()
@@ -387,7 +404,7 @@ def main():
     # ---- end to end through the public API, host buffers -------------------------
     for _ in range(max(1, min(args.warmup, 2))):
         r, _ = step_e2e()
-        r.close()
+        close(r)
     barrier()
     ctx.mark(2)
     te0 = time.perf_counter()
@@ -395,7 +412,7 @@ def main():
     for _ in range(args.steps):
         r, nnz = step_e2e()
         nnz_tot += nnz
-        r.close()
+        close(r)
     ctx.mark(3)
     barrier()
     e_wall = (time.perf_counter() - te0) * 1000.0
@@ -404,9 +421,11 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_ms = float(te[0])
     e2e = {'value': world * ndays * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
-           'h2d_bytes_per_step': int(wind.nbytes), 'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
+           'h2d_bytes_per_step': int(wind.nbytes) * world, 'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
            'ms_per_step': e_ms / args.steps, 'timer': 'host wall clock between device synchronisations',
-           'api': 'parasitoids_b200.Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}
+           'api': ('parasitoids_b200.batch.solve_batch: wind from pinned host memory on every rank, sampled cells of all proposals '
+                   'all-gathered and copied to host') if world > 1 else
+                  'parasitoids_b200.Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}
 
     if rank == 0:
         line = {'metric': 'simulated days/sec (fp64)', 'value': value, 'unit': 'days/s', 'n_gpus': world, 'steps': args.steps,
@@ -414,7 +433,7 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': P, 'fft_len': N,
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
-                           'parallelism': 'one parameter proposal per GPU, NCCL all_gather of 1024 sampled cells x days' if world > 1 else 'single solve',
+                           'parallelism': 'likelihood batch of %d proposals, one per GPU (batch.solve_batch), one NCCL all_gather of 1024 sampled cells x days per step' % world if world > 1 else 'single solve',
                            'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'roofline_chain': roofline_chain}

@@ -1,0 +1,96 @@
+"""Batched likelihood path: many independent parameter proposals, each a
+complete forward solve, sharded over the GPUs of one box.
+
+The reference evaluates ONE proposal at a time: PyMC's AdaptiveMetropolis
+writes the 15 block variables into ``Params`` and calls ``pop_model``
+(Bayes_Run.py:186-196, 204-336), which runs ``prob_mass`` for every day and
+then ``get_populations``; the likelihood only reads the model at the sample
+cells (Bayes_funcs.py:58-74, 167-173).  A batch of B proposals is therefore B
+independent units of work: they are partitioned over the ranks with no
+data-path collective, every rank solves its share on its own GPU, and the
+sampled-cell values -- the only thing the likelihood needs from every proposal
+-- are exchanged with ONE all_gather (NCCL over NVLink when the process group
+is NCCL; the CPU tests use gloo).
+"""
+import numpy as np
+
+from . import Run
+
+# order of the block-updated variables (Bayes_Run.py:186-187, 218-231)
+PROPOSAL_FIELDS = ('g_aw', 'g_bw', 'f_a1', 'f_b1', 'f_a2', 'f_b2', 'sig_x', 'sig_y', 'corr',
+                   'sig_x_l', 'sig_y_l', 'corr_l', 'lam', 'n_periods', 'mu_r')
+
+
+def unpack_proposal(p):
+    """15 block variables -> (hparams, Dparams, Dlparams, mu_r, n_periods) in the
+    argument order of ``prob_mass`` (Run.py:374-379, Bayes_Run.py:218-231)."""
+    p = np.asarray(p, dtype=float).ravel()
+    if p.size != len(PROPOSAL_FIELDS):
+        raise ValueError('a proposal has {} entries, got {}'.format(len(PROPOSAL_FIELDS), p.size))
+    hparams = (p[12], p[0], p[1], p[2], p[3], p[4], p[5])
+    return hparams, tuple(p[6:9]), tuple(p[9:12]), float(p[14]), int(round(p[13]))
+
+
+def shard(n_items, world, rank):
+    """Indices of the items rank ``rank`` of ``world`` owns: contiguous blocks,
+    the first ``n_items % world`` ranks take one extra item."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError('bad rank {} of {}'.format(rank, world))
+    base, extra = divmod(int(n_items), world)
+    lo = rank * base + min(rank, extra)
+    return list(range(lo, lo + base + (1 if rank < extra else 0)))
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return None
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=False, r_dur=1, r_number=1.0,
+                r_dist=None, r_start=None, device=None, group=None, wind_device_ptr=None, wind_shape=None):
+    """Solve every proposal and return the model at ``cells`` for all of them.
+
+    wind:       (nd_wind, periods, 3) consecutive days (``Run.stack_wind``), shared by all proposals
+    proposals:  (B, 15) array in ``PROPOSAL_FIELDS`` order
+    cells:      (K, 2) int (row, col) sample cells of the domain
+    returns     (B, ndays, K) float64, identical on every rank
+
+    With an initialised ``torch.distributed`` process group the proposals are
+    sharded over the ranks (``shard``) and the results all-gathered; without
+    one this is a plain loop on one GPU."""
+    proposals = np.asarray(proposals, dtype=float).reshape(-1, len(PROPOSAL_FIELDS))
+    cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
+    B, K = proposals.shape[0], cells.shape[0]
+    dist = _dist()
+    world = dist.get_world_size(group) if dist else 1
+    rank = dist.get_rank(group) if dist else 0
+    mine = shard(B, world, rank)
+    per = -(-B // world)                      # padded shard length
+    local = np.zeros((per, ndays, K))
+    for slot, b in enumerate(mine):
+        hp, dp, dl, mu_r, n_periods = unpack_proposal(proposals[b])
+        res = Run.solve(wind, ndays, hp, dp, dl, mu_r, n_periods, rad_dist, rad_res, prob_model=prob_model, r_dur=r_dur,
+                        r_number=r_number, r_dist=r_dist, r_start=r_start, want_coo=False, keep_device=True,
+                        wind_device_ptr=wind_device_ptr, wind_shape=wind_shape, device=device)
+        try:
+            local[slot] = res.sample(cells)
+        finally:
+            res.close()
+    if world == 1:
+        return local[:B]
+    import torch
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(local)
+    if backend == 'nccl':
+        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    out = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)       # concatenated along dim 0 (gloo and nccl both accept this form)
+    out = out.cpu().numpy().reshape((world, per) + tuple(t.shape[1:]))
+    full = np.empty((B, ndays, K))
+    for r in range(world):
+        idx = shard(B, world, r)
+        full[idx] = out[r, :len(idx)]
+    return full
