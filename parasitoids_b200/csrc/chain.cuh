@@ -50,10 +50,29 @@ struct ChainDims {
     int N;      // FFT torus side, 7-smooth, >= P + 2*mmax
     int Nc;     // N/2 + 1 spectral columns kept
     int ldS;    // leading dimension (doubles) of real states
-    int ldY;    // leading dimension (complex) of Yt  (>= P)
-    int ldW;    // leading dimension (complex) of Wt  (>= N)
-    int ldK;    // leading dimension (complex) of kernel row spectra (>= 2*mmax+1)
+    int ldY;    // row slots per column tile of Yt  (>= P)
+    int ldW;    // row slots per column tile of Wt  (>= N)
+    int ldK;    // row slots per column tile of the kernel row spectra (>= 2*mmax+1)
 };
+
+// Layout of the transposed spectra Yt / Wt / Krt: spectral columns are grouped in
+// tiles of PKB_CB; element (column k, row r) lives at ((k / CB) * ld + r) * CB + k % CB.
+// The row kernels (which own a row pair and sweep over k) then touch CB * 16 B
+// contiguous bytes per row and tile -- whole 128-byte lines at CB = 8, with the two
+// rows of a pair adjacent -- instead of one 32-byte sector every ld * 16 B, which
+// HBM serves at a fraction of its streaming rate.  The column kernel (which owns a
+// column and sweeps over r) walks consecutive lines, one 16-byte element per line;
+// neighbouring columns are in flight on neighbouring CTAs, so lines fill in L2.
+#ifndef PKB_CB
+#define PKB_CB 4
+#endif
+static_assert(PKB_CB == 2 || PKB_CB == 4 || PKB_CB == 8, "PKB_CB must be 2, 4 or 8");
+__host__ __device__ __forceinline__ size_t spec_index(int k, int r, int ld) {
+    return ((size_t)(k / PKB_CB) * ld + r) * PKB_CB + (k % PKB_CB);
+}
+__host__ __device__ __forceinline__ size_t spec_size(int ncols, int ld) {
+    return (size_t)((ncols + PKB_CB - 1) / PKB_CB) * ld * PKB_CB;
+}
 
 struct ChainCtrl {
     int trunc;   // state is zero outside [0,D)^2: only that block is read
@@ -82,35 +101,40 @@ __device__ __forceinline__ void hermitian_split(cplx zk, cplx zn, cplx& A, cplx&
     B = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
 }
 
-#define PKB_UNPACK_U 4   // independent gathers in flight per thread in the pack / unpack loops
+#define PKB_UNPACK_U 2   // independent column PAIRS in flight per thread in the pack / unpack loops
 
-// x holds the digit-reversed transform of two packed real rows; write their
-// half spectra transposed: dst[k * ld + 0] = A_k, dst[k * ld + 1] = B_k (B only if two).
-// dst and ld are even (32-byte aligned pairs).
-__device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan, int Nc, cplx* __restrict__ dst, size_t ld, bool two,
+// x holds the digit-reversed transform of two packed real rows a (row r) and b (row r + 1);
+// write their half spectra A_k, B_k into the tiled transposed array dst.  Each thread
+// handles two adjacent columns (k, k + 1) so that every store is 32 bytes.
+__device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan, int Nc, cplx* __restrict__ dst, int ld, int r, bool two,
                                              int tid, int T) {
-    for (int k0 = tid; k0 < Nc; k0 += PKB_UNPACK_U * T) {
-        int2 pr[PKB_UNPACK_U];
+    const int npair = (Nc + 1) / 2;
+    for (int j0 = tid; j0 < npair; j0 += PKB_UNPACK_U * T) {
+        int4 pr[PKB_UNPACK_U];
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
-            const int k = k0 + u * T;
-            pr[u] = k < Nc ? __ldg(&plan.pair[k]) : make_int2(0, 0);
+            const int j = j0 + u * T;
+            // pair[] has N entries and N is even or 2j + 1 < N; the last odd column reads a valid dummy
+            pr[u] = j < npair ? __ldg(reinterpret_cast<const int4*>(plan.pair) + j) : make_int4(0, 0, 0, 0);
         }
-        cplx zk[PKB_UNPACK_U], zn[PKB_UNPACK_U];
+        cplx zk[2 * PKB_UNPACK_U], zn[2 * PKB_UNPACK_U];
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
-            zk[u] = x[pr[u].x];
-            zn[u] = x[pr[u].y];
+            zk[2 * u] = x[pr[u].x];
+            zn[2 * u] = x[pr[u].y];
+            zk[2 * u + 1] = x[pr[u].z];
+            zn[2 * u + 1] = x[pr[u].w];
         }
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
-            const int k = k0 + u * T;
-            if (k < Nc) {
-                cplx A, B;
-                hermitian_split(zk[u], zn[u], A, B);
-                cplx* o = dst + (size_t)k * ld;
-                if (two) st_pair(o, A, B);
-                else o[0] = A;
+            const int j = j0 + u * T;
+            if (j < npair) {
+                cplx A0, B0, A1, B1;
+                hermitian_split(zk[2 * u], zn[2 * u], A0, B0);
+                hermitian_split(zk[2 * u + 1], zn[2 * u + 1], A1, B1);
+                cplx* o = dst + spec_index(2 * j, r, ld);
+                st_pair(o, A0, A1);
+                if (two) st_pair(o + PKB_CB, B0, B1);
             }
         }
     }
@@ -137,7 +161,7 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
             return cmake(s0[j], two ? s1[j] : 0.0);
         };
         fft_forward_from(x, tws, plan, tid, T, ld);
-        unpack_store(x, plan, d.Nc, Yt + r0, (size_t)d.ldY, two, tid, T);
+        unpack_store(x, plan, d.Nc, Yt, d.ldY, r0, two, tid, T);
         __syncthreads();
     }
 }
@@ -172,7 +196,7 @@ __global__ void PKB_ROWS_LB k_kernel_rows(const double* __restrict__ K, int Wk, 
             return cmake(k0[dx], two ? k1[dx] : 0.0);
         };
         fft_forward_from(x, tws, plan, tid, T, ld);
-        unpack_store(x, plan, d.Nc, Krt + q0, (size_t)d.ldK, two, tid, T);
+        unpack_store(x, plan, d.Nc, Krt, d.ldK, q0, two, tid, T);
         __syncthreads();
     }
 }
@@ -233,17 +257,18 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
     cplx* myscr = scr + (size_t)blockIdx.x * ((size_t)plan.cols_kb * RL * T);
     const int off_last = plan.ntw - 1;   // table offset of the last stage (one entry)
     for (int c = blockIdx.x; c < d.Nc; c += gridDim.x) {
-        const cplx* ycol = Yt + (size_t)c * d.ldY;
-        const cplx* kcol = Krt + (size_t)c * d.ldK;
-        cplx* wcol = Wt + (size_t)c * d.ldW;
+        // row i of this column lives at col[i * PKB_CB]
+        const cplx* ycol = Yt + spec_index(c, 0, d.ldY);
+        const cplx* kcol = Krt + spec_index(c, 0, d.ldK);
+        cplx* wcol = Wt + spec_index(c, 0, d.ldW);
         auto ld_filter = [&](int i) -> cplx {
-            if (i <= m) return kcol[i];
-            if (i >= N - m) return kcol[i - (N - nq)];
+            if (i <= m) return kcol[(size_t)i * PKB_CB];
+            if (i >= N - m) return kcol[(size_t)(i - (N - nq)) * PKB_CB];
             return cmake(0.0, 0.0);
         };
-        auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[i] : cmake(0.0, 0.0); };
+        auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[(size_t)i * PKB_CB] : cmake(0.0, 0.0); };
         auto st_out = [&](int i, cplx v) {
-            if (i < hi || i >= N - m) wcol[i] = v;
+            if (i < hi || i >= N - m) wcol[(size_t)i * PKB_CB] = v;
         };
         for (int phase = 0; phase < 2; ++phase) {
             auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
@@ -339,35 +364,41 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             else { r = m + 2 * j; out_b = (r + 1 < P - m) ? r + 1 : -1; }
             fold = false; out_a = r; ra = r; rb = out_b;
         }
-        const bool pair_ld = !fold && out_b >= 0;
-        // scatter the Hermitian pair Z = A + iB into digit-reversed order
-        for (int k0 = tid; k0 < Nc; k0 += PKB_UNPACK_U * T) {
-            int2 pr[PKB_UNPACK_U];
-            cplx a[PKB_UNPACK_U], b[PKB_UNPACK_U];
+        // scatter the Hermitian pair Z = A + iB into digit-reversed order; each thread
+        // handles two adjacent columns (32-byte loads per row)
+        const int npair = (Nc + 1) / 2;
+        for (int j0 = tid; j0 < npair; j0 += PKB_UNPACK_U * T) {
+            int4 pr[PKB_UNPACK_U];
+            cplx a[2 * PKB_UNPACK_U], b[2 * PKB_UNPACK_U];
 #pragma unroll
             for (int u = 0; u < PKB_UNPACK_U; ++u) {
-                const int k = k0 + u * T;
-                if (k < Nc) {
-                    pr[u] = __ldg(&plan.pair[k]);
-                    const cplx* w = Wt + (size_t)k * d.ldW;
-                    if (pair_ld) ld_pair(w + ra, a[u], b[u]);
-                    else {
-                        a[u] = w[ra];
-                        b[u] = rb >= 0 ? w[rb] : zero;
-                    }
+                const int j = j0 + u * T;
+                if (j < npair) {
+                    pr[u] = __ldg(reinterpret_cast<const int4*>(plan.pair) + j);
+                    ld_pair(Wt + spec_index(2 * j, ra, d.ldW), a[2 * u], a[2 * u + 1]);
+                    if (rb >= 0) ld_pair(Wt + spec_index(2 * j, rb, d.ldW), b[2 * u], b[2 * u + 1]);
+                    else { b[2 * u] = zero; b[2 * u + 1] = zero; }
                 } else {
-                    pr[u] = make_int2(0, 0); a[u] = zero; b[u] = zero;
+                    pr[u] = make_int4(0, 0, 0, 0);
+                    a[2 * u] = a[2 * u + 1] = b[2 * u] = b[2 * u + 1] = zero;
                 }
             }
 #pragma unroll
             for (int u = 0; u < PKB_UNPACK_U; ++u) {
-                const int k = k0 + u * T;
-                if (k < Nc) {
-                    if (k == 0 || N - k == k) {
-                        x[pr[u].x] = cmake(a[u].x, b[u].x);        // self-conjugate bins are real
-                    } else {
-                        x[pr[u].x] = cmake(a[u].x - b[u].y, a[u].y + b[u].x);    // A + iB
-                        x[pr[u].y] = cmake(a[u].x + b[u].y, b[u].x - a[u].y);    // conj(A) + i conj(B)
+                const int j = j0 + u * T;
+                if (j < npair) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = 2 * j + h;
+                        if (k >= Nc) break;
+                        const cplx av = a[2 * u + h], bv = b[2 * u + h];
+                        const int pk = h ? pr[u].z : pr[u].x, pn = h ? pr[u].w : pr[u].y;
+                        if (k == 0 || N - k == k) {
+                            x[pk] = cmake(av.x, bv.x);        // self-conjugate bins are real
+                        } else {
+                            x[pk] = cmake(av.x - bv.y, av.y + bv.x);    // A + iB
+                            x[pn] = cmake(av.x + bv.y, bv.x - av.y);    // conj(A) + i conj(B)
+                        }
                     }
                 }
             }

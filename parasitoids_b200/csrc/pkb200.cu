@@ -512,7 +512,8 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     std::vector<int2> pair(N);
     for (int k = 0; k < N; ++k) pair[k] = make_int2(perm[k], perm[(N - k) % N]);
     CU(cudaMalloc((void**)&rec.twb, sizeof(cplx) * twb.size()));
-    CU(cudaMalloc((void**)&rec.pair, sizeof(int2) * N));
+    CU(cudaMalloc((void**)&rec.pair, sizeof(int2) * (N + 2)));
+    CU(cudaMemset(rec.pair, 0, sizeof(int2) * (N + 2)));
     CU(cudaMalloc((void**)&rec.perm, sizeof(int) * N));
     CU(cudaMemcpy(rec.twb, twb.data(), sizeof(cplx) * twb.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(rec.pair, pair.data(), sizeof(int2) * N, cudaMemcpyHostToDevice));
@@ -850,9 +851,9 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     d.N = pkb_smooth_len(std::max(2, d.P + 2 * mmax));
     d.Nc = d.N / 2 + 1;
     d.ldS = roundup(d.P, 16);
-    d.ldY = roundup(d.P, 8);
-    d.ldW = roundup(d.N, 8);
-    d.ldK = roundup(2 * mmax + 1, 8);
+    d.ldY = roundup(d.P, 2);
+    d.ldW = roundup(d.N, 2);
+    d.ldK = roundup(2 * mmax + 1, 2);
     TRY(get_plan(ctx, d.N, &ch->plan));
     if (fft_smem_bytes(ch->plan) > (size_t)ctx->max_smem)
         return fail(PKB_ELIMIT, "torus side %d (domain %d + filter radius %d) exceeds the shared-memory FFT limit of %d points", d.N, D,
@@ -873,9 +874,9 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
-    TRY(ch->Yt.alloc(ctx, (size_t)d.Nc * d.ldY));
-    TRY(ch->Wt.alloc(ctx, (size_t)d.Nc * d.ldW));
-    TRY(ch->Krt.alloc(ctx, (size_t)d.Nc * d.ldK));
+    TRY(ch->Yt.alloc(ctx, spec_size(d.Nc + 1, d.ldY)));
+    TRY(ch->Wt.alloc(ctx, spec_size(d.Nc + 1, d.ldW)));
+    TRY(ch->Krt.alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
     TRY(ch->rstat.alloc(ctx, d.P));
     TRY(ch->ctrl.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->meta.alloc(ctx, 1 + PKB_MAX_COHORTS));
@@ -1298,7 +1299,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
             if (krad(j) > D / 2) return fail(PKB_ELIMIT, "kernel radius %d is larger than the domain radius", krad(j));
         }
         for (int j = 0; j + 1 < rd; ++j) {
-            TRY(ch->kcache[j].alloc(ctx, (size_t)d.Nc * d.ldK));
+            TRY(ch->kcache[j].alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
             krt[j] = ch->kcache[j].p;
         }
         // r_spread[j] as a state (Run.py:469-474); `spread` holds the latest one

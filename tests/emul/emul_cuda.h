@@ -38,6 +38,8 @@ struct dim3 {
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int a, int b, int c, int d) { int4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
 namespace emu {
 struct Fiber {
