@@ -168,7 +168,31 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
 
 // Row spectra of the wrap-shifted kernel (CalcSol.py:58-64 on the N torus).
 // K: dense (Wk x Wk) window centred on the release cell, support radius m.
-// Krt[kc][q], q = dy for dy in [0,m], q = dy + 2m+1 for dy in [-m,-1].
+// Krt column k, row q: q = dy for dy in [0,m], q = dy + 2m+1 for dy in [-m,-1].
+// One job = one row pair (q0, q0 + 1), q0 = 2 * job.
+__device__ __forceinline__ void kernel_rows_job(cplx* x, const cplx* tws, const double* __restrict__ K, int Wk, int m, const ChainDims& d,
+                                                cplx* __restrict__ Krt, const FftPlan& plan, int job, int tid, int T) {
+    const int nq = 2 * m + 1;
+    const int ck = Wk / 2;
+    const int N = d.N;
+    const int q0 = 2 * job;
+    const bool two = q0 + 1 < nq;
+    const int dy0 = q0 <= m ? q0 : q0 - nq;
+    const int dy1 = !two ? 0 : (q0 + 1 <= m ? q0 + 1 : q0 + 1 - nq);
+    const double* k0 = K + (size_t)(ck + dy0) * Wk + ck;
+    const double* k1 = K + (size_t)(ck + dy1) * Wk + ck;
+    auto ld = [&](int j) -> cplx {
+        int dx;
+        if (j <= m) dx = j;
+        else if (j >= N - m) dx = j - N;
+        else return cmake(0.0, 0.0);
+        return cmake(k0[dx], two ? k1[dx] : 0.0);
+    };
+    fft_forward_from(x, tws, plan, tid, T, ld);
+    unpack_store(x, plan, d.Nc, Krt, d.ldK, q0, two, tid, T);
+    __syncthreads();
+}
+
 // grid = persistent over the m+1 row pairs, block = T
 __global__ void PKB_ROWS_LB k_kernel_rows(const double* __restrict__ K, int Wk, int m, ChainDims d, cplx* __restrict__ Krt,
                                           FftPlan plan) {
@@ -178,26 +202,33 @@ __global__ void PKB_ROWS_LB k_kernel_rows(const double* __restrict__ K, int Wk, 
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
-    const int nq = 2 * m + 1;
-    const int ck = Wk / 2;
-    const int N = d.N;
-    for (int job = blockIdx.x; 2 * job < nq; job += gridDim.x) {
-        const int q0 = 2 * job;
-        const bool two = q0 + 1 < nq;
-        const int dy0 = q0 <= m ? q0 : q0 - nq;
-        const int dy1 = !two ? 0 : (q0 + 1 <= m ? q0 + 1 : q0 + 1 - nq);
-        const double* k0 = K + (size_t)(ck + dy0) * Wk + ck;
-        const double* k1 = K + (size_t)(ck + dy1) * Wk + ck;
-        auto ld = [&](int j) -> cplx {
-            int dx;
-            if (j <= m) dx = j;
-            else if (j >= N - m) dx = j - N;
-            else return cmake(0.0, 0.0);
-            return cmake(k0[dx], two ? k1[dx] : 0.0);
-        };
-        fft_forward_from(x, tws, plan, tid, T, ld);
-        unpack_store(x, plan, d.Nc, Krt, d.ldK, q0, two, tid, T);
-        __syncthreads();
+    for (int job = blockIdx.x; job <= m; job += gridDim.x) kernel_rows_job(x, tws, K, Wk, m, d, Krt, plan, job, tid, T);
+}
+
+// Row spectra of the kernels of a whole block of days in ONE launch (the fused
+// solve: phase 1 has left every day's kernel on the device, so none of this work
+// needs to sit on the chain's critical path).  Day i: window K0 + i * kstride,
+// radius b.m[i], spectra to Krt0 + i * krt_stride; jobs [b.job0[i], b.job0[i+1]).
+#define PKB_KR_MAXD 64
+struct KrBatch {
+    int nd;
+    int job0[PKB_KR_MAXD + 1];
+    int m[PKB_KR_MAXD];
+};
+__global__ void PKB_ROWS_LB k_kernel_rows_batch(const double* __restrict__ K0, size_t kstride, int Wk, KrBatch b, ChainDims d,
+                                                cplx* __restrict__ Krt0, size_t krt_stride, FftPlan plan) {
+    PKB_DYN_SMEM(raw);
+    cplx* x = reinterpret_cast<cplx*>(raw);
+    cplx* tws = x + plan.N;
+    const int tid = threadIdx.x, T = blockDim.x;
+    fft_load_twiddles(tws, plan, tid, T);
+    __syncthreads();
+    const int total = b.job0[b.nd];
+    int day = 0;
+    for (int job = blockIdx.x; job < total; job += gridDim.x) {
+        while (job >= b.job0[day + 1]) ++day;      // jobs of a CTA increase monotonically
+        kernel_rows_job(x, tws, K0 + (size_t)day * kstride, Wk, b.m[day], d, Krt0 + (size_t)day * krt_stride, plan,
+                        job - b.job0[day], tid, T);
     }
 }
 
@@ -327,6 +358,47 @@ __device__ __forceinline__ double block_reduce8(double (&v)[8], double* red, int
     return r;
 }
 
+// Flag / kept sum / kept count / minimum of a state from its per-row statistics
+// -> control block and step meta (CalcSol.py:36-37, 134-135).  Whole CTA; fixed
+// summation order for a given block size.  red: 8 * 32 doubles.
+__device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const ChainDims& d, ChainCtrl* __restrict__ ctrl,
+                                                    StepMeta* __restrict__ meta, int apply_trunc, double* red, int tid, int T) {
+    // st[0] pad max, st[1] kept sum, st[2] kept count, st[3] -min
+    double st[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
+    // contiguous chunks per thread so the summation order over rows is fixed
+    const int chunk = (d.P + T - 1) / T;
+    const volatile RowStats* rv = rstat;
+    for (int r = tid * chunk; r < d.P && r < (tid + 1) * chunk; ++r) {
+        const double pm = rv[r].padmax, ks = rv[r].ksum, vm = rv[r].vmin;
+        const int kc = rv[r].kcnt;
+        st[0] = fmax(st[0], pm);
+        if (r < d.D) { st[1] += ks; st[2] += (double)kc; st[3] = fmax(st[3], -vm); }
+    }
+    __syncthreads();
+    const double rr = block_reduce8(st, red, tid, T);
+    if (tid < 4) red[256 + tid] = rr;
+    __syncthreads();
+    if (tid == 0) {
+        const double bp = red[256], bs = red[257], bc = red[258], bm = -red[259];
+        const int flag = bp > 1e-8 ? 1 : 0;          // CalcSol.py:36-37
+        meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->vmin = bm;
+        meta->add = (1.0 - bs) / bc;                 // CalcSol.py:135
+        meta->flag = flag;
+        ctrl->flag = flag;
+        // a fresh convolution result is a full P x P state; it becomes a
+        // truncated one only where the caller applies CalcSol.py:200-201
+        ctrl->trunc = apply_trunc ? flag : 0;
+    }
+}
+
+// grid = 1, block = 256 (stencil path and re-thresholding; the FFT path finalises
+// in the last CTA of k_rows_inv)
+__global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta,
+                                int apply_trunc) {
+    PKB_SHARED(double, red, 264);
+    step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x);
+}
+
 // number of inverse-row jobs: 2m fold jobs, an unpaired row m if m is odd, then row pairs
 __host__ __device__ __forceinline__ int rows_inv_jobs(int P, int m) {
     if (P - 2 * m <= 0) return 2 * m;
@@ -340,9 +412,11 @@ __host__ __device__ __forceinline__ int rows_inv_jobs(int P, int m) {
 // real and imaginary part; "fold" jobs carry the two linear-convolution rows that
 // fold onto the same output row mod P (their sum is re + im).
 __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
-                                       RowStats* __restrict__ rstat, double negval, FftPlan plan) {
+                                       RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
+                                       ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(double, red, 264);
+    PKB_SHARED(int, last, 1);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -447,34 +521,16 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         }
         __syncthreads();
     }
-}
-
-// grid = 1, block = 256.  Fixed-order tree over the P rows.
-__global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta,
-                                int apply_trunc) {
-    PKB_SHARED(double, red, 256);
-    const int tid = threadIdx.x, T = blockDim.x;
-    double pmax = -INFINITY, ks = 0.0, kc = 0.0, vmn = INFINITY;
-    // contiguous chunks per thread so the summation order over rows is fixed
-    const int chunk = (d.P + T - 1) / T;
-    for (int r = tid * chunk; r < d.P && r < (tid + 1) * chunk; ++r) {
-        const RowStats rs = rstat[r];
-        pmax = fmax(pmax, rs.padmax);
-        if (r < d.D) { ks += rs.ksum; kc += (double)rs.kcnt; vmn = fmin(vmn, rs.vmin); }
-    }
-    const double bp = block_max(pmax, red);
-    const double bs = block_sum(ks, red);
-    const double bc = block_sum(kc, red);
-    const double bm = block_min(vmn, red);
+    // the CTA that finishes last reduces the row statistics of the whole state
     if (tid == 0) {
-        const int flag = bp > 1e-8 ? 1 : 0;          // CalcSol.py:36-37
-        meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->vmin = bm;
-        meta->add = (1.0 - bs) / bc;                 // CalcSol.py:135
-        meta->flag = flag;
-        ctrl->flag = flag;
-        // a fresh convolution result is a full P x P state; it becomes a
-        // truncated one only where the caller applies CalcSol.py:200-201
-        ctrl->trunc = apply_trunc ? flag : 0;
+        __threadfence();
+        last[0] = atomicAdd(done, 1) == (int)gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (last[0]) {
+        __threadfence();
+        step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, tid, T);
+        if (tid == 0) *done = 0;
     }
 }
 

@@ -70,6 +70,8 @@ struct PlanRec {
 struct pkb_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t aux;       // side stream: output emission overlapped with the next chain step
+    cudaEvent_t ev_step[2], ev_emit[2];
     long long launches;
     std::map<int, PlanRec> plans;
     // size-bucketed free lists: repeated solves (MCMC proposals, bench steps)
@@ -214,15 +216,15 @@ static cudaEvent_t prof_event(pkb_ctx* ctx) {
     }
     return e;
 }
-static void prof_begin(pkb_ctx* ctx, const char* name) {
+static void prof_begin(pkb_ctx* ctx, const char* name, cudaStream_t strm) {
     pkb_ctx::ProfRec r;
     r.name = name;
     r.a = prof_event(ctx);
     r.b = prof_event(ctx);
-    cudaEventRecord(r.a, ctx->stream);
+    cudaEventRecord(r.a, strm);
     ctx->prof_pending.push_back(r);
 }
-static void prof_end(pkb_ctx* ctx) { cudaEventRecord(ctx->prof_pending.back().b, ctx->stream); }
+static void prof_end(pkb_ctx* ctx, cudaStream_t strm) { cudaEventRecord(ctx->prof_pending.back().b, strm); }
 // fold finished event pairs into the accumulators (call after a stream sync)
 static void prof_collect(pkb_ctx* ctx) {
     for (auto& r : ctx->prof_pending) {
@@ -238,13 +240,14 @@ static void prof_collect(pkb_ctx* ctx) {
     ctx->prof_pending.clear();
 }
 
-#define LAUNCH(ctx, kern, grid, block, smem, ...)                             \
+#define LAUNCH_ON(ctx, strm, kern, grid, block, smem, ...)                    \
     do {                                                                      \
-        if ((ctx)->prof_on) prof_begin((ctx), #kern);                         \
-        PKB_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);      \
-        if ((ctx)->prof_on) prof_end((ctx));                                  \
+        if ((ctx)->prof_on) prof_begin((ctx), #kern, (strm));                 \
+        PKB_LAUNCH(kern, grid, block, smem, (strm), __VA_ARGS__);             \
+        if ((ctx)->prof_on) prof_end((ctx), (strm));                          \
         (ctx)->launches++;                                                    \
     } while (0)
+#define LAUNCH(ctx, kern, grid, block, smem, ...) LAUNCH_ON(ctx, (ctx)->stream, kern, grid, block, smem, __VA_ARGS__)
 
 static int check_launches(pkb_ctx* ctx, const char* where) {
     cudaError_t e = cudaGetLastError();
@@ -255,6 +258,7 @@ static int check_launches(pkb_ctx* ctx, const char* where) {
 static int sync_check(pkb_ctx* ctx, const char* where) {
     TRY(check_launches(ctx, where));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->aux);
     if (e != cudaSuccess) return fail(PKB_ECUDA, "stream synchronize failed in %s: %s", where, cudaGetErrorString(e));
     if (!ctx->prof_pending.empty()) prof_collect(ctx);
     return 0;
@@ -295,10 +299,16 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
+    CU(cudaStreamCreate(&ctx->aux));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_step[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 5; ++i) CU(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&ctx->marks[i]));
     TRY(opt_in_smem(k_rows_fwd));
     TRY(opt_in_smem(k_kernel_rows));
+    TRY(opt_in_smem(k_kernel_rows_batch));
     TRY(opt_in_smem(k_cols));
     TRY(opt_in_smem(k_rows_inv));
     TRY(opt_in_smem(k_fft_test));
@@ -328,6 +338,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->marks[i]);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_emit[i]); }
+    cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -821,6 +833,7 @@ struct pkb_chain {
     int cur;
     DBuf<cplx> Yt, Wt, Krt;
     DBuf<cplx> cscr;        // k_cols: per-CTA parking space for the filter column spectrum
+    DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
     int grid_rows, grid_cols;
     DBuf<RowStats> rstat;
     DBuf<ChainCtrl> ctrl;   // [0] main state, [1 + j] cohort j
@@ -878,6 +891,8 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     TRY(ch->Wt.alloc(ctx, spec_size(d.Nc + 1, d.ldW)));
     TRY(ch->Krt.alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
     TRY(ch->rstat.alloc(ctx, d.P));
+    TRY(ch->done.alloc(ctx, 1));
+    CU(cudaMemsetAsync(ch->done.p, 0, sizeof(int), ctx->stream));
     TRY(ch->ctrl.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->meta.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->dout.alloc(ctx, (size_t)D * D));
@@ -918,12 +933,14 @@ extern "C" int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N) {
     return 0;
 }
 
-// One convolution step: dst = src (*) K on the P torus.  K is a device window
-// Wk x Wk with support radius m.  krt: row spectra buffer to (re)use;
-// krt_ready: it already holds the spectra of K.  Leaves per-row statistics in
-// ch->rstat (taken with ch->negval).
+// One convolution step: dst = src (*) K on the P torus, followed by the step's
+// flag / sums -> ctrl[slot], meta[slot] (apply_trunc: mark a flagged state as
+// truncated to the domain, CalcSol.py:200-201; readers of a state honour
+// ctrl->trunc, so the pad is only physically zeroed where a caller can see it).
+// K is a device window Wk x Wk with support radius m.  krt: row spectra buffer to
+// (re)use; krt_ready: it already holds the spectra of K.
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
-                     cplx* krt, bool krt_ready) {
+                     cplx* krt, bool krt_ready, int slot, int apply_trunc) {
     pkb_ctx* ctx = ch->ctx;
     const ChainDims& d = ch->d;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
@@ -932,6 +949,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         const size_t smem = ((size_t)(8 + 2 * m) * (32 + 2 * m) + (size_t)(2 * m + 1) * (2 * m + 1)) * sizeof(double);
         LAUNCH(ctx, k_stencil, dim3((d.P + 31) / 32, (d.P + 7) / 8), dim3(32, 8), smem, src, K, Wk, m, d, src_ctrl, dst);
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
+        LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
         return 0;
     }
     // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
@@ -942,16 +960,15 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     LAUNCH(ctx, k_cols, std::min(d.Nc, ch->grid_cols), ch->plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
            ch->Wt.p, ch->cscr.p, ch->plan);
     const int njobs = rows_inv_jobs(d.P, m);
-    LAUNCH(ctx, k_rows_inv, std::min(njobs, ch->grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan);
+    LAUNCH(ctx, k_rows_inv, std::min(njobs, ch->grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan,
+           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
     return 0;
 }
 
-// flag / sums of the state whose row statistics are in ch->rstat -> ctrl[slot], meta[slot];
-// apply_trunc: also truncate a flagged state to the domain (CalcSol.py:200-201)
-static void finalize_step(pkb_chain* ch, double* state, int slot, int apply_trunc) {
+// flag / sums of a state whose row statistics are in ch->rstat -> ctrl[0], meta[0] (re-thresholding)
+static void finalize_state(pkb_chain* ch) {
     pkb_ctx* ctx = ch->ctx;
-    LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, ch->d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
-    if (apply_trunc) LAUNCH(ctx, k_zero_pad, ch->d.P, 256, 0, state, ch->d, (const ChainCtrl*)(ch->ctrl.p + slot));
+    LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, ch->d, ch->ctrl.p, ch->meta.p, 0);
 }
 
 extern "C" int pkb_chain_set_state(pkb_chain* ch, const double* A) {
@@ -1007,9 +1024,9 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
     return 0;
 }
 
-static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m) {
+static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr) {
     const int nxt = ch->cur ^ 1;
-    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, ch->Krt.p, false));
+    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc));
     ch->cur = nxt;
     return 0;
 }
@@ -1019,8 +1036,7 @@ extern "C" int pkb_chain_conv(pkb_chain* ch, const double* B, int k) {
     CU(cudaSetDevice(ch->ctx->device));
     int m = 0;
     TRY(upload_filter(ch, B, k, &m));
-    TRY(chain_conv_main(ch, ch->kup.p, 2 * m + 1, m));
-    finalize_step(ch, ch->S[ch->cur].p, 0, 0);
+    TRY(chain_conv_main(ch, ch->kup.p, 2 * m + 1, m, 0));
     ch->stats_valid = true;
     return sync_check(ch->ctx, "pkb_chain_conv");
 }
@@ -1028,8 +1044,7 @@ extern "C" int pkb_chain_conv(pkb_chain* ch, const double* B, int k) {
 extern "C" int pkb_chain_conv_kernel(pkb_chain* ch, pkb_kset* ks, int i) {
     if (!ch || !ks || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_chain_conv_kernel: bad argument");
     CU(cudaSetDevice(ch->ctx->device));
-    TRY(chain_conv_main(ch, ks->acc.p + (size_t)ks->W * ks->W * i, ks->W, ks->hmeta[i].rad));
-    finalize_step(ch, ch->S[ch->cur].p, 0, 0);
+    TRY(chain_conv_main(ch, ks->acc.p + (size_t)ks->W * ks->W * i, ks->W, ks->hmeta[i].rad, 0));
     ch->stats_valid = true;
     return sync_check(ch->ctx, "pkb_chain_conv_kernel");
 }
@@ -1044,7 +1059,7 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
     if (!ch->stats_valid || negval != ch->negval) {
         ch->negval = negval;
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)S, d, ch->rstat.p, negval);
-        finalize_step(ch, S, 0, 0);
+        finalize_state(ch);
         ch->stats_valid = true;
     }
     if (out) {
@@ -1075,9 +1090,8 @@ static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, 
         if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
         cplx* kr = krt ? krt[j] : ch->Krt.p;
         const bool rdy = krt && ready && ready[j];
-        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, F[j], Wk[j], m[j], kr, rdy));
+        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, F[j], Wk[j], m[j], kr, rdy, 1 + j, 1));   // CalcSol.py:103-105 (same-shape re-FFT)
         if (ready) ready[j] = true;
-        finalize_step(ch, ch->coh[j].p, 1 + j, 1);     // CalcSol.py:103-105 (same-shape re-FFT)
         src = ch->coh[j].p;
         src_ctrl = ch->ctrl.p + 1 + j;
     }
@@ -1098,8 +1112,7 @@ extern "C" int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters,
         if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
         int m = 0;
         TRY(upload_filter(ch, filters[j], ks[j], &m));
-        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false));
-        finalize_step(ch, ch->coh[j].p, 1 + j, 1);
+        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false, 1 + j, 1));
         if (out) {
             if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p);
             else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p);
@@ -1276,17 +1289,53 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     auto kern = [&](int i) { return (const double*)(ks->acc.p + nW * i); };
     auto krad = [&](int i) { return ks->hmeta[i].rad; };
 
+    // Row spectra of the daily kernels, a block of days per launch, ahead of the
+    // chain (phase 1 left every kernel on the device): off the critical path.
+    const size_t krt_stride = spec_size(d.Nc + 1, d.ldK);
+    const int kr_chunk = (int)std::max<size_t>(1, std::min<size_t>(PKB_KR_MAXD, ((size_t)4 << 30) / (krt_stride * sizeof(cplx))));
+    DBuf<cplx> krt_all;
+    TRY(krt_all.alloc(ctx, krt_stride * std::min(kr_chunk, nd)));
+    int kr_first = -1;      // first day held in krt_all
+    auto day_spectra = [&](int n, cplx** out) -> int {
+        // spectra of day n (nullptr: the stencil path needs none)
+        *out = nullptr;
+        if (krad(n) <= ctx->stencil_max_radius) return 0;
+        if (kr_first < 0 || n >= kr_first + kr_chunk) {
+            KrBatch kb;
+            memset(&kb, 0, sizeof kb);
+            kr_first = n;
+            kb.nd = std::min(kr_chunk, nd - n);
+            for (int i = 0; i < kb.nd; ++i) {
+                kb.m[i] = krad(n + i);
+                kb.job0[i + 1] = kb.job0[i] + (kb.m[i] > ctx->stencil_max_radius ? kb.m[i] + 1 : 0);
+            }
+            LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[kb.nd], ch->grid_rows), ctx->fft_threads, fft_smem_bytes(ch->plan), kern(n),
+                   nW, ks->W, kb, d, krt_all.p, krt_stride, ch->plan);
+        }
+        *out = krt_all.p + krt_stride * (n - kr_first);
+        return 0;
+    };
+
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n)));
-            finalize_step(ch, ch->S[ch->cur].p, 0, 1);
-            LAUNCH(ctx, k_emit_dense, D, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)ch->meta.p, negval, 1, 0,
-                   res->dense.p + nD * n);
+            cplx* krt = nullptr;
+            TRY(day_spectra(n, &krt));
+            // step n overwrites the state buffer that the emission of day n-2 reads
+            if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+            // r_small_vals + dense output on the side stream, overlapped with step n+1
+            CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
+            LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
+                      res->dense.p + nD * n);
+            CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
         }
+        for (int i = 0; i < 2; ++i)
+            if (nd - 1 - i >= 1) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[(nd - 1 - i) & 1], 0));
     } else {
         const int rd = a->r_dur;
         const double rn = a->r_number;
@@ -1326,8 +1375,9 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         }
         // post-release days (CalcSol.py:308-323)
         for (int n = rd; n < nd; ++n) {
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n)));
-            finalize_step(ch, ch->S[ch->cur].p, 0, 1);
+            cplx* kday = nullptr;
+            TRY(day_spectra(n, &kday));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
             for (int c = 0; c < rd; ++c) {

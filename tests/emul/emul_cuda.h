@@ -94,6 +94,7 @@ static inline double atomicAdd(double* addr, double val) {
     return o;
 }
 static inline int atomicAdd(int* addr, int val) { return __atomic_fetch_add(addr, val, __ATOMIC_RELAXED); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicOr(int* addr, int val) { return __atomic_fetch_or(addr, val, __ATOMIC_RELAXED); }
 static inline int atomicMax(int* addr, int val) {
     int old = __atomic_load_n(addr, __ATOMIC_RELAXED);
@@ -149,6 +150,9 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSucce
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
