@@ -101,37 +101,43 @@ __device__ __forceinline__ void hermitian_split(cplx zk, cplx zn, cplx& A, cplx&
     B = cmake(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
 }
 
-#define PKB_UNPACK_U 2   // independent column PAIRS in flight per thread in the pack / unpack loops
+#ifndef PKB_UNPACK_U
+#define PKB_UNPACK_U 2   // column PAIRS in flight per thread in the pack / unpack loops (deeper did not help: not latency bound)
+#endif
+#ifndef PKB_PREFETCH
+#define PKB_PREFETCH 1    // bit 0: rows_fwd, bit 1: rows_inv prefetch their next job into L2 (measured: bit 1 is no gain)
+#endif
+// column PAIRS in flight per thread in the pack / unpack loops (covers N <= 5120 at 256 threads in one sweep)
 
 // x holds the digit-reversed transform of two packed real rows a (row r) and b (row r + 1);
 // write their half spectra A_k, B_k into the tiled transposed array dst.  Each thread
 // handles two adjacent columns (k, k + 1) so that every store is 32 bytes.
+// The caller has NOT yet synchronised after the last forward stage: the first sweep's
+// gather indices are fetched (L2 latency) before the barrier.
 __device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan, int Nc, cplx* __restrict__ dst, int ld, int r, bool two,
                                              int tid, int T) {
     const int npair = (Nc + 1) / 2;
-    for (int j0 = tid; j0 < npair; j0 += PKB_UNPACK_U * T) {
+    bool synced = false;
+    for (int j0 = tid; j0 < npair || !synced; j0 += PKB_UNPACK_U * T) {
         int4 pr[PKB_UNPACK_U];
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
             const int j = j0 + u * T;
-            // pair[] has N entries and N is even or 2j + 1 < N; the last odd column reads a valid dummy
+            // pair[] has N + 2 entries; the last odd column reads a valid dummy
             pr[u] = j < npair ? __ldg(reinterpret_cast<const int4*>(plan.pair) + j) : make_int4(0, 0, 0, 0);
         }
-        cplx zk[2 * PKB_UNPACK_U], zn[2 * PKB_UNPACK_U];
-#pragma unroll
-        for (int u = 0; u < PKB_UNPACK_U; ++u) {
-            zk[2 * u] = x[pr[u].x];
-            zn[2 * u] = x[pr[u].y];
-            zk[2 * u + 1] = x[pr[u].z];
-            zn[2 * u + 1] = x[pr[u].w];
+        if (!synced) {
+            __syncthreads();
+            synced = true;
         }
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
             const int j = j0 + u * T;
             if (j < npair) {
+                const cplx zk0 = x[pr[u].x], zn0 = x[pr[u].y], zk1 = x[pr[u].z], zn1 = x[pr[u].w];
                 cplx A0, B0, A1, B1;
-                hermitian_split(zk[2 * u], zn[2 * u], A0, B0);
-                hermitian_split(zk[2 * u + 1], zn[2 * u + 1], A1, B1);
+                hermitian_split(zk0, zn0, A0, B0);
+                hermitian_split(zk1, zn1, A1, B1);
                 cplx* o = dst + spec_index(2 * j, r, ld);
                 st_pair(o, A0, A1);
                 if (two) st_pair(o + PKB_CB, B0, B1);
@@ -160,7 +166,15 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
             if (j >= lim) return cmake(0.0, 0.0);
             return cmake(s0[j], two ? s1[j] : 0.0);
         };
-        fft_forward_from(x, tws, plan, tid, T, ld);
+        {   // next job's two rows -> L2 while this one is transformed
+            const int nr0 = 2 * (job + (int)gridDim.x);
+            if ((PKB_PREFETCH & 1) && nr0 < lim) {
+                const char* nxt = reinterpret_cast<const char*>(S + (size_t)nr0 * d.ldS);
+                const int nbytes = (nr0 + 1 < lim ? 2 : 1) * d.ldS * (int)sizeof(double);
+                for (int o = tid * 128; o < nbytes; o += T * 128) prefetch_l2(nxt + o);
+            }
+        }
+        fft_forward_from(x, tws, plan, tid, T, ld, false);
         unpack_store(x, plan, d.Nc, Yt, d.ldY, r0, two, tid, T);
         __syncthreads();
     }
@@ -188,7 +202,7 @@ __device__ __forceinline__ void kernel_rows_job(cplx* x, const cplx* tws, const 
         else return cmake(0.0, 0.0);
         return cmake(k0[dx], two ? k1[dx] : 0.0);
     };
-    fft_forward_from(x, tws, plan, tid, T, ld);
+    fft_forward_from(x, tws, plan, tid, T, ld, false);
     unpack_store(x, plan, d.Nc, Krt, d.ldK, q0, two, tid, T);
     __syncthreads();
 }
@@ -407,6 +421,19 @@ __host__ __device__ __forceinline__ int rows_inv_jobs(int P, int m) {
     return 2 * m + (m & 1) + (rest > 0 ? (rest + 1) / 2 : 0);
 }
 
+// rows of job `job`: inputs (ra, rb) of Wt, outputs (out_a, out_b) of the state, fold flag
+__device__ __forceinline__ void rows_inv_decode(int job, int m, int P, int N, int& ra, int& rb, int& out_a, int& out_b, bool& fold) {
+    if (job < m) { fold = true; out_a = job; out_b = -1; ra = job; rb = job + P; }
+    else if (job < 2 * m) { const int t = job - m; fold = true; out_a = P - m + t; out_b = -1; ra = out_a; rb = N - m + t; }
+    else {
+        // interior rows [m, P-m): pairs start on even rows
+        int j = job - 2 * m, r;
+        if (m & 1) { r = j == 0 ? m : m + 1 + 2 * (j - 1); out_b = (j > 0 && r + 1 < P - m) ? r + 1 : -1; }
+        else { r = m + 2 * j; out_b = (r + 1 < P - m) ? r + 1 : -1; }
+        fold = false; out_a = r; ra = r; rb = out_b;
+    }
+}
+
 // grid = persistent over rows_inv_jobs(P, m) jobs, block = T
 // A job is one inverse transform.  "Pair" jobs carry two interior output rows as
 // real and imaginary part; "fold" jobs carry the two linear-convolution rows that
@@ -429,14 +456,19 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         int ra, rb, out_a, out_b;
         bool fold;
-        if (job < m) { fold = true; out_a = job; out_b = -1; ra = job; rb = job + P; }
-        else if (job < 2 * m) { const int t = job - m; fold = true; out_a = P - m + t; out_b = -1; ra = out_a; rb = N - m + t; }
-        else {
-            // interior rows [m, P-m): pairs start on even rows (32-byte aligned loads)
-            int j = job - 2 * m, r;
-            if (m & 1) { r = j == 0 ? m : m + 1 + 2 * (j - 1); out_b = (j > 0 && r + 1 < P - m) ? r + 1 : -1; }
-            else { r = m + 2 * j; out_b = (r + 1 < P - m) ? r + 1 : -1; }
-            fold = false; out_a = r; ra = r; rb = out_b;
+        rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
+        {   // next job's Wt rows -> L2 while this one is transformed
+            const int nj = job + (int)gridDim.x;
+            if ((PKB_PREFETCH & 2) && nj < njobs) {
+                int na, nb, oa, ob;
+                bool nf;
+                rows_inv_decode(nj, m, P, N, na, nb, oa, ob, nf);
+                const int ntile = (Nc + PKB_CB - 1) / PKB_CB;
+                for (int t = tid; t < ntile; t += T) {
+                    prefetch_l2(Wt + spec_index(t * PKB_CB, na, d.ldW));
+                    if (nb >= 0) prefetch_l2(Wt + spec_index(t * PKB_CB, nb, d.ldW));
+                }
+            }
         }
         // scatter the Hermitian pair Z = A + iB into digit-reversed order; each thread
         // handles two adjacent columns (32-byte loads per row)

@@ -299,15 +299,17 @@ __device__ __forceinline__ int fft_tw_offset(const FftPlan& p, int s) {
 }
 
 // Forward stages s0 .. s1-1 in shared memory (x holds the data on entry; M0 / off0 are the
-// block size and table offset of stage s0).  A barrier follows every stage.
-__device__ __forceinline__ void fft_fwd_stages(cplx* x, const cplx* tws, const FftPlan& p, int s0, int s1, int M0, int off0, int tid, int T) {
+// block size and table offset of stage s0).  A barrier follows every stage (the one after
+// the last stage only if final_sync).
+__device__ __forceinline__ void fft_fwd_stages(cplx* x, const cplx* tws, const FftPlan& p, int s0, int s1, int M0, int off0, int tid, int T,
+                                               bool final_sync = true) {
     int M = M0, off = off0;
     for (int s = s0; s < s1; ++s) {
         const int R = plan_radix(p, s);
         fft_stage_dispatch<false>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
         off += M / R;
         M /= R;
-        __syncthreads();
+        if (final_sync || s + 1 < s1) __syncthreads();
     }
 }
 // Inverse stages s1-1 down to s0 in shared memory; M1 = block size AFTER stage s1-1 has been
@@ -327,11 +329,11 @@ __device__ __forceinline__ void fft_inv_stages(cplx* x, const cplx* tws, const F
 // Whole forward transform with the first stage fed by ld(index) (global memory).
 // tws must be loaded; the caller guarantees x is free.  Returns synchronised.
 template <class Load>
-__device__ __forceinline__ void fft_forward_from(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Load ld) {
+__device__ __forceinline__ void fft_forward_from(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Load ld, bool final_sync = true) {
     const int R0 = plan_radix(p, 0);
     fft_stage_dispatch<false>(R0, p.N, p.N, tws, tid, T, ld, SmemStore{x});
-    __syncthreads();
-    fft_fwd_stages(x, tws, p, 1, p.nstage, p.N / R0, p.N / R0, tid, T);
+    if (final_sync || p.nstage > 1) __syncthreads();
+    fft_fwd_stages(x, tws, p, 1, p.nstage, p.N / R0, p.N / R0, tid, T, final_sync);
 }
 
 // Whole inverse transform (unnormalised, result = N * ifft) with the last stage

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -468,12 +469,26 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     std::vector<int> fac;
     if (!min_factor(N, fac)) return fail(PKB_EINVAL, "FFT length %d cannot be factored into the supported radices", N);
     std::sort(fac.begin(), fac.end(), [](int a, int b) { return a > b; });
+    bool forced = false;
+    if (const char* env = getenv("PKB_FFT_PLAN")) {
+        // tuning hook: explicit radix sequence "12,8,7,7" (used as is when its product is N)
+        std::vector<int> f2;
+        long long prod = 1;
+        for (const char* q = env; *q;) {
+            const int r = atoi(q);
+            if (r >= 2 && r <= 12 && r != 11) { f2.push_back(r); prod *= r; }
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (prod == N && !f2.empty()) { fac = f2; forced = true; }
+    }
     // last radix (k_cols keeps whole last-stage blocks per thread, stride R_last
     // complex between threads): the largest odd one is bank-conflict free
     int last = -1;
     for (size_t i = 0; i < fac.size() && last < 0; ++i)
         if (fac[i] & 1) last = (int)i;
     if (last < 0) last = 0;
+    if (forced) last = (int)fac.size() - 1;
     const int rl = fac[last];
     fac.erase(fac.begin() + last);
     fac.push_back(rl);

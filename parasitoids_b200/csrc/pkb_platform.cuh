@@ -48,6 +48,14 @@ __device__ __forceinline__ void st_pair(cplx* p, cplx a, cplx b) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 #endif
 }
+// hint: bring the 128-byte line at p into L2 (persistent kernels prefetch their NEXT job's inputs)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !PKB_IS_EMUL
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ void ld_pair(const cplx* p, cplx& a, cplx& b) {
 #if PKB_IS_EMUL
     a = p[0];

@@ -11,7 +11,57 @@
 #include <cstdlib>
 #include <random>
 
+// pure shared-memory FFT rate: every CTA transforms its own buffer forward and back `reps` times
+__global__ void PKB_ROWS_LB k_fft_core(cplx* out, int reps, FftPlan plan) {
+    PKB_DYN_SMEM(raw);
+    cplx* x = reinterpret_cast<cplx*>(raw);
+    cplx* tws = x + plan.N;
+    const int tid = threadIdx.x, T = blockDim.x;
+    fft_load_twiddles(tws, plan, tid, T);
+    for (int i = tid; i < plan.N; i += T) x[i] = cmake(1.0 / (i + 1), 0.5 / (i + 2));
+    __syncthreads();
+    for (int r = 0; r < reps; ++r) {
+        fft_fwd_stages(x, tws, plan, 0, plan.nstage, plan.N, 0, tid, T);
+        fft_inv_stages(x, tws, plan, plan.nstage, 0, 1, plan.ntw, tid, T);
+        const double sc = 1.0 / plan.N;
+        for (int i = tid; i < plan.N; i += T) x[i] = cmake(x[i].x * sc, x[i].y * sc);
+        __syncthreads();
+    }
+    if (tid == 0) out[blockIdx.x] = x[blockIdx.x % plan.N];
+}
+
+static int core_bench(pkb_ctx* ctx, int N, int T, int reps) {
+    FftPlan plan;
+    if (get_plan(ctx, N, &plan)) { fprintf(stderr, "%s\n", pkb_last_error()); return 1; }
+    opt_in_smem(k_fft_core);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fft_core, T, fft_smem_bytes(plan));
+    const int grid = occ * ctx->sm_count;
+    cplx* out = nullptr;
+    cudaMalloc(&out, sizeof(cplx) * grid);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k_fft_core<<<grid, T, fft_smem_bytes(plan), ctx->stream>>>(out, 2, plan);
+    cudaEventRecord(a, ctx->stream);
+    k_fft_core<<<grid, T, fft_smem_bytes(plan), ctx->stream>>>(out, reps, plan);
+    cudaEventRecord(b, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    printf("core N=%d radices", N);
+    for (int s = 0; s < plan.nstage; ++s) printf(" %d", plan_radix(plan, s));
+    const double ntr = 2.0 * reps * grid;   // forward + inverse
+    printf("  T=%d occ=%d: %.2f us per transform per SM (%.0f cycles at 1.965 GHz), err %s\n", T, occ,
+           1000.0 * ms / (ntr / ctx->sm_count), 1965.0 * 1000.0 * ms / (ntr / ctx->sm_count), cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "core")) {
+        pkb_ctx* c0 = nullptr;
+        if (pkb_create(0, &c0)) { fprintf(stderr, "%s\n", pkb_last_error()); return 1; }
+        return core_bench(c0, argc > 2 ? atoi(argv[2]) : 4704, argc > 3 ? atoi(argv[3]) : 256, argc > 4 ? atoi(argv[4]) : 20);
+    }
     const int D = argc > 1 ? atoi(argv[1]) : 4097;
     const int k = argc > 2 ? atoi(argv[2]) : 361;
     const int steps = argc > 3 ? atoi(argv[3]) : 10;
