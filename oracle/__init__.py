@@ -16,10 +16,10 @@ ref_loader  imports the *unmodified* reference modules from /root/reference
             with the 3-line ``mvn.mvnun`` shim (build-container only).
 make_golden generates tests/golden/*.npz from the reference itself.
 
-Parity pinning: pinned.  The restatement is checked (tests/test_oracle_*.py)
+Parity pinning: pinned.  The restatement is checked (tests/test_oracle.py)
 against golden vectors produced by running the reference's own code in the
 build container (oracle/make_golden.py, vectors committed under
 tests/golden/), and against the reference's own known-answer tests
 (tests/test_CalcSol.py:75-139 in the reference tree, restated in
-tests/test_calcsol_ref_cases.py).
+tests/test_oracle.py::test_reference_known_answers and tests/test_chain.py).
 """

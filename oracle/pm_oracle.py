@@ -9,7 +9,7 @@ BVNMVN/BVU), is absent from the reference tree *and* from current SciPy, so it
 is restated here from the published algorithm (A. Genz, "Numerical computation
 of rectangular bivariate and trivariate normal and t probabilities",
 Statistics and Computing 14 (2004) 251-260; TVPACK routine BVU) and checked in
-tests/test_oracle_pm.py against SciPy's compiled Genz BVU
+tests/test_oracle.py against SciPy's compiled Genz BVU
 (``scipy.special._ufuncs._bivariate_normal_cdf``) and against golden vectors
 produced by the reference's own ``get_mvn_cdf_values`` / ``prob_mass``.
 """

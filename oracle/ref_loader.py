@@ -6,7 +6,7 @@ TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
 so nothing reachable from ``pytest -m gpu``, ``smoke()`` or ``bench.py`` may
 call this.  It is used by ``oracle/make_golden.py`` (to produce the committed
 fixtures under tests/golden/) and by the container-only cross-checks in
-tests/test_oracle_vs_reference.py (skipped when the tree is absent).
+tests/test_oracle.py (skipped when the tree is absent).
 
 The reference's ``ParasitoidModel.py:22,340`` needs ``scipy.stats.mvn.mvnun``
 (Fortran MVNDST), which current SciPy no longer ships.  SciPy does ship the
