@@ -143,3 +143,87 @@ def test_reference_known_answers():
     CO.fftconv2(A_hat, sparse.csr_matrix(B))
     C, flag = CO.ifft2(A_hat, A.shape)
     assert np.allclose(C.toarray(), signal.fftconvolve(A, B, 'same'))
+
+
+# ---------------------------------------------------------------------------
+# Container-only: the restatement against the UNMODIFIED reference modules
+# executed from /root/reference (absent on the GPU box -> skipped there).
+def _reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not present (GPU box)')
+    return ref_loader
+
+
+def test_oracle_vs_live_reference_phase1(tmp_path):
+    """get_mvn_cdf_values, h_flight_prob and a short prob_mass run by the
+    reference's own code, now, against the oracle."""
+    rl = _reference()
+    from oracle import pm_oracle as PO
+    pm, cs, gv = rl.load()
+    rng = np.random.default_rng(42)
+    for _ in range(4):
+        sx, sy, rho = rng.uniform(20, 200), rng.uniform(20, 200), rng.uniform(-0.7, 0.7)
+        mu = rng.uniform(-12.5, 12.5, 2)
+        with rl.quiet():
+            ref = pm.get_mvn_cdf_values(25.0, mu, pm.Dmat(sx, sy, rho))
+        got = PO.get_mvn_cdf_values(25.0, mu, PO.Dmat(sx, sy, rho))
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 5e-16
+    periods = 48
+    w = np.zeros((2, periods, 3))
+    w[:, :, 0] = 0.4 * np.sin(np.linspace(0, 4, 2 * periods)).reshape(2, periods)
+    w[:, :, 1] = 0.2 * np.cos(np.linspace(0, 3, 2 * periods)).reshape(2, periods)
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    hp = (1., 1.263, 3.913, 7.302, 2.614, 23.999, 2.350)
+    with rl.quiet():
+        href = pm.h_flight_prob(w[0], *hp)
+    assert np.abs(PO.h_flight_prob(w[0], *hp) - href).max() < 1e-17
+    wind_data = {1: w[0], 2: w[1]}
+    args = (1, wind_data, hp, (171.82, 144.58, 0.253), (7.096, 7.260, 0.0), 1.179, 2, 1500.0, 30)
+    import warnings
+    with rl.quiet(), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = pm.prob_mass(*args).toarray()
+        got = PO.prob_mass(*args).toarray()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-15 and abs(got.sum() - 1) < 1e-14
+
+
+def test_oracle_vs_live_reference_chain():
+    """get_solutions / get_populations (with the documented back_solve fix) by
+    the reference's own CalcSol, now, against the oracle."""
+    rl = _reference()
+    from oracle import cs_oracle as CO
+    pm, cs, gv = rl.load(fixed_back_solve=True)
+    rng = np.random.default_rng(9)
+    D = 41
+    pmfs = []
+    for k in (9, 13, 11, 15, 9):
+        a = rng.random((k, k))
+        a[a < 0.3] = 0
+        pmfs.append(sparse.coo_matrix(a / a.sum()))
+    ms = [15, 15]
+    days = list(range(5))
+
+    def first():
+        p = pmfs[0]
+        off = D // 2 - p.shape[0] // 2
+        return sparse.coo_matrix((p.data, (p.row + off, p.col + off)), shape=(D, D))
+    ref, got = [first()], [first()]
+    with rl.quiet():
+        cs.get_solutions(ref, pmfs, days, 5, D, ms)
+    CO.get_solutions(got, pmfs, days, 5, D, ms)
+    for a, b in zip(ref, got):
+        assert np.abs(a.toarray() - b.toarray()).max() < 1e-15
+    r_spread = []
+    for p in pmfs[:2]:
+        off = D // 2 - p.shape[0] // 2
+        r_spread.append(sparse.coo_matrix((p.data, (p.row + off, p.col + off)), shape=(D, D)).tocsr())
+    import warnings
+    with rl.quiet(), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        pref = cs.get_populations(r_spread, pmfs, days, 5, D, ms, 2, 1000.0, lambda d: 0.5)
+    pgot = CO.get_populations(r_spread, pmfs, days, 5, D, ms, 2, 1000.0, lambda d: 0.5)
+    for a, b in zip(pref, pgot):
+        assert np.abs(a.toarray() - b.toarray()).max() < 1e-11
