@@ -35,6 +35,7 @@ import sys
 import tempfile
 import threading
 import time
+import warnings
 
 import numpy as np
 
@@ -51,7 +52,50 @@ WORKLOADS = {
     # name: (days, hourly samples/day, interp_num, rad_dist, rad_res)
     'synthetic_4097x4097_60d': (60, 24, 60, 51200.0, 2048),
     'synthetic_801x801_18d': (18, 24, 60, 10000.0, 400),          # Kalbar-sized, for quick checks
+    # BASELINE.json configs[4]: 512 MCMC proposals x the full Kalbar population solve (Run.py:126-138),
+    # sharded over the ranks by parasitoids_b200.batch.solve_batch (strong scaling)
+    'kalbar_batch512': (18, 48, 30, 10000.0, 400),
 }
+BATCH = 512
+
+
+def kalbar_wind():
+    """Kalbar wind series (data/kalbarwind.txt as committed in tests/golden/wind.npz) through get_wind_data."""
+    from parasitoids_b200 import ParasitoidModel as PM
+    from parasitoids_b200 import Run
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'wind.npz'))
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = os.path.join(tmp, 'kalbar')
+        with open(prefix + 'wind.txt', 'w') as fobj:
+            for d, block in zip(z['kalbar_days'], z['kalbar_raw']):
+                for wx, wy, _ in block:
+                    fobj.write('%d\t%.17g\t%.17g\n' % (d, wx, wy))
+        wind_data, days = PM.get_wind_data(prefix, 30, '00:00')
+    return Run.stack_wind(wind_data, days), wind_data, days, 10000.0, 400
+
+
+def prior_proposals(B, seed=7):
+    """B draws from the central region of the priors of Bayes_Run.py:102-130 (PyMC2
+    alpha/beta and tau parameterisations), in batch.PROPOSAL_FIELDS order."""
+    rng = np.random.default_rng(seed)
+    sd = 1.0 / np.sqrt(0.3)
+    P = np.empty((B, 15))
+    P[:, 0] = rng.gamma(2.2, 1.0, B)                                   # g_aw
+    P[:, 1] = rng.gamma(5.0, 1.0, B)                                   # g_bw
+    P[:, 2] = np.clip(rng.normal(6.0, sd, B), 0.0, 9.0)                # f_a1
+    P[:, 3] = 1.0 + rng.gamma(2.0, 1.0, B)                             # f_b1
+    P[:, 4] = np.clip(rng.normal(20.0, sd, B), 15.0, 24.0)             # f_a2
+    P[:, 5] = 1.0 + rng.gamma(2.0, 1.0, B)                             # f_b2
+    P[:, 6] = rng.gamma(26.0, 1.0 / 0.15, B)                           # sig_x
+    P[:, 7] = rng.gamma(15.0, 1.0 / 0.15, B)                           # sig_y
+    P[:, 8] = 2.0 * rng.beta(5.0, 5.0, B) - 1.0                        # corr
+    P[:, 9] = np.maximum(rng.gamma(2.0, 1.0 / 0.08, B), 2.0)           # sig_x_l
+    P[:, 10] = np.maximum(rng.gamma(2.0, 1.0 / 0.14, B), 2.0)          # sig_y_l
+    P[:, 11] = 2.0 * rng.beta(5.0, 5.0, B) - 1.0                       # corr_l
+    P[:, 12] = rng.beta(5.0, 1.0, B)                                   # lam
+    P[:, 13] = np.maximum(rng.poisson(30, B), 1)                       # n_periods
+    P[:, 14] = np.clip(rng.normal(1.0, 1.0, B), 0.05, 3.0)             # mu_r
+    return P
 
 
 def synthetic_wind(ndays, per_day, seed=20261018):
@@ -73,6 +117,8 @@ def load_workload(name):
     package's own get_wind_data (the reference's input path)."""
     from parasitoids_b200 import ParasitoidModel as PM
     from parasitoids_b200 import Run
+    if name == 'kalbar_batch512':
+        return kalbar_wind()
     ndays, per_day, interp, rad_dist, rad_res = WORKLOADS[name]
     raw = synthetic_wind(ndays, per_day)
     with tempfile.TemporaryDirectory() as tmp:
@@ -290,10 +336,16 @@ def main():
     # N > 1: a likelihood batch of one parameter proposal per rank (proposal 0 = the defaults),
     # sharded by parasitoids_b200.batch.solve_batch; the only collective is its all_gather
     model = (HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res)
+    batch_mode = args.workload == 'kalbar_batch512'
     proposals = np.tile(np.array([HPARAMS[1], HPARAMS[2], HPARAMS[3], HPARAMS[4], HPARAMS[5], HPARAMS[6], *DPARAMS, *DLPARAMS,
                                   HPARAMS[0], N_PERIODS, MU_R]), (world, 1))
     proposals[:, 6] *= 1 + 0.01 * np.arange(world)
     proposals[:, 7] *= 1 - 0.005 * np.arange(world)
+    pop_kw = dict(prob_model=True)
+    if batch_mode:
+        proposals = prior_proposals(BATCH)
+        pop_kw = dict(prob_model=False, r_dur=1, r_number=130000.0)      # Run.py:126-138 (kalbar preset)
+    units = (BATCH if batch_mode else world) * ndays                     # simulated days per step, all ranks
     wind_dev = torch.from_numpy(wind).cuda(local)
     wind_pinned = torch.from_numpy(wind).pin_memory()
     rng = np.random.default_rng(7)
@@ -303,17 +355,21 @@ def main():
         pass
 
     def step_device():
-        if world > 1:
-            batch.solve_batch(None, proposals, cells, ndays, rad_dist, rad_res, prob_model=True, device=local,
-                              wind_device_ptr=wind_dev.data_ptr(), wind_shape=wind.shape)
+        if world > 1 or batch_mode:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')      # proposals with strong drift warn about wasps leaving the domain
+                batch.solve_batch(None, proposals, cells, ndays, rad_dist, rad_res, device=local,
+                                  wind_device_ptr=wind_dev.data_ptr(), wind_shape=wind.shape, **pop_kw)
             return None
         return Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
                          wind_shape=wind.shape, device=local)
 
     def step_e2e():
-        if world > 1:
+        if world > 1 or batch_mode:
             # host wind in, sampled cells of every proposal out (what the likelihood consumes)
-            out = batch.solve_batch(wind_pinned.numpy(), proposals, cells, ndays, rad_dist, rad_res, prob_model=True, device=local)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                out = batch.solve_batch(wind_pinned.numpy(), proposals, cells, ndays, rad_dist, rad_res, device=local, **pop_kw)
             return None, out.size // 2        # counted below as 16 bytes per entry
         res = Run.solve(wind_pinned.numpy(), ndays, *model, want_coo=True, device=local)
         off, rows, cols, vals = res.coo_arrays()
@@ -331,8 +387,10 @@ def main():
             r.close()
 
     # geometry of the workload (one untimed solve on every rank)
-    r = Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
-                  wind_shape=wind.shape, device=local)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        r = Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
+                      wind_shape=wind.shape, device=local)
     info = (r.P, r.N, r.dom_len, r.flags(), r.radii())
     r.close()
     for _ in range(args.warmup):
@@ -354,7 +412,7 @@ def main():
         chain = 0.0
         for _ in range(args.steps):
             close(step_device())
-            chain += ctx.timing()['chain_ms']
+            chain += ctx.timing()['chain_ms']      # phase-2 time of the LAST solve of the step
         ctx.mark(1)
         barrier()
         t1 = time.perf_counter()
@@ -373,7 +431,7 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_ms, wall_ms, prof_ms = float(tt[0]), float(tt[1]), float(tt[2])
-    value = world * ndays * args.steps / (t_ms / 1000.0)
+    value = units * args.steps / (t_ms / 1000.0)
 
     # ---- per-kernel roofline (rank 0) --------------------------------------------
     P, N, D, flags, radii = info
@@ -397,10 +455,10 @@ def main():
     if cnt:
         ach = share[dom] / (ms / cnt / 1000.0) / 1e9
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': traffic_from_profiles(dom), 'peak_source': peak_src, 'launches': cnt,
+                    'traffic': None if batch_mode else traffic_from_profiles(dom), 'peak_source': peak_src, 'launches': cnt,
                     'avg_launch_ms': ms / cnt, 'algorithmic_bytes_per_launch': share[dom]}
     roofline_chain = None
-    if nsteps_chain:
+    if nsteps_chain and not batch_mode:      # batch mode: proposals differ in torus size; the per-kernel roofline above still applies
         nflag = sum(1 for f in flags if f)
         bytes_solve = sum(chain_bytes(P, D, f) for f in flags[1:])
         # whole chain phase of the solve (library events around phase 2, pass A): kernels, gaps and overlap included
@@ -431,20 +489,20 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_ms = float(te[0])
-    e2e = {'value': world * ndays * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
-           'h2d_bytes_per_step': int(wind.nbytes) * world, 'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
+    e2e = {'value': units * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
+           'h2d_bytes_per_step': int(wind.nbytes) * (len(proposals) if (world > 1 or batch_mode) else 1), 'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
            'ms_per_step': e_ms / args.steps, 'timer': 'host wall clock between device synchronisations',
            'api': ('parasitoids_b200.batch.solve_batch: wind from pinned host memory on every rank, sampled cells of all proposals '
-                   'all-gathered and copied to host') if world > 1 else
+                   'all-gathered and copied to host') if (world > 1 or batch_mode) else
                   'parasitoids_b200.Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}
 
     if rank == 0:
         line = {'metric': 'simulated days/sec (fp64)', 'value': value, 'unit': 'days/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'warmup': args.warmup, 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if batch_mode else 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': P, 'fft_len': N,
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
-                           'parallelism': 'likelihood batch of %d proposals, one per GPU (batch.solve_batch), one NCCL all_gather of 1024 sampled cells x days per step' % world if world > 1 else 'single solve',
+                           'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if (world > 1 or batch_mode) else 'single solve',
                            'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'roofline_chain': roofline_chain}
