@@ -392,6 +392,7 @@ def main():
         r = Run.solve(None, ndays, *model, want_coo=False, keep_device=True, wind_device_ptr=wind_dev.data_ptr(),
                       wind_shape=wind.shape, device=local)
     info = (r.P, r.N, r.dom_len, r.flags(), r.radii())
+    window_steps = r.window_steps()
     r.close()
     for _ in range(args.warmup):
         close(step_device())
@@ -502,6 +503,7 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': P, 'fft_len': N,
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
+                           'support_window_steps': window_steps,
                            'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if (world > 1 or batch_mode) else 'single solve',
                            'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),

@@ -81,7 +81,7 @@ int pkb_create(int device, pkb_ctx** out);
 int pkb_destroy(pkb_ctx* ctx);
 int pkb_sync(pkb_ctx* ctx);
 /* option keys: "stencil_max_radius" (direct-convolution switch point),
- * "fft_threads" */
+ * "fft_threads", "windows" (0/1: support-window chain steps in pkb_solve, default 1) */
 int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
 /* device time in ms of the phases of the last pkb_solve: [0] phase 1,
  * [1] chain, [2] output compaction + D2H, [3] total */
@@ -197,6 +197,9 @@ typedef struct pkb_solve_args {
 
 int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
 int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape);
+/* number of chain steps that ran on a support-window torus smaller than N (exact: the state is
+ * identically zero outside the window while the spread has not reached the domain edge) */
+int pkb_result_window_steps(pkb_result* r, int* n);
 int pkb_result_day_meta(pkb_result* r, int day, pkb_day_meta* kmeta, pkb_step_meta* smeta);
 /* dense solution of one day: device->host copy on demand */
 int pkb_result_dense(pkb_result* r, int day, double* out);

@@ -207,6 +207,12 @@ class SolveResult(object):
         _lib.check(_lib.lib().pkb_result_day_meta(self.h, day, C.byref(km), C.byref(sm)))
         return km, sm
 
+    def window_steps(self):
+        """Chain steps that ran on a support-window torus (see ChainDims::win in csrc/chain.cuh)."""
+        n = C.c_int()
+        _lib.check(_lib.lib().pkb_result_window_steps(self.h, C.byref(n)))
+        return n.value
+
     def flags(self):
         return [bool(self.day_meta(d)[1].flag) for d in range(self.ndays)]
 

@@ -90,6 +90,7 @@ _SIGS = {
     'pkb_smooth_len': (C.c_int, [C.c_int]),
     'pkb_solve': (C.c_int, [_H, C.POINTER(SolveArgs), _HP]),
     'pkb_result_info': (C.c_int, [_H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'pkb_result_window_steps': (C.c_int, [_H, c_int_p]),
     'pkb_result_day_meta': (C.c_int, [_H, C.c_int, C.POINTER(DayMeta), C.POINTER(StepMeta)]),
     'pkb_result_dense': (C.c_int, [_H, C.c_int, c_double_p]),
     'pkb_result_coo': (C.c_int, [_H, C.POINTER(c_ll_p), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p)]),

@@ -53,6 +53,12 @@ struct ChainDims {
     int ldY;    // row slots per column tile of Yt  (>= P)
     int ldW;    // row slots per column tile of Wt  (>= N)
     int ldK;    // row slots per column tile of the kernel row spectra (>= 2*mmax+1)
+    // Window mode (win != 0): the state is known to be EXACTLY zero outside the square
+    // [wr0, wr0 + wn) x [wc0, wc0 + wn) and the convolution result fits inside the domain, so
+    // the step is a plain linear convolution of that window on a torus N >= wn + 2m that may be
+    // much smaller than the full one: nothing wraps, nothing folds, no flag can trip.  The
+    // result lands in [wr0 - m, wr0 + wn + m) x [wc0 - m, wc0 + wn + m); everything else stays zero.
+    int win, wr0, wc0, wn;
 };
 
 // Layout of the transposed spectra Yt / Wt / Krt: spectral columns are grouped in
@@ -155,8 +161,9 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
-    const int lim = ctrl->trunc ? d.D : d.P;
+    const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
     const int njobs = (lim + 1) / 2;
+    if (d.win) S += (size_t)d.wr0 * d.ldS + d.wc0;     // rows / columns below are relative to the window
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         const int r0 = 2 * job;
         const bool two = r0 + 1 < lim;
@@ -295,10 +302,10 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
-    const int lim = ctrl->trunc ? d.D : d.P;
+    const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
     const int N = d.N, nq = 2 * m + 1;
     const int L = plan.nstage, R0 = plan_radix(plan, 0), RL = plan_radix(plan, L - 1), nbl = N / RL;
-    const int hi = d.P + m;   // rows [0, P+m) and [N-m, N) are needed by the fold
+    const int hi = (d.win ? d.wn : d.P) + m;   // rows [0, extent + m) and [N-m, N) are needed downstream
     cplx* myscr = scr + (size_t)blockIdx.x * ((size_t)plan.cols_kb * RL * T);
     const int off_last = plan.ntw - 1;   // table offset of the last stage (one entry)
     for (int c = blockIdx.x; c < d.Nc; c += gridDim.x) {
@@ -450,16 +457,27 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
     const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
-    const int njobs = rows_inv_jobs(P, m);
+    const int wout = d.wn + 2 * m;                       // window mode: side of the result
+    const int njobs = d.win ? (wout + 1) / 2 : rows_inv_jobs(P, m);
     const double scale = 1.0 / ((double)N * (double)N);
     const cplx zero = cmake(0.0, 0.0);
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         int ra, rb, out_a, out_b;
         bool fold;
-        rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
+        if (d.win) {
+            // linear rows j = -m + 2 job and j + 1 (mod N in Wt) -> state rows wr0 + j
+            const int ja = 2 * job - m, jb = ja + 1;
+            fold = false;
+            ra = ja < 0 ? ja + N : ja;
+            out_a = d.wr0 + ja;
+            if (jb < d.wn + m) { rb = jb < 0 ? jb + N : jb; out_b = d.wr0 + jb; }
+            else { rb = -1; out_b = -1; }
+        } else {
+            rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
+        }
         {   // next job's Wt rows -> L2 while this one is transformed
             const int nj = job + (int)gridDim.x;
-            if ((PKB_PREFETCH & 2) && nj < njobs) {
+            if ((PKB_PREFETCH & 2) && !d.win && nj < njobs) {
                 int na, nb, oa, ob;
                 bool nf;
                 rows_inv_decode(nj, m, P, N, na, nb, oa, ob, nf);
@@ -512,22 +530,30 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         __syncthreads();
         fft_inverse_to(x, tws, plan, tid, T, SmemStore{x});
         __syncthreads();
-        // fold the columns mod P in place (2m <= P, so the two ranges are disjoint)
-        for (int c = tid; c < m; c += T) {
-            x[c] = cadd(x[c], x[c + P]);
-            x[P - m + c] = cadd(x[P - m + c], x[N - m + c]);
+        if (!d.win) {
+            // fold the columns mod P in place (2m <= P, so the two ranges are disjoint)
+            for (int c = tid; c < m; c += T) {
+                x[c] = cadd(x[c], x[c + P]);
+                x[P - m + c] = cadd(x[P - m + c], x[N - m + c]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        double* dst_a = Sout + (size_t)out_a * d.ldS;
-        double* dst_b = Sout + (size_t)(out_b >= 0 ? out_b : out_a) * d.ldS;
+        // full mode: output column c <- x[c], c in [0, P); window mode: output column
+        // wc0 - m + i <- linear column i - m (mod N), i in [0, wn + 2m)
+        const int ncols = d.win ? wout : P;
+        const int col0 = d.win ? d.wc0 - m : 0;
+        double* dst_a = Sout + (size_t)out_a * d.ldS + col0;
+        double* dst_b = Sout + (size_t)(out_b >= 0 ? out_b : out_a) * d.ldS + col0;
         // st[0..3]: row a (pad max, kept sum, kept count, -min); st[4..7]: row b
         double st[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
+        if (d.win) { st[0] = st[4] = 0.0; st[3] = st[7] = 0.0; }     // the untouched rest of the row is zero
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
-        for (int c = tid; c < P; c += T) {
-            const cplx z = x[c];
+        const int Dc = D - col0;                                     // first pad column, relative to col0
+        for (int c = tid; c < ncols; c += T) {
+            const cplx z = x[d.win ? (c < m ? c - m + N : c - m) : c];
             const double va = (fold ? z.x + z.y : z.x) * scale;
             dst_a[c] = va;
-            if (pad_a || c >= D) st[0] = fmax(st[0], va);
+            if (pad_a || c >= Dc) st[0] = fmax(st[0], va);
             else {
                 st[3] = fmax(st[3], -va);
                 if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
@@ -535,7 +561,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             if (out_b >= 0) {
                 const double vb = z.y * scale;
                 dst_b[c] = vb;
-                if (pad_b || c >= D) st[4] = fmax(st[4], vb);
+                if (pad_b || c >= Dc) st[4] = fmax(st[4], vb);
                 else {
                     st[7] = fmax(st[7], -vb);
                     if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
@@ -578,15 +604,26 @@ __global__ void k_set_ctrl(ChainCtrl* __restrict__ ctrl, int trunc, int flag) {
 // grid = D, block = 256
 // strict != 0: keep v > negval (cuda_lib.py:117-119) instead of !(v < negval)
 __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const StepMeta* __restrict__ meta, double negval, int prob_model,
-                             int strict, double* __restrict__ out) {
+                             int strict, double* __restrict__ out, int* __restrict__ rownnz) {
+    PKB_SHARED(int, cnt, 1);
     const int r = blockIdx.x;
     const double add = prob_model ? meta->add : 0.0;
     const double* src = S + (size_t)r * d.ldS;
     double* dst = out + (size_t)r * d.D;
+    if (rownnz && threadIdx.x == 0) cnt[0] = 0;
+    if (rownnz) __syncthreads();
+    int n = 0;
     for (int c = threadIdx.x; c < d.D; c += blockDim.x) {
         const double v = src[c];
         const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
-        dst[c] = keep ? v + add : 0.0;
+        const double o = keep ? v + add : 0.0;
+        dst[c] = o;
+        n += o != 0.0 ? 1 : 0;
+    }
+    if (rownnz) {       // per-row non-zero count for the COO compaction (saves a pass over the output)
+        if (n) atomicAdd(&cnt[0], n);
+        __syncthreads();
+        if (threadIdx.x == 0) rownnz[r] = cnt[0];
     }
 }
 
@@ -720,34 +757,34 @@ __global__ void __launch_bounds__(1024) k_row_scan(const int* __restrict__ rownn
         acc += rownnz[i];
     }
 }
-// grid = ndays*D, block = 256
+// grid = ndays*D, block = 256.  Each thread owns a contiguous segment of the row: count its
+// non-zeros, one block-wide exclusive scan of the 256 counts, ordered write.
 __global__ void k_coo_write(const double* __restrict__ G, int D, const long long* __restrict__ rowoff, int* __restrict__ rows,
                             int* __restrict__ cols, double* __restrict__ vals) {
     PKB_SHARED(int, cnt, 256);
-    PKB_SHARED(int, basepos, 1);
     const int r = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    if (tid == 0) basepos[0] = 0;
+    const int seg = (D + T - 1) / T;
+    const int c0 = tid * seg, c1 = c0 + seg < D ? c0 + seg : D;
+    const double* row = G + (size_t)r * D;
+    int n = 0;
+    for (int c = c0; c < c1; ++c) n += row[c] != 0.0 ? 1 : 0;
+    cnt[tid] = n;
     __syncthreads();
-    for (int c0 = 0; c0 < D; c0 += T) {
-        const int c = c0 + tid;
-        const double v = c < D ? G[(size_t)r * D + c] : 0.0;
-        const int nz = v != 0.0 ? 1 : 0;
-        cnt[tid] = nz;
+    // inclusive scan (Hillis-Steele) over the block
+    for (int s = 1; s < T; s <<= 1) {
+        const int add = tid >= s ? cnt[tid - s] : 0;
         __syncthreads();
-        // inclusive scan (Hillis-Steele) over the block
-        for (int s = 1; s < T; s <<= 1) {
-            int add = tid >= s ? cnt[tid - s] : 0;
-            __syncthreads();
-            cnt[tid] += add;
-            __syncthreads();
+        cnt[tid] += add;
+        __syncthreads();
+    }
+    long long pos = rowoff[r] + cnt[tid] - n;
+    const int rr = r % D;
+    for (int c = c0; c < c1; ++c) {
+        const double v = row[c];
+        if (v != 0.0) {
+            rows[pos] = rr; cols[pos] = c; vals[pos] = v;
+            ++pos;
         }
-        if (nz) {
-            const long long pos = rowoff[r] + basepos[0] + cnt[tid] - 1;
-            rows[pos] = r % D; cols[pos] = c; vals[pos] = v;
-        }
-        __syncthreads();
-        if (tid == 0) basepos[0] += cnt[T - 1];
-        __syncthreads();
     }
 }
 

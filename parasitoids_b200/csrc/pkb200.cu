@@ -90,6 +90,7 @@ struct pkb_ctx {
     std::map<std::string, std::pair<long long, double> > prof_acc;
     int stencil_max_radius;
     int fft_threads;
+    int use_windows;        // fused solve: support-window steps (option "windows", default on)
     int sm_count;
     int max_smem;
 };
@@ -295,6 +296,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->launches = 0;
     ctx->stencil_max_radius = 3;
     ctx->fft_threads = PKB_ROWS_T;
+    ctx->use_windows = 1;
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->prof_on = false;
@@ -356,6 +358,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "stencil_max_radius")) {
         if (value < -1 || value > 24) return fail(PKB_EINVAL, "stencil_max_radius must be in [-1, 24]");
         ctx->stencil_max_radius = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "windows")) {
+        ctx->use_windows = value != 0;
         return 0;
     }
     if (!strcmp(key, "fft_threads")) {
@@ -548,6 +554,18 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     p.twb = rec.twb;
     p.pair = rec.pair;
     p.perm = rec.perm;
+    p.grid_rows = p.grid_cols = 0;
+    if (fft_smem_bytes(p) <= (size_t)ctx->max_smem) {
+        // resident CTAs per SM of the persistent kernels at this plan's footprint (capped at 2:
+        // the register file holds two 256-thread CTAs of these kernels)
+        const size_t sm1 = fft_smem_bytes(p);
+        int occ_r = 0, occ_i = 0, occ_c = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, ctx->fft_threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, ctx->fft_threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols, p.cols_threads, sm1));
+        p.grid_rows = std::min(2, std::min(occ_r, occ_i)) * ctx->sm_count;
+        p.grid_cols = std::min(2, occ_c) * ctx->sm_count;
+    }
     ctx->plans[N] = rec;
     *out = p;
     return 0;
@@ -849,6 +867,7 @@ struct pkb_chain {
     DBuf<cplx> Yt, Wt, Krt;
     DBuf<cplx> cscr;        // k_cols: per-CTA parking space for the filter column spectrum
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
+    size_t cscr_per_cta;
     int grid_rows, grid_cols;
     DBuf<RowStats> rstat;
     DBuf<ChainCtrl> ctrl;   // [0] main state, [1 + j] cohort j
@@ -882,23 +901,17 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     d.ldY = roundup(d.P, 2);
     d.ldW = roundup(d.N, 2);
     d.ldK = roundup(2 * mmax + 1, 2);
+    d.win = d.wr0 = d.wc0 = d.wn = 0;
     TRY(get_plan(ctx, d.N, &ch->plan));
     if (fft_smem_bytes(ch->plan) > (size_t)ctx->max_smem)
         return fail(PKB_ELIMIT, "torus side %d (domain %d + filter radius %d) exceeds the shared-memory FFT limit of %d points", d.N, D,
                     mmax, (int)(ctx->max_smem / sizeof(cplx)));
-    {
-        // resident CTAs per SM of the persistent kernels at this plan's footprint
-        const size_t sm1 = fft_smem_bytes(ch->plan);
-        int occ_r = 0, occ_i = 0, occ_c = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, ctx->fft_threads, sm1));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, ctx->fft_threads, sm1));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols, ch->plan.cols_threads, sm1));
-        if (occ_r < 1 || occ_i < 1 || occ_c < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
-        ch->grid_rows = std::min(occ_r, occ_i) * ctx->sm_count;
-        ch->grid_cols = occ_c * ctx->sm_count;
-        const int rl = plan_radix(ch->plan, ch->plan.nstage - 1);
-        TRY(ch->cscr.alloc(ctx, (size_t)ch->grid_cols * ch->plan.cols_kb * rl * ch->plan.cols_threads));
-    }
+    if (ch->plan.grid_rows < 1 || ch->plan.grid_cols < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
+    ch->grid_rows = ch->plan.grid_rows;
+    ch->grid_cols = ch->plan.grid_cols;
+    // k_cols parking space: any plan up to this torus side needs at most N + R_last * threads slots per CTA
+    ch->cscr_per_cta = (size_t)d.N + 21 * 256 + 256;
+    TRY(ch->cscr.alloc(ctx, (size_t)2 * ctx->sm_count * ch->cscr_per_cta));
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
@@ -908,6 +921,7 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     TRY(ch->rstat.alloc(ctx, d.P));
     TRY(ch->done.alloc(ctx, 1));
     CU(cudaMemsetAsync(ch->done.p, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ch->rstat.p, 0, sizeof(RowStats) * d.P, ctx->stream));    // rows a windowed step never touches are zero rows
     TRY(ch->ctrl.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->meta.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->dout.alloc(ctx, (size_t)D * D));
@@ -955,27 +969,45 @@ extern "C" int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N) {
 // K is a device window Wk x Wk with support radius m.  krt: row spectra buffer to
 // (re)use; krt_ready: it already holds the spectra of K.
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
-                     cplx* krt, bool krt_ready, int slot, int apply_trunc) {
+                     cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr) {
     pkb_ctx* ctx = ch->ctx;
-    const ChainDims& d = ch->d;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
-    if (2 * m > d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, d.P);
+    if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
     if (m <= ctx->stencil_max_radius) {
+        const ChainDims& d = ch->d;
         const size_t smem = ((size_t)(8 + 2 * m) * (32 + 2 * m) + (size_t)(2 * m + 1) * (2 * m + 1)) * sizeof(double);
         LAUNCH(ctx, k_stencil, dim3((d.P + 31) / 32, (d.P + 7) / 8), dim3(32, 8), smem, src, K, Wk, m, d, src_ctrl, dst);
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
         LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
         return 0;
     }
+    // geometry of this step: the chain's torus, or a smaller one around the state's support window
+    ChainDims d = ch->d;
+    FftPlan plan = ch->plan;
+    if (win) {
+        d.win = 1; d.wr0 = win[0]; d.wc0 = win[1]; d.wn = win[2];
+        d.N = pkb_smooth_len(std::max(2, d.wn + 2 * m));
+        d.Nc = d.N / 2 + 1;
+        d.ldY = roundup(d.wn, 2);
+        d.ldW = roundup(d.N, 2);
+        d.ldK = roundup(2 * m + 1, 2);
+        TRY(get_plan(ctx, d.N, &plan));
+        if (plan.grid_rows < 1 || plan.grid_cols < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
+        krt_ready = false;          // row spectra prepared for the full torus do not apply
+        krt = ch->Krt.p;
+    }
     // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
     const int T = ctx->fft_threads;
-    const size_t sm1 = fft_smem_bytes(ch->plan);
-    if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, ch->grid_rows), T, sm1, K, Wk, m, d, krt, ch->plan);
-    LAUNCH(ctx, k_rows_fwd, std::min((d.P + 1) / 2, ch->grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, ch->plan);
-    LAUNCH(ctx, k_cols, std::min(d.Nc, ch->grid_cols), ch->plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
-           ch->Wt.p, ch->cscr.p, ch->plan);
-    const int njobs = rows_inv_jobs(d.P, m);
-    LAUNCH(ctx, k_rows_inv, std::min(njobs, ch->grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, ch->plan,
+    const size_t sm1 = fft_smem_bytes(plan);
+    const int rows_in = win ? d.wn : d.P;
+    if ((size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads > ch->cscr_per_cta)
+        return fail(PKB_ELIMIT, "column scratch too small for torus side %d", d.N);
+    if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
+    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
+    LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
+           ch->Wt.p, ch->cscr.p, plan);
+    const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
+    LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
            ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
     return 0;
 }
@@ -1039,9 +1071,9 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
     return 0;
 }
 
-static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr) {
+static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr) {
     const int nxt = ch->cur ^ 1;
-    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc));
+    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win));
     ch->cur = nxt;
     return 0;
 }
@@ -1079,7 +1111,7 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
     }
     if (out) {
         if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p);
-        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, 0, ch->dout.p);
+        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, 0, ch->dout.p, (int*)nullptr);
         CU(cudaMemcpyAsync(out, ch->dout.p, (size_t)d.D * d.D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (apply_trunc) {
@@ -1130,7 +1162,7 @@ extern "C" int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters,
         TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false, 1 + j, 1));
         if (out) {
             if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p);
-            else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p);
+            else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p, (int*)nullptr);
             CU(cudaMemcpyAsync(out + nd * j, ch->dout.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
         src = ch->coh[j].p;
@@ -1188,10 +1220,13 @@ extern "C" int pkb_chain_get_state(pkb_chain* ch, double* out) {
 struct pkb_result {
     pkb_ctx* ctx;
     int ndays, D, P, N, max_shape;
+    int window_steps;       // chain steps run on a support-window torus (ChainDims::win)
     DBuf<double> dense;     // [ndays][D][D]
     DBuf<double> pre;       // optional [ndays][D][D] un-thresholded (parity export)
     std::vector<DayMeta> kmeta;
     std::vector<StepMeta> smeta;
+    DBuf<int> rownnz;       // [ndays][D] non-zeros per output row (COO compaction)
+    std::vector<char> counted;   // days whose rownnz the emission kernel already filled
     HBuf<long long> dayoff;
     HBuf<int> rows, cols;
     HBuf<double> vals;
@@ -1200,12 +1235,19 @@ struct pkb_result {
 
 static int build_coo(pkb_ctx* ctx, pkb_result* r) {
     const int D = r->D, nd = r->ndays;
-    DBuf<int> rownnz;
+    DBuf<int>& rownnz = r->rownnz;
     DBuf<long long> rowoff, dayoff;
-    TRY(rownnz.alloc(ctx, (size_t)nd * D));
+    if (!rownnz.p) TRY(rownnz.alloc(ctx, (size_t)nd * D));
     TRY(rowoff.alloc(ctx, (size_t)nd * D));
     TRY(dayoff.alloc(ctx, nd + 1));
-    LAUNCH(ctx, k_row_nnz, nd * D, 256, 0, (const double*)r->dense.p, D, rownnz.p);
+    // count the rows of the days the emission kernels did not already count (runs of consecutive days)
+    for (int d0 = 0; d0 < nd;) {
+        if (d0 < (int)r->counted.size() && r->counted[d0]) { ++d0; continue; }
+        int d1 = d0;
+        while (d1 < nd && !(d1 < (int)r->counted.size() && r->counted[d1])) ++d1;
+        LAUNCH(ctx, k_row_nnz, (d1 - d0) * D, 256, 0, (const double*)(r->dense.p + (size_t)D * D * d0), D, rownnz.p + (size_t)D * d0);
+        d0 = d1;
+    }
     LAUNCH(ctx, k_row_scan, 1, 1024, 0, (const int*)rownnz.p, D, nd, rowoff.p, dayoff.p);
     TRY(r->dayoff.alloc(ctx, nd + 1));
     CU(cudaMemcpyAsync(r->dayoff.p, dayoff.p, sizeof(long long) * (nd + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1281,6 +1323,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     res->D = D;
     res->max_shape = 2 * mmax + 1;
     res->have_coo = false;
+    res->window_steps = 0;
     res->kmeta = ks->hmeta;
     res->smeta.assign(nd, StepMeta());
     for (auto& sm : res->smeta) memset(&sm, 0, sizeof sm);
@@ -1298,6 +1341,8 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     res->N = d.N;
     const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
     TRY(res->dense.alloc(ctx, nD * nd));
+    res->counted.assign(nd, 0);
+    if (a->want_coo) TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
     DBuf<StepMeta> dsm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
@@ -1331,22 +1376,45 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         return 0;
     };
 
+    // Support window of the state (host-side bookkeeping, exact: the first state is a kernel of
+    // radius m0 at the domain centre and every step grows the support by the day's radius).
+    // While the grown window stays inside the domain the step runs on a torus sized for the
+    // window instead of the whole padded domain (ChainDims::win).
+    int wr0 = D / 2 - krad(0), wn = 2 * krad(0) + 1;
+    bool wmode = ctx->use_windows != 0;
+    if (wmode) CU(cudaMemsetAsync(ch->S[1].p, 0, (size_t)d.P * d.ldS * sizeof(double), ctx->stream));
+    int win[3];
+    auto step_window = [&](int n) -> const int* {
+        const int m = krad(n);
+        if (wmode && wr0 - m >= 0 && wr0 + wn + m <= D && pkb_smooth_len(wn + 2 * m) < d.N) {
+            win[0] = win[1] = wr0; win[2] = wn;
+            wr0 -= m; wn += 2 * m;
+            if (m <= ctx->stencil_max_radius) return nullptr;       // the stencil path works on the whole torus
+            res->window_steps++;
+            return win;
+        }
+        wmode = false;      // the state is no longer confined: whole-torus steps from here on
+        return nullptr;
+    };
+
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
+            const int* wp = step_window(n);
             cplx* krt = nullptr;
-            TRY(day_spectra(n, &krt));
+            if (!wp) TRY(day_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
             LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
-                      res->dense.p + nD * n);
+                      res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
+            if (a->want_coo) res->counted[n] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
         }
         for (int i = 0; i < 2; ++i)
@@ -1390,9 +1458,10 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         }
         // post-release days (CalcSol.py:308-323)
         for (int n = rd; n < nd; ++n) {
+            const int* wp = rd == 1 ? step_window(n) : nullptr;
             cplx* kday = nullptr;
-            TRY(day_spectra(n, &kday));
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday));
+            if (!wp) TRY(day_spectra(n, &kday));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
             for (int c = 0; c < rd; ++c) {
@@ -1429,6 +1498,12 @@ extern "C" int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, 
     if (P) *P = r->P;
     if (N) *N = r->N;
     if (max_shape) *max_shape = r->max_shape;
+    return 0;
+}
+
+extern "C" int pkb_result_window_steps(pkb_result* r, int* n) {
+    if (!r || !n) return fail(PKB_EINVAL, "pkb_result_window_steps: NULL argument");
+    *n = r->window_steps;
     return 0;
 }
 

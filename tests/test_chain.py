@@ -301,3 +301,37 @@ def test_debug_fft_matches_numpy(pkb, n):
         pkb._lib.check(lib.pkb_debug_fft(ctx.h, n, pkb._lib.dptr(zin), pkb._lib.dptr(out), inverse))
         got = out.view(np.complex128)
         assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()) * np.log2(n + 1)
+
+
+def test_window_steps_match_whole_torus_steps(pkb):
+    """While the state's support window fits inside the domain the fused solve runs
+    each step on a torus sized for the window (ChainDims::win); the results must
+    equal the whole-torus steps to rounding, for both models."""
+    rng = np.random.default_rng(1)
+    nd, periods, rad_res, rad_dist = 7, 96, 60, 3000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        x = np.cumsum(rng.normal(0, 0.05, nd * periods)).reshape(nd, periods)
+        w[:, :, c] = 0.3 * np.sin(np.linspace(0, 6, nd * periods)).reshape(nd, periods) + x * 0.2
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=1, r_number=1000.0)):
+        out = {}
+        for windows in (1, 0):
+            ctx.set_option('windows', windows)
+            l0 = ctx.launch_count()
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                res = pkb.Run.solve(w, nd, *args, want_coo=False, want_dense=True, **kw)
+            out[windows] = ([res.dense(d) for d in range(nd)], res.flags(), res.N, ctx.launch_count() - l0)
+            res.close()
+        ctx.set_option('windows', 1)
+        assert out[1][1] == out[0][1]
+        # windowed steps compute their own kernel row spectra (one extra launch each): they were taken
+        assert out[1][3] > out[0][3], 'no step ran in window mode'
+        for d in range(nd):
+            a, b = out[1][0][d], out[0][0][d]
+            assert ((a != 0) != (b != 0)).sum() == 0
+            # population grids are probabilities scaled by r_number
+            assert np.abs(a - b).max() <= 1e-15 * kw.get('r_number', 1.0)
