@@ -15,6 +15,7 @@
 #include "chain.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +73,10 @@ struct pkb_ctx {
     int device;
     cudaStream_t stream;
     cudaStream_t aux;       // side stream: output emission overlapped with the next chain step
+    cudaStream_t cp;        // copy stream: per-day COO compaction + D2H while the chain is still running
+    std::vector<cudaEvent_t> day_events;
+    cudaEvent_t ev_cp;
+    size_t coo_hint;        // triplets of the last solve (initial size of the next one's host buffers)
     cudaEvent_t ev_step[2], ev_emit[2];
     long long launches;
     std::map<int, PlanRec> plans;
@@ -261,6 +266,7 @@ static int sync_check(pkb_ctx* ctx, const char* where) {
     TRY(check_launches(ctx, where));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->aux);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->cp);
     if (e != cudaSuccess) return fail(PKB_ECUDA, "stream synchronize failed in %s: %s", where, cudaGetErrorString(e));
     if (!ctx->prof_pending.empty()) prof_collect(ctx);
     return 0;
@@ -302,7 +308,16 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
-    CU(cudaStreamCreate(&ctx->aux));
+    {
+        // the side streams carry short kernels that must slip in between the persistent FFT kernels
+        // of the main stream: highest priority, so their CTAs are placed first whenever SM slots free up
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->cp, cudaStreamNonBlocking, hi));
+    }
+    CU(cudaEventCreateWithFlags(&ctx->ev_cp, cudaEventDisableTiming));
+    ctx->coo_hint = 0;
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&ctx->ev_step[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
@@ -342,6 +357,9 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_emit[i]); }
+    for (cudaEvent_t e : ctx->day_events) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ev_cp);
+    cudaStreamDestroy(ctx->cp);
     cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1226,6 +1244,9 @@ struct pkb_result {
     std::vector<DayMeta> kmeta;
     std::vector<StepMeta> smeta;
     DBuf<int> rownnz;       // [ndays][D] non-zeros per output row (COO compaction)
+    DBuf<long long> rowoff; // [ndays][D] exclusive scan of rownnz within each day
+    DBuf<long long> daytot; // [ndays][2]: (0, non-zeros of the day)
+    HBuf<long long> tot_host;
     std::vector<char> counted;   // days whose rownnz the emission kernel already filled
     HBuf<long long> dayoff;
     HBuf<int> rows, cols;
@@ -1233,41 +1254,87 @@ struct pkb_result {
     bool have_coo;
 };
 
-static int build_coo(pkb_ctx* ctx, pkb_result* r) {
+// ---- COO output, pipelined with the chain ------------------------------------
+// As soon as a day's dense solution has been emitted its rows are counted and
+// scanned on the emitting stream (coo_day_ready); once the whole chain has been
+// ENQUEUED the host walks the days in order, learns each day's size from an
+// 16-byte D2H, and queues that day's compaction + triplet copy on the copy stream
+// (coo_collect) -- so the 16 bytes/non-zero cross PCIe while later days are still
+// being computed.
+static int coo_day_ready(pkb_ctx* ctx, pkb_result* r, int day, cudaStream_t strm) {
+    const int D = r->D;
+    const size_t nD = (size_t)D * D;
+    if (!r->counted[day])
+        LAUNCH_ON(ctx, strm, k_row_nnz, D, 256, 0, (const double*)(r->dense.p + nD * day), D, r->rownnz.p + (size_t)D * day);
+    LAUNCH_ON(ctx, strm, k_row_scan, 1, 1024, 0, (const int*)(r->rownnz.p + (size_t)D * day), D, 1, r->rowoff.p + (size_t)D * day,
+              r->daytot.p + 2 * day);
+    CU(cudaMemcpyAsync(r->tot_host.p + 2 * day, r->daytot.p + 2 * day, 2 * sizeof(long long), cudaMemcpyDeviceToHost, strm));
+    CU(cudaEventRecord(ctx->day_events[day], strm));
+    return 0;
+}
+
+template <class T>
+static int hbuf_grow(pkb_ctx* ctx, HBuf<T>& b, size_t used, size_t newcap) {
+    HBuf<T> nb;
+    TRY(nb.alloc(ctx, newcap));
+    if (used) memcpy(nb.p, b.p, used * sizeof(T));
+    std::swap(nb.p, b.p);
+    std::swap(nb.n, b.n);
+    std::swap(nb.ctx, b.ctx);
+    return 0;       // nb's destructor returns the old block to the pool
+}
+
+static int coo_collect(pkb_ctx* ctx, pkb_result* r) {
     const int D = r->D, nd = r->ndays;
-    DBuf<int>& rownnz = r->rownnz;
-    DBuf<long long> rowoff, dayoff;
-    if (!rownnz.p) TRY(rownnz.alloc(ctx, (size_t)nd * D));
-    TRY(rowoff.alloc(ctx, (size_t)nd * D));
-    TRY(dayoff.alloc(ctx, nd + 1));
-    // count the rows of the days the emission kernels did not already count (runs of consecutive days)
-    for (int d0 = 0; d0 < nd;) {
-        if (d0 < (int)r->counted.size() && r->counted[d0]) { ++d0; continue; }
-        int d1 = d0;
-        while (d1 < nd && !(d1 < (int)r->counted.size() && r->counted[d1])) ++d1;
-        LAUNCH(ctx, k_row_nnz, (d1 - d0) * D, 256, 0, (const double*)(r->dense.p + (size_t)D * D * d0), D, rownnz.p + (size_t)D * d0);
-        d0 = d1;
-    }
-    LAUNCH(ctx, k_row_scan, 1, 1024, 0, (const int*)rownnz.p, D, nd, rowoff.p, dayoff.p);
+    const size_t nD = (size_t)D * D;
     TRY(r->dayoff.alloc(ctx, nd + 1));
-    CU(cudaMemcpyAsync(r->dayoff.p, dayoff.p, sizeof(long long) * (nd + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(sync_check(ctx, "COO sizing"));
-    const long long total = r->dayoff.p[nd];
-    DBuf<int> drows, dcols;
-    DBuf<double> dvals;
-    TRY(drows.alloc(ctx, total));
-    TRY(dcols.alloc(ctx, total));
-    TRY(dvals.alloc(ctx, total));
-    LAUNCH(ctx, k_coo_write, nd * D, 256, 0, (const double*)r->dense.p, D, (const long long*)rowoff.p, drows.p, dcols.p, dvals.p);
-    TRY(r->rows.alloc(ctx, total));
-    TRY(r->cols.alloc(ctx, total));
-    TRY(r->vals.alloc(ctx, total));
-    if (total > 0) {
-        CU(cudaMemcpyAsync(r->rows.p, drows.p, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->cols.p, dcols.p, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->vals.p, dvals.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    r->dayoff.p[0] = 0;
+    size_t cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)nd * D * 64);
+    TRY(r->rows.alloc(ctx, cap));
+    TRY(r->cols.alloc(ctx, cap));
+    TRY(r->vals.alloc(ctx, cap));
+    // one day's triplets at a time through a device staging area (worst case D*D entries)
+    DBuf<int> srow, scol;
+    DBuf<double> sval;
+    TRY(srow.alloc(ctx, nD));
+    TRY(scol.alloc(ctx, nD));
+    TRY(sval.alloc(ctx, nD));
+    const bool dbg = getenv("PKB_DEBUG_COO") != nullptr;
+    const auto t00 = std::chrono::steady_clock::now();
+    for (int day = 0; day < nd; ++day) {
+        cudaError_t e = cudaEventSynchronize(ctx->day_events[day]);
+        if (dbg && (day % 10 == 0 || day == nd - 1))
+            fprintf(stderr, "coo day %d ready at %.2f ms\n", day, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
+        if (e != cudaSuccess) return fail(PKB_ECUDA, "waiting for day %d of the solve failed: %s", day, cudaGetErrorString(e));
+        const long long tot = r->tot_host.p[2 * day + 1];
+        const size_t off = (size_t)r->dayoff.p[day];
+        r->dayoff.p[day + 1] = (long long)(off + tot);
+        if (off + tot > cap) {
+            CU(cudaStreamSynchronize(ctx->cp));                   // copies into the old blocks must have landed
+            const size_t newcap = std::max<size_t>(off + tot + (off + tot) / 4, cap * 2);
+            TRY(hbuf_grow(ctx, r->rows, off, newcap));
+            TRY(hbuf_grow(ctx, r->cols, off, newcap));
+            TRY(hbuf_grow(ctx, r->vals, off, newcap));
+            cap = newcap;
+        }
+        CU(cudaStreamWaitEvent(ctx->cp, ctx->day_events[day], 0));
+        LAUNCH_ON(ctx, ctx->cp, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
+                  (const long long*)(r->rowoff.p + (size_t)D * day), srow.p, scol.p, sval.p);
+        if (tot > 0) {
+            CU(cudaMemcpyAsync(r->rows.p + off, srow.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->cols.p + off, scol.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->vals.p + off, sval.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+        }
     }
-    TRY(sync_check(ctx, "COO copy"));
+    if (dbg) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "chain done at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
+        cudaStreamSynchronize(ctx->cp);
+        fprintf(stderr, "copies done at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
+    }
+    CU(cudaEventRecord(ctx->ev_cp, ctx->cp));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp, 0));
+    ctx->coo_hint = (size_t)r->dayoff.p[nd];
     r->have_coo = true;
     return 0;
 }
@@ -1342,7 +1409,18 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
     TRY(res->dense.alloc(ctx, nD * nd));
     res->counted.assign(nd, 0);
-    if (a->want_coo) TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
+    if (a->want_coo) {
+        TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
+        TRY(res->rowoff.alloc(ctx, (size_t)nd * D));
+        TRY(res->daytot.alloc(ctx, 2 * (size_t)nd));
+        TRY(res->tot_host.alloc(ctx, 2 * (size_t)nd));
+        while ((int)ctx->day_events.size() < nd) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->day_events.push_back(e);
+        }
+    }
+    auto emitted = [&](int day, cudaStream_t strm) -> int { return a->want_coo ? coo_day_ready(ctx, res, day, strm) : 0; };
     DBuf<StepMeta> dsm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
@@ -1401,6 +1479,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
+        TRY(emitted(0, ctx->stream));
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
             const int* wp = step_window(n);
             cplx* krt = nullptr;
@@ -1416,6 +1495,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
                       res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
             if (a->want_coo) res->counted[n] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
+            TRY(emitted(n, ctx->aux));
         }
         for (int i = 0; i < 2; ++i)
             if (nd - 1 - i >= 1) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[(nd - 1 - i) & 1], 0));
@@ -1443,6 +1523,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         ca.n = 1; ca.S[0] = ch->S[ch->cur].p; ca.w[0] = a->r_dist[0];
         LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, rn * (1 - a->r_dist[0]), 1, negval, 1, res->dense.p, (double*)nullptr);
+        TRY(emitted(0, ctx->stream));
         // release days (CalcSol.py:296-306)
         for (int day = 1; day < rd; ++day) {
             TRY(set_state_kernel_dev(ch, kern(day), ks->W, krad(day)));
@@ -1455,6 +1536,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
             }
             ca.n = day + 1;
             LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, (1 - wsum) * rn, 1, negval, 0, res->dense.p + nD * day, (double*)nullptr);
+            TRY(emitted(day, ctx->stream));
         }
         // post-release days (CalcSol.py:308-323)
         for (int n = rd; n < nd; ++n) {
@@ -1470,14 +1552,15 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
             }
             ca.n = rd;
             LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, 0.0, 0, negval, 0, res->dense.p + nD * n, (double*)nullptr);
+            TRY(emitted(n, ctx->stream));
         }
     }
-    CU(cudaMemcpyAsync(res->smeta.data(), dsm.p, sizeof(StepMeta) * nd, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    TRY(sync_check(ctx, "pkb_solve chain"));
 
-    // ---- outputs -----------------------------------------------------------
-    if (a->want_coo) TRY(build_coo(ctx, res));
+    // ---- outputs (the chain is enqueued, not finished: compaction and D2H overlap it) ----
+    if (a->want_coo) TRY(coo_collect(ctx, res));
+    // (pageable destination: this copy blocks the host until the chain has finished, so it comes last)
+    CU(cudaMemcpyAsync(res->smeta.data(), dsm.p, sizeof(StepMeta) * nd, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     TRY(sync_check(ctx, "pkb_solve outputs"));
     float ms = 0.f;
