@@ -759,10 +759,11 @@ __global__ void __launch_bounds__(1024) k_row_scan(const int* __restrict__ rownn
 }
 // grid = ndays*D, block = 256.  Each thread owns a contiguous segment of the row: count its
 // non-zeros, one block-wide exclusive scan of the 256 counts, ordered write.
-__global__ void k_coo_write(const double* __restrict__ G, int D, const long long* __restrict__ rowoff, int* __restrict__ rows,
-                            int* __restrict__ cols, double* __restrict__ vals) {
+__global__ void k_coo_write(const double* __restrict__ G, int D, const long long* __restrict__ rowoff, const int* __restrict__ rownnz,
+                            int* __restrict__ rows, int* __restrict__ cols, double* __restrict__ vals) {
     PKB_SHARED(int, cnt, 256);
     const int r = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    if (rownnz[r] == 0) return;        // thresholded solutions are mostly empty rows: do not even read them
     const int seg = (D + T - 1) / T;
     const int c0 = tid * seg, c1 = c0 + seg < D ? c0 + seg : D;
     const double* row = G + (size_t)r * D;

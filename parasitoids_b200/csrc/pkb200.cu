@@ -1319,7 +1319,7 @@ static int coo_collect(pkb_ctx* ctx, pkb_result* r) {
         }
         CU(cudaStreamWaitEvent(ctx->cp, ctx->day_events[day], 0));
         LAUNCH_ON(ctx, ctx->cp, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
-                  (const long long*)(r->rowoff.p + (size_t)D * day), srow.p, scol.p, sval.p);
+                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), srow.p, scol.p, sval.p);
         if (tot > 0) {
             CU(cudaMemcpyAsync(r->rows.p + off, srow.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
             CU(cudaMemcpyAsync(r->cols.p + off, scol.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
