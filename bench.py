@@ -436,7 +436,8 @@ def main():
 
     # ---- per-kernel roofline (rank 0) --------------------------------------------
     P, N, D, flags, radii = info
-    kernels = ['k_rows_fwd', 'k_cols', 'k_rows_inv', 'k_kernel_rows', 'k_kernel_rows_batch', 'k_emit_dense', 'k_step_finalize',
+    kernels = ['k_rows_fwd', 'k_cols', 'k_rows_inv', 'k_rows_fwd_win', 'k_cols_win', 'k_rows_inv_win', 'k_kernel_rows_win',
+               'k_kernel_rows', 'k_kernel_rows_batch', 'k_emit_dense', 'k_step_finalize',
                'k_zero_pad', 'k_period', 'k_day_finalize', 'k_drift', 'k_hprob', 'k_bvn_setup', 'k_copy_domain', 'k_place_kernel',
                'k_stencil', 'k_row_stats']
     prof = {k: ctx.profile_get(k) for k in kernels}
@@ -445,7 +446,9 @@ def main():
     nsteps_chain = prof['k_cols'][0]
     peak, peak_src = peaks()
     dom = max(chain_k, key=lambda k: prof[k][1])
-    # algorithmic bytes per launch of each chain kernel = its share of B_day
+    # algorithmic bytes per launch of each chain kernel = its share of B_day; the
+    # per-kernel roofline is taken on the whole-torus launches only (support-window steps run the same
+    # kernels on a smaller torus and are accounted separately as k_*_win)
     share = {'k_rows_fwd': 8.0 * P * P,                      # kernel/state row pass: write one half-spectrum
              'k_cols': 40.0 * P * P,                         # column pass + multiply (24 P^2) and inverse column pass (16 P^2)
              'k_rows_inv': 16.0 * P * P,                     # inverse row pass: read half-spectrum, write real grid

@@ -255,6 +255,14 @@ static void prof_collect(pkb_ctx* ctx) {
         (ctx)->launches++;                                                    \
     } while (0)
 #define LAUNCH(ctx, kern, grid, block, smem, ...) LAUNCH_ON(ctx, (ctx)->stream, kern, grid, block, smem, __VA_ARGS__)
+// same launch, accounted under another name in the per-kernel profile (support-window steps)
+#define LAUNCH_AS(ctx, name, kern, grid, block, smem, ...)                    \
+    do {                                                                      \
+        if ((ctx)->prof_on) prof_begin((ctx), (name), (ctx)->stream);         \
+        PKB_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);      \
+        if ((ctx)->prof_on) prof_end((ctx), (ctx)->stream);                   \
+        (ctx)->launches++;                                                    \
+    } while (0)
 
 static int check_launches(pkb_ctx* ctx, const char* where) {
     cudaError_t e = cudaGetLastError();
@@ -1020,11 +1028,20 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     const int rows_in = win ? d.wn : d.P;
     if ((size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads > ch->cscr_per_cta)
         return fail(PKB_ELIMIT, "column scratch too small for torus side %d", d.N);
+    const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
+    if (win) {
+        LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
+        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
+        LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
+                  m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan);
+        LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
+        return 0;
+    }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
     LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
            ch->Wt.p, ch->cscr.p, plan);
-    const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
            ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
     return 0;
