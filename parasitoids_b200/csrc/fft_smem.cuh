@@ -30,8 +30,9 @@ struct FftPlan {
     int N;
     int nstage;
     int ntw;                    // entries of twb (all stages)
+    int threads;                // row kernels: threads per CTA (fewer when more CTAs fit an SM, see pkb200.cu:get_plan)
     int cols_threads, cols_kb;  // k_cols geometry: threads per column, last-stage blocks per thread
-    int grid_rows, grid_cols;   // persistent grid sizes (host side): resident CTAs per SM (at most 2) x SM count
+    int grid_rows, grid_cols;   // persistent grid sizes (host side): resident CTAs per SM (at most 4) x SM count
     unsigned long long rpack;   // radix of stage s in bits [4s, 4s+4)
     // device tables
     const cplx* twb;            // stage after stage: exp(-2 pi i k / M_s), k in [0, M_s / R_s)

@@ -525,11 +525,24 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     fac.erase(fac.begin() + last);
     fac.push_back(rl);
     if ((int)fac.size() > PKB_FFT_MAX_STAGES) return fail(PKB_ELIMIT, "FFT length %d needs too many stages", N);
+    // Threads per CTA.  The pure transform runs faster with MORE resident CTAs per SM (independent
+    // CTAs sit in different phases and hide each other's shared-memory latency and barriers: core
+    // benchmark at N = 2352, 2 x 256 threads 6.1 k cycles per transform, 4 x 128 threads 4.8 k), and
+    // the register file holds 512 threads of these kernels; so the CTA shrinks as more transforms fit
+    // into shared memory: 2 x 256, 3 x 160 or 4 x 128 threads.
+    {
+        int ntw = 0, M = N;
+        for (int r : fac) { ntw += M / r; M /= r; }
+        const size_t foot = (size_t)(N + ntw) * sizeof(cplx) + 1024;      // + the per-CTA reservation
+        const int fit = (int)(233472 / foot);
+        p.threads = std::min(ctx->fft_threads, fit >= 4 ? 128 : (fit == 3 ? 160 : 256));
+    }
     // k_cols geometry: threads per column and last-stage blocks per thread
     {
         const int nbl = N / rl;
         int best_t = 0, best_kb = 0;
-        for (int t = 32; t <= PKB_COLS_TMAX; t += 32) {
+        // at least 4 warps per column whenever there is work for them (a 1-warp CTA would "waste" the least)
+        for (int t = nbl >= 128 ? 128 : 32; t <= std::min(PKB_COLS_TMAX, std::max(128, p.threads)); t += 32) {
             const int kb = (nbl + t - 1) / t;
             // least idle work first, then the most threads
             if (!best_t || t * kb < best_t * best_kb || (t * kb == best_t * best_kb && t > best_t)) { best_t = t; best_kb = kb; }
@@ -582,15 +595,14 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     p.perm = rec.perm;
     p.grid_rows = p.grid_cols = 0;
     if (fft_smem_bytes(p) <= (size_t)ctx->max_smem) {
-        // resident CTAs per SM of the persistent kernels at this plan's footprint (capped at 2:
-        // the register file holds two 256-thread CTAs of these kernels)
+        // resident CTAs per SM of the persistent kernels at this plan's footprint (at most 4)
         const size_t sm1 = fft_smem_bytes(p);
         int occ_r = 0, occ_i = 0, occ_c = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, ctx->fft_threads, sm1));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, ctx->fft_threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, p.threads, sm1));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, p.threads, sm1));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols, p.cols_threads, sm1));
-        p.grid_rows = std::min(2, std::min(occ_r, occ_i)) * ctx->sm_count;
-        p.grid_cols = std::min(2, occ_c) * ctx->sm_count;
+        p.grid_rows = std::min(4, std::min(occ_r, occ_i)) * ctx->sm_count;
+        p.grid_cols = std::min(4, occ_c) * ctx->sm_count;
     }
     ctx->plans[N] = rec;
     *out = p;
@@ -608,7 +620,7 @@ extern "C" int pkb_debug_fft(pkb_ctx* ctx, int n, const double* in, double* out,
     TRY(a.alloc(ctx, n));
     TRY(b.alloc(ctx, n));
     CU(cudaMemcpyAsync(a.p, in, sizeof(cplx) * n, cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_fft_test, 1, ctx->fft_threads, fft_smem_bytes(plan), a.p, b.p, inverse, plan);
+    LAUNCH(ctx, k_fft_test, 1, plan.threads, fft_smem_bytes(plan), a.p, b.p, inverse, plan);
     CU(cudaMemcpyAsync(out, b.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx, "pkb_debug_fft");
 }
@@ -937,7 +949,7 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ch->grid_cols = ch->plan.grid_cols;
     // k_cols parking space: any plan up to this torus side needs at most N + R_last * threads slots per CTA
     ch->cscr_per_cta = (size_t)d.N + 21 * 256 + 256;
-    TRY(ch->cscr.alloc(ctx, (size_t)2 * ctx->sm_count * ch->cscr_per_cta));
+    TRY(ch->cscr.alloc(ctx, (size_t)4 * ctx->sm_count * ch->cscr_per_cta));
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
@@ -1023,7 +1035,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         krt = ch->Krt.p;
     }
     // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
-    const int T = ctx->fft_threads;
+    const int T = plan.threads;
     const size_t sm1 = fft_smem_bytes(plan);
     const int rows_in = win ? d.wn : d.P;
     if ((size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads > ch->cscr_per_cta)
@@ -1464,7 +1476,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
                 kb.m[i] = krad(n + i);
                 kb.job0[i + 1] = kb.job0[i] + (kb.m[i] > ctx->stencil_max_radius ? kb.m[i] + 1 : 0);
             }
-            LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[kb.nd], ch->grid_rows), ctx->fft_threads, fft_smem_bytes(ch->plan), kern(n),
+            LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[kb.nd], ch->grid_rows), ch->plan.threads, fft_smem_bytes(ch->plan), kern(n),
                    nW, ks->W, kb, d, krt_all.p, krt_stride, ch->plan);
         }
         *out = krt_all.p + krt_stride * (n - kr_first);
