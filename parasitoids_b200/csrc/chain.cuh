@@ -328,9 +328,9 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
                 for (int i = tid; i < N; i += T) x[i] = ld(i);
                 __syncthreads();
             } else {
-                fft_stage_dispatch<false>(R0, N, N, tws, tid, T, ld, SmemStore{x});
+                fft_stage_dispatch<false, true>(R0, N, N, plan.tw0, tid, T, ld, SmemStore{x});
                 __syncthreads();
-                fft_fwd_stages(x, tws, plan, 1, L - 1, N / R0, N / R0, tid, T);
+                fft_fwd_stages(x, tws, plan, 1, L - 1, N / R0, 0, tid, T);
             }
 #define PKB_CALL_(RR) cols_final<RR>(x, myscr, tid, T, nbl, phase)
             PKB_RADIX_SWITCH(RL, PKB_CALL_)
@@ -341,7 +341,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
             for (int i = tid; i < N; i += T) st_out(i, x[i]);
         } else {
             fft_inv_stages(x, tws, plan, L - 1, 1, RL, off_last, tid, T);
-            fft_stage_dispatch<true>(R0, N, N, tws, tid, T, SmemLoad{x}, st_out);
+            fft_stage_dispatch<true, true>(R0, N, N, plan.tw0, tid, T, SmemLoad{x}, st_out);
         }
         __syncthreads();
     }
@@ -356,7 +356,10 @@ struct RowStats {
 };
 
 // Block reduction of 8 per-thread values: entries with (i & 3) == 0 or 3 by max, the
-// others by sum.  Result valid in thread i (i < 8) of warp 0.  red: 8 * 32 doubles.
+// others by sum.  Result valid in thread i (i < 8) of warp 0.  red: PKB_RED_DOUBLES doubles
+// (8 stats x up to 8 warps, then 8 results); the FFT kernels alias it onto the start of their
+// (then idle) transform buffer so that they carry no static shared memory.
+#define PKB_RED_DOUBLES 72
 __device__ __forceinline__ double block_reduce8(double (&v)[8], double* red, int tid, int T) {
     const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
 #pragma unroll
@@ -367,14 +370,14 @@ __device__ __forceinline__ double block_reduce8(double (&v)[8], double* red, int
             const double t = __shfl_down_sync(0xffffffffu, v[i], o);
             v[i] = ismax ? fmax(v[i], t) : v[i] + t;
         }
-        if (lane == 0) red[i * 32 + wid] = v[i];
+        if (lane == 0) red[i * 8 + wid] = v[i];
     }
     __syncthreads();
     double r = 0.0;
     if (tid < 8) {
         const bool ismax = (tid & 3) == 0 || (tid & 3) == 3;
-        r = red[tid * 32];
-        for (int w = 1; w < nw; ++w) r = ismax ? fmax(r, red[tid * 32 + w]) : r + red[tid * 32 + w];
+        r = red[tid * 8];
+        for (int w = 1; w < nw; ++w) r = ismax ? fmax(r, red[tid * 8 + w]) : r + red[tid * 8 + w];
     }
     return r;
 }
@@ -397,10 +400,10 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
     }
     __syncthreads();
     const double rr = block_reduce8(st, red, tid, T);
-    if (tid < 4) red[256 + tid] = rr;
+    if (tid < 4) red[64 + tid] = rr;
     __syncthreads();
     if (tid == 0) {
-        const double bp = red[256], bs = red[257], bc = red[258], bm = -red[259];
+        const double bp = red[64], bs = red[65], bc = red[66], bm = -red[67];
         const int flag = bp > 1e-8 ? 1 : 0;          // CalcSol.py:36-37
         meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->vmin = bm;
         meta->add = (1.0 - bs) / bc;                 // CalcSol.py:135
@@ -416,7 +419,7 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
 // in the last CTA of k_rows_inv)
 __global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta,
                                 int apply_trunc) {
-    PKB_SHARED(double, red, 264);
+    PKB_SHARED(double, red, PKB_RED_DOUBLES);
     step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x);
 }
 
@@ -449,10 +452,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc) {
     PKB_DYN_SMEM(raw);
-    PKB_SHARED(double, red, 264);
-    PKB_SHARED(int, last, 1);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
+    // reduction scratch and the "last CTA" flag live at the start of the transform buffer, which is
+    // idle whenever they are used (after a job's output loop; fft_smem_bytes() >= 1 KB)
+    double* red = reinterpret_cast<double*>(raw);
+    int* last = reinterpret_cast<int*>(red + PKB_RED_DOUBLES);
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
@@ -568,11 +573,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                 }
             }
         }
+        __syncthreads();                               // every thread is done reading x: reuse it as scratch
         const double r = block_reduce8(st, red, tid, T);
-        if (tid < 8) red[256 + tid] = r;
+        if (tid < 8) red[64 + tid] = r;
         __syncthreads();
         if (tid == 0 || (tid == 1 && out_b >= 0)) {
-            const double* q = red + 256 + 4 * tid;
+            const double* q = red + 64 + 4 * tid;
             RowStats rs;
             rs.padmax = q[0]; rs.ksum = q[1]; rs.kcnt = (int)q[2]; rs.vmin = -q[3]; rs.pad_ = 0;
             rstat[tid ? out_b : out_a] = rs;

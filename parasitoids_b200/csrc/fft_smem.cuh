@@ -29,13 +29,16 @@ namespace pkb {
 struct FftPlan {
     int N;
     int nstage;
-    int ntw;                    // entries of twb (all stages)
+    int ntw;                    // entries of twb (stages 1 .. nstage-1)
     int threads;                // row kernels: threads per CTA (fewer when more CTAs fit an SM, see pkb200.cu:get_plan)
     int cols_threads, cols_kb;  // k_cols geometry: threads per column, last-stage blocks per thread
     int grid_rows, grid_cols;   // persistent grid sizes (host side): resident CTAs per SM (at most 4) x SM count
     unsigned long long rpack;   // radix of stage s in bits [4s, 4s+4)
     // device tables
-    const cplx* twb;            // stage after stage: exp(-2 pi i k / M_s), k in [0, M_s / R_s)
+    const cplx* tw0;            // stage 0: exp(-2 pi i k / N), k in [0, N / R_0) -- read from global memory (L2): the
+                                // stage-0 inputs (forward) come from global memory anyway, and keeping this largest
+                                // table out of shared memory is what lets a third 4704-point transform fit an SM
+    const cplx* twb;            // stages 1.., one after the other: exp(-2 pi i k / M_s), k in [0, M_s / R_s) -> shared memory
     const int2* pair;           // pair[k] = (pos(k), pos((N - k) mod N)), pos = index of bin k after the forward pass
     const int* perm;            // perm[k] = pos(k)
 };
@@ -46,8 +49,12 @@ __host__ __device__ __forceinline__ int plan_radix(const FftPlan& p, int s) { re
 __device__ __forceinline__ int fast_div(int j, int d, unsigned magic) { return d == 1 ? j : (int)__umulhi((unsigned)j, magic); }
 __device__ __forceinline__ unsigned div_magic(int d) { return d == 1 ? 0u : 0xFFFFFFFFu / (unsigned)d + 1u; }
 
-// shared-memory footprint (bytes) of one transform: data + base twiddles
-__host__ __device__ __forceinline__ size_t fft_smem_bytes(const FftPlan& p) { return (size_t)(p.N + p.ntw) * sizeof(cplx); }
+// shared-memory footprint (bytes) of one transform: data + base twiddles of the inner stages
+// (never below 1 KB: the row kernels reuse the start of the buffer as reduction scratch)
+__host__ __device__ __forceinline__ size_t fft_smem_bytes(const FftPlan& p) {
+    const size_t b = (size_t)(p.N + p.ntw) * sizeof(cplx);
+    return b < 1024 ? 1024 : b;
+}
 
 // ---- compile-time twiddles -----------------------------------------------------
 // a * exp(-2 pi i J / R)
@@ -222,7 +229,7 @@ __device__ __forceinline__ void twiddle_apply(cplx (&v)[R], cplx w1) {
 // twk: this stage's base twiddles exp(-2 pi i k / M), k in [0, M/R)  (shared memory)
 // Inputs come from ld(index) and outputs go to st(index, value): shared memory for
 // inner stages, global memory for the first forward / last inverse stage.
-template <int R, bool INV, class Load, class Store>
+template <int R, bool INV, bool GTW, class Load, class Store>
 __device__ __forceinline__ void fft_stage(int N, int M, const cplx* twk, int tid, int T, Load ld, Store st) {
     const int Ms = M / R;
     const int nb = N / R;
@@ -236,7 +243,7 @@ __device__ __forceinline__ void fft_stage(int N, int M, const cplx* twk, int tid
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = ld(base + q * Ms);
         if (Ms > 1) {
-            const cplx w1 = twk[k];
+            const cplx w1 = GTW ? __ldg(&twk[k]) : twk[k];
             if (!INV) {
                 dft<R>(v);
                 twiddle_apply<R, false>(v, w1);
@@ -267,9 +274,10 @@ __device__ __forceinline__ void fft_stage(int N, int M, const cplx* twk, int tid
         default: { CALL(12); } break;        \
     }
 
-template <bool INV, class Load, class Store>
+// GTW: twk points to global memory (stage 0) instead of shared memory
+template <bool INV, bool GTW, class Load, class Store>
 __device__ __forceinline__ void fft_stage_dispatch(int R, int N, int M, const cplx* twk, int tid, int T, Load ld, Store st) {
-#define PKB_CALL_(RR) fft_stage<RR, INV>(N, M, twk, tid, T, ld, st)
+#define PKB_CALL_(RR) fft_stage<RR, INV, GTW>(N, M, twk, tid, T, ld, st)
     PKB_RADIX_SWITCH(R, PKB_CALL_)
 #undef PKB_CALL_
 }
@@ -289,10 +297,10 @@ __device__ __forceinline__ void fft_load_twiddles(cplx* tws, const FftPlan& p, i
     for (int i = tid; i < p.ntw; i += T) tws[i] = p.twb[i];
 }
 
-// offset of stage s's base table inside twb
+// offset of stage s's (s >= 1) base table inside twb
 __device__ __forceinline__ int fft_tw_offset(const FftPlan& p, int s) {
-    int M = p.N, off = 0;
-    for (int t = 0; t < s; ++t) {
+    int M = p.N / plan_radix(p, 0), off = 0;
+    for (int t = 1; t < s; ++t) {
         const int R = plan_radix(p, t);
         off += M / R;
         M /= R;
@@ -308,7 +316,7 @@ __device__ __forceinline__ void fft_fwd_stages(cplx* x, const cplx* tws, const F
     int M = M0, off = off0;
     for (int s = s0; s < s1; ++s) {
         const int R = plan_radix(p, s);
-        fft_stage_dispatch<false>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
+        fft_stage_dispatch<false, false>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
         off += M / R;
         M /= R;
         if (final_sync || s + 1 < s1) __syncthreads();
@@ -323,7 +331,7 @@ __device__ __forceinline__ void fft_inv_stages(cplx* x, const cplx* tws, const F
         const int R = plan_radix(p, s);
         M *= R;
         off -= M / R;
-        fft_stage_dispatch<true>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
+        fft_stage_dispatch<true, false>(R, p.N, M, tws + off, tid, T, SmemLoad{x}, SmemStore{x});
         __syncthreads();
     }
 }
@@ -333,9 +341,9 @@ __device__ __forceinline__ void fft_inv_stages(cplx* x, const cplx* tws, const F
 template <class Load>
 __device__ __forceinline__ void fft_forward_from(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Load ld, bool final_sync = true) {
     const int R0 = plan_radix(p, 0);
-    fft_stage_dispatch<false>(R0, p.N, p.N, tws, tid, T, ld, SmemStore{x});
+    fft_stage_dispatch<false, true>(R0, p.N, p.N, p.tw0, tid, T, ld, SmemStore{x});
     if (final_sync || p.nstage > 1) __syncthreads();
-    fft_fwd_stages(x, tws, p, 1, p.nstage, p.N / R0, p.N / R0, tid, T, final_sync);
+    fft_fwd_stages(x, tws, p, 1, p.nstage, p.N / R0, 0, tid, T, final_sync);
 }
 
 // Whole inverse transform (unnormalised, result = N * ifft) with the last stage
@@ -344,7 +352,7 @@ template <class Store>
 __device__ __forceinline__ void fft_inverse_to(cplx* x, const cplx* tws, const FftPlan& p, int tid, int T, Store st) {
     const int R0 = plan_radix(p, 0);
     fft_inv_stages(x, tws, p, p.nstage, 1, 1, p.ntw, tid, T);
-    fft_stage_dispatch<true>(R0, p.N, p.N, tws, tid, T, SmemLoad{x}, st);
+    fft_stage_dispatch<true, true>(R0, p.N, p.N, p.tw0, tid, T, SmemLoad{x}, st);
 }
 
 }  // namespace pkb

@@ -64,6 +64,7 @@ extern "C" int pkb_version(void) { return 100; }
 // ---------------------------------------------------------------------------
 struct PlanRec {
     FftPlan plan;
+    cplx* tw0;
     cplx* twb;
     int2* pair;
     int* perm;
@@ -350,6 +351,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->plans) {
+        cudaFree(kv.second.tw0);
         cudaFree(kv.second.twb);
         cudaFree(kv.second.pair);
         cudaFree(kv.second.perm);
@@ -531,21 +533,31 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     // the register file holds 512 threads of these kernels; so the CTA shrinks as more transforms fit
     // into shared memory: 2 x 256, 3 x 160 or 4 x 128 threads.
     {
-        int ntw = 0, M = N;
-        for (int r : fac) { ntw += M / r; M /= r; }
+        int ntw = 0, M = N / fac[0];
+        for (size_t i = 1; i < fac.size(); ++i) { ntw += M / fac[i]; M /= fac[i]; }
         const size_t foot = (size_t)(N + ntw) * sizeof(cplx) + 1024;      // + the per-CTA reservation
         const int fit = (int)(233472 / foot);
         p.threads = std::min(ctx->fft_threads, fit >= 4 ? 128 : (fit == 3 ? 160 : 256));
+        if (const char* env = getenv("PKB_FFT_T")) {          // tuning hook
+            const int t = atoi(env);
+            if (t >= 32 && t <= 256 && t % 32 == 0) p.threads = t;
+        }
     }
     // k_cols geometry: threads per column and last-stage blocks per thread
     {
         const int nbl = N / rl;
         int best_t = 0, best_kb = 0;
         // at least 4 warps per column whenever there is work for them (a 1-warp CTA would "waste" the least)
-        for (int t = nbl >= 128 ? 128 : 32; t <= std::min(PKB_COLS_TMAX, std::max(128, p.threads)); t += 32) {
+        // (when three or four transforms fit an SM the column kernel simply takes the row kernels' CTA size:
+        // measured at N = 4704, 3 x 160 threads 306 us against 313 us for 3 x 128 and 326 us for 2 x 224)
+        for (int t = p.threads < 256 ? p.threads : (nbl >= 128 ? 128 : 32); t <= std::min(PKB_COLS_TMAX, p.threads); t += 32) {
             const int kb = (nbl + t - 1) / t;
             // least idle work first, then the most threads
             if (!best_t || t * kb < best_t * best_kb || (t * kb == best_t * best_kb && t > best_t)) { best_t = t; best_kb = kb; }
+        }
+        if (const char* env = getenv("PKB_COLS_T")) {         // tuning hook
+            const int t = atoi(env);
+            if (t >= 32 && t <= PKB_COLS_TMAX && t % 32 == 0) { best_t = t; best_kb = (nbl + t - 1) / t; }
         }
         p.cols_threads = best_t;
         p.cols_kb = best_kb;
@@ -555,21 +567,22 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         p.rpack |= (unsigned long long)r << (4 * p.nstage);
         ++p.nstage;
     }
-    // base twiddles of every stage: exp(-2 pi i k / M_s), k < M_s / R_s
+    // base twiddles exp(-2 pi i k / M_s), k < M_s / R_s: stage 0 -> tw0 (global), stages 1.. -> twb (shared memory)
     const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
-    std::vector<cplx> twb;
+    std::vector<cplx> tw0, twb;
     {
         int M = N;
         for (int s = 0; s < p.nstage; ++s) {
             const int Ms = M / fac[s];
             for (int k = 0; k < Ms; ++k) {
                 const long double a = -twopi * (long double)k / (long double)M;
-                twb.push_back(cmake((double)cosl(a), (double)sinl(a)));
+                (s == 0 ? tw0 : twb).push_back(cmake((double)cosl(a), (double)sinl(a)));
             }
             M = Ms;
         }
+        if (twb.empty()) twb.push_back(cmake(1.0, 0.0));
     }
-    p.ntw = (int)twb.size();
+    p.ntw = p.nstage > 1 ? (int)twb.size() : 0;
     std::vector<int> perm(N);
     for (int k = 0; k < N; ++k) {
         int f = k, M = N, pos = 0;
@@ -583,6 +596,9 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     }
     std::vector<int2> pair(N);
     for (int k = 0; k < N; ++k) pair[k] = make_int2(perm[k], perm[(N - k) % N]);
+    CU(cudaMalloc((void**)&rec.tw0, sizeof(cplx) * tw0.size()));
+    CU(cudaMemcpy(rec.tw0, tw0.data(), sizeof(cplx) * tw0.size(), cudaMemcpyHostToDevice));
+    p.tw0 = rec.tw0;
     CU(cudaMalloc((void**)&rec.twb, sizeof(cplx) * twb.size()));
     CU(cudaMalloc((void**)&rec.pair, sizeof(int2) * (N + 2)));
     CU(cudaMemset(rec.pair, 0, sizeof(int2) * (N + 2)));

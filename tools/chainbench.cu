@@ -20,11 +20,10 @@ __global__ void PKB_ROWS_LB k_fft_core(cplx* out, int reps, FftPlan plan) {
     fft_load_twiddles(tws, plan, tid, T);
     for (int i = tid; i < plan.N; i += T) x[i] = cmake(1.0 / (i + 1), 0.5 / (i + 2));
     __syncthreads();
+    const double sc = 1.0 / plan.N;
     for (int r = 0; r < reps; ++r) {
-        fft_fwd_stages(x, tws, plan, 0, plan.nstage, plan.N, 0, tid, T);
-        fft_inv_stages(x, tws, plan, plan.nstage, 0, 1, plan.ntw, tid, T);
-        const double sc = 1.0 / plan.N;
-        for (int i = tid; i < plan.N; i += T) x[i] = cmake(x[i].x * sc, x[i].y * sc);
+        fft_forward_from(x, tws, plan, tid, T, SmemLoad{x});
+        fft_inverse_to(x, tws, plan, tid, T, [&](int i, cplx v) { x[i] = cmake(v.x * sc, v.y * sc); });
         __syncthreads();
     }
     if (tid == 0) out[blockIdx.x] = x[blockIdx.x % plan.N];
