@@ -15,6 +15,7 @@
 #include "chain.cuh"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -76,6 +77,7 @@ struct pkb_ctx {
     cudaStream_t aux;       // side stream: output emission overlapped with the next chain step
     cudaStream_t cp;        // copy stream: per-day COO compaction + D2H while the chain is still running
     std::vector<cudaEvent_t> day_events;
+    std::vector<cudaEvent_t> win_events;
     cudaEvent_t ev_cp;
     size_t coo_hint;        // triplets of the last solve (initial size of the next one's host buffers)
     cudaEvent_t ev_step[2], ev_emit[2];
@@ -368,6 +370,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_emit[i]); }
     for (cudaEvent_t e : ctx->day_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->win_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_cp);
     cudaStreamDestroy(ctx->cp);
     cudaStreamDestroy(ctx->aux);
@@ -1047,8 +1050,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         d.ldK = roundup(2 * m + 1, 2);
         TRY(get_plan(ctx, d.N, &plan));
         if (plan.grid_rows < 1 || plan.grid_cols < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
-        krt_ready = false;          // row spectra prepared for the full torus do not apply
-        krt = ch->Krt.p;
+        if (!krt_ready) krt = ch->Krt.p;     // (spectra prepared for another torus do not apply: callers pass per-window ones)
     }
     // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
     const int T = plan.threads;
@@ -1058,7 +1060,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         return fail(PKB_ELIMIT, "column scratch too small for torus side %d", d.N);
     const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
     if (win) {
-        LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
+        if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
         LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan);
@@ -1520,6 +1522,60 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         return nullptr;
     };
 
+    // Row spectra of the kernels of the window steps: every such step has its own torus, so they
+    // cannot share the batched launch above; they are launched on the side stream now (dry run of
+    // the window bookkeeping) and the chain waits on a per-step event.
+    std::vector<int> win_slot(nd, -1);
+    DBuf<cplx> krt_win;
+    {
+        const int first = a->prob_model ? 1 : a->r_dur;
+        std::vector<std::array<int, 3> > wsteps;     // (day, window side, torus side)
+        if (a->prob_model || a->r_dur == 1) {
+            const int sv_wr0 = wr0, sv_wn = wn, sv_ws = res->window_steps;
+            const bool sv_mode = wmode;
+            for (int n = first; n < nd; ++n) {
+                const int side = wn;
+                if (step_window(n)) wsteps.push_back({n, side, pkb_smooth_len(std::max(2, side + 2 * krad(n)))});
+                if (!wmode) break;
+            }
+            wr0 = sv_wr0; wn = sv_wn; wmode = sv_mode; res->window_steps = sv_ws;
+        }
+        if (!wsteps.empty()) {
+            TRY(krt_win.alloc(ctx, krt_stride * wsteps.size()));
+            while (ctx->win_events.size() < wsteps.size()) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->win_events.push_back(e);
+            }
+            CU(cudaEventRecord(ctx->ev_step[0], ctx->stream));            // the kernels exist (phase 1 ran on the main stream)
+            CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[0], 0));
+            for (size_t i = 0; i < wsteps.size(); ++i) {
+                const int n = wsteps[i][0], m = krad(n);
+                ChainDims dw = d;
+                FftPlan pw;
+                dw.N = wsteps[i][2];
+                dw.Nc = dw.N / 2 + 1;
+                dw.ldK = roundup(2 * m + 1, 2);
+                TRY(get_plan(ctx, dw.N, &pw));
+                if (pw.grid_rows < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", dw.N);
+                if (ctx->prof_on) prof_begin(ctx, "k_kernel_rows_win", ctx->aux);
+                PKB_LAUNCH(k_kernel_rows, std::min(m + 1, pw.grid_rows), pw.threads, fft_smem_bytes(pw), ctx->aux, kern(n), ks->W, m, dw,
+                           krt_win.p + krt_stride * i, pw);
+                if (ctx->prof_on) prof_end(ctx, ctx->aux);
+                ctx->launches++;
+                CU(cudaEventRecord(ctx->win_events[i], ctx->aux));
+                win_slot[n] = (int)i;
+            }
+        }
+    }
+    auto window_spectra = [&](int n, cplx** out) -> int {
+        *out = nullptr;
+        if (win_slot[n] < 0) return 0;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->win_events[win_slot[n]], 0));
+        *out = krt_win.p + krt_stride * win_slot[n];
+        return 0;
+    };
+
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
@@ -1529,6 +1585,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
             const int* wp = step_window(n);
             cplx* krt = nullptr;
             if (!wp) TRY(day_spectra(n, &krt));
+            else TRY(window_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp));
@@ -1588,6 +1645,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
             const int* wp = rd == 1 ? step_window(n) : nullptr;
             cplx* kday = nullptr;
             if (!wp) TRY(day_spectra(n, &kday));
+            else TRY(window_spectra(n, &kday));
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
