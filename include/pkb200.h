@@ -196,6 +196,15 @@ typedef struct pkb_solve_args {
 } pkb_solve_args;
 
 int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
+/* Likelihood batch (the call pattern of Bayes_Run.py:204-336, one forward solve per MCMC proposal, for
+ * `nprop` proposals at once): proposals[nprop][15] in the order of the block-updated variables
+ * (Bayes_Run.py:186-187: g_aw g_bw f_a1 f_b1 f_a2 f_b2 sig_x sig_y corr sig_x_l sig_y_l corr_l lam
+ * n_periods mu_r); everything else (wind, domain, release settings) from `base`.  out[nprop][ndays][K]
+ * receives the model at the K (row, col) sample cells -- what popdensity_to_emergence / popdensity_grid
+ * read (Bayes_funcs.py:58-74,167-173); status[nprop][ndays] (may be NULL) the PKB_ST_* bits of every
+ * (proposal, day) kernel.  Kernel construction is batched over groups of proposals. */
+int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells /*[K][2]*/, int K,
+                    double* out, int* status);
 int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape);
 /* number of chain steps that ran on a support-window torus smaller than N (exact: the state is
  * identically zero outside the window while the spread has not reached the domain edge) */

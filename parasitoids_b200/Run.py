@@ -265,12 +265,9 @@ class SolveResult(object):
             pass
 
 
-def solve(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model=True,
-          r_dur=1, r_number=1.0, r_dist=None, r_start=None, want_coo=True, want_dense=False, keep_device=False,
-          wind_device_ptr=None, wind_shape=None, device=None):
-    """Fused forward solve.  ``wind``: ndarray (nd_wind, periods, 3) of
-    consecutive days (or None with ``wind_device_ptr``/``wind_shape`` for a
-    wind array already resident on the device).  Returns a ``SolveResult``."""
+def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur, r_number,
+                r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape):
+    """Fill a ``pkb_solve_args``; returns it with the arrays it points into (keep them alive)."""
     a = _abi.SolveArgs()
     if wind_device_ptr is not None:
         nd_wind, periods = int(wind_shape[0]), int(wind_shape[1])
@@ -294,6 +291,17 @@ def solve(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, ra
     a.want_dense_host = 1 if want_dense else 0
     a.want_coo = 1 if want_coo else 0
     a.keep_dense_device = 1 if keep_device else 0
+    return a, (keep, w)
+
+
+def solve(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model=True,
+          r_dur=1, r_number=1.0, r_dist=None, r_start=None, want_coo=True, want_dense=False, keep_device=False,
+          wind_device_ptr=None, wind_shape=None, device=None):
+    """Fused forward solve.  ``wind``: ndarray (nd_wind, periods, 3) of
+    consecutive days (or None with ``wind_device_ptr``/``wind_shape`` for a
+    wind array already resident on the device).  Returns a ``SolveResult``."""
+    a, keep = _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur,
+                          r_number, r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape)
     h = C.c_void_p()
     _lib.check(_lib.lib().pkb_solve(_lib.ctx(device).h, C.byref(a), C.byref(h)))
     del keep

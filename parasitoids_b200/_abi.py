@@ -89,6 +89,7 @@ _SIGS = {
     'pkb_debug_fft': (C.c_int, [_H, C.c_int, c_double_p, c_double_p, C.c_int]),
     'pkb_smooth_len': (C.c_int, [C.c_int]),
     'pkb_solve': (C.c_int, [_H, C.POINTER(SolveArgs), _HP]),
+    'pkb_solve_batch': (C.c_int, [_H, C.POINTER(SolveArgs), c_double_p, C.c_int, c_int_p, C.c_int, c_double_p, c_int_p]),
     'pkb_result_info': (C.c_int, [_H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'pkb_result_window_steps': (C.c_int, [_H, c_int_p]),
     'pkb_result_day_meta': (C.c_int, [_H, C.c_int, C.POINTER(DayMeta), C.POINTER(StepMeta)]),

@@ -49,6 +49,32 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number, r_dist, r_start, device,
+                 wind_device_ptr, wind_shape, ids):
+    """This rank's proposals through ONE library call (``pkb_solve_batch``: kernel construction
+    batched over groups of proposals, chains back to back on the device-resident kernels)."""
+    import ctypes as C
+    from . import _abi, _lib
+    from . import ParasitoidModel as PM
+    hp, dp, dl, mu_r, n_periods = unpack_proposal(props[0])
+    a, keep = Run._solve_args(wind, ndays, hp, dp, dl, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur, r_number,
+                              r_dist, r_start, False, False, True, wind_device_ptr, wind_shape)
+    props = np.ascontiguousarray(props, dtype=np.float64)
+    n = props.shape[0]
+    out = np.empty((n, ndays, cells.shape[0]))
+    status = np.zeros((n, ndays), dtype=np.int32)
+    _lib.check(_lib.lib().pkb_solve_batch(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells), cells.shape[0],
+                                          _lib.dptr(out), _lib.iptr(status)))
+    del keep
+    # the reference's assertion / warning sites, per (proposal, day) kernel (ParasitoidModel.py:529-599)
+    for i in range(n):
+        for d in np.nonzero(status[i])[0]:
+            meta = _abi.DayMeta()
+            meta.status = int(status[i, d])
+            PM._raise_for_status(meta, int(d), ('proposal', int(ids[i])) + tuple(props[i]))
+    return out
+
+
 def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=False, r_dur=1, r_number=1.0,
                 r_dist=None, r_start=None, device=None, group=None, wind_device_ptr=None, wind_shape=None):
     """Solve every proposal and return the model at ``cells`` for all of them.
@@ -70,15 +96,9 @@ def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=Fal
     mine = shard(B, world, rank)
     per = -(-B // world)                      # padded shard length
     local = np.zeros((per, ndays, K))
-    for slot, b in enumerate(mine):
-        hp, dp, dl, mu_r, n_periods = unpack_proposal(proposals[b])
-        res = Run.solve(wind, ndays, hp, dp, dl, mu_r, n_periods, rad_dist, rad_res, prob_model=prob_model, r_dur=r_dur,
-                        r_number=r_number, r_dist=r_dist, r_start=r_start, want_coo=False, keep_device=True,
-                        wind_device_ptr=wind_device_ptr, wind_shape=wind_shape, device=device)
-        try:
-            local[slot] = res.sample(cells)
-        finally:
-            res.close()
+    if mine:
+        local[:len(mine)] = _solve_shard(wind, proposals[mine], cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number,
+                                         r_dist, r_start, device, wind_device_ptr, wind_shape, mine)
     if world == 1:
         return local[:B]
     import torch

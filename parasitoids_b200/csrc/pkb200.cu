@@ -1386,45 +1386,34 @@ static int coo_collect(pkb_ctx* ctx, pkb_result* r) {
     return 0;
 }
 
-extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out) {
-    if (!ctx || !a || !out || !a->wind) return fail(PKB_EINVAL, "pkb_solve: NULL argument");
-    *out = nullptr;
+static int check_solve_args(const pkb_solve_args* a) {
     if (a->ndays < 1 || a->ndays > a->nd_wind) return fail(PKB_EINVAL, "pkb_solve: ndays %d must be in [1, %d]", a->ndays, a->nd_wind);
     if (!a->prob_model) {
         if (a->r_dur < 1 || a->r_dur > a->ndays) return fail(PKB_EINVAL, "pkb_solve: r_dur %d must be in [1, ndays]", a->r_dur);
         if (a->r_dur > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "pkb_solve: r_dur is limited to %d days", PKB_MAX_COHORTS);
         if (!a->r_dist) return fail(PKB_EINVAL, "pkb_solve: r_dist is NULL");
     }
-    CU(cudaSetDevice(ctx->device));
-    const int nd = a->ndays;
-    const double negval = a->negval > 0 ? a->negval : 1e-8;
-    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    return 0;
+}
 
-    // ---- phase 1 (Run.py:412-425) ------------------------------------------
-    DBuf<double> dwind;
-    const double* wind_dev = a->wind;
-    if (!a->wind_on_device) {
-        const size_t nw = (size_t)a->nd_wind * a->periods * 3;
-        TRY(dwind.alloc(ctx, nw));
-        CU(cudaMemcpyAsync(dwind.p, a->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        wind_dev = dwind.p;
-    }
-    std::vector<pkb_day_args> dargs(nd, a->day);
-    for (int i = 0; i < nd; ++i) {
+// per-day prob_mass arguments of one solve (Run.py:412-425)
+static void solve_day_args(const pkb_solve_args* a, pkb_day_args* dargs) {
+    for (int i = 0; i < a->ndays; ++i) {
+        dargs[i] = a->day;
         dargs[i].wind_day = i;
         dargs[i].single = 0;
         dargs[i].start_time = (!a->prob_model && i == 0 && a->r_start >= 0) ? a->r_start : -1.0;   // Run.py:418-421
     }
-    pkb_kset* ks = nullptr;
-    TRY(kernels_build_dev(ctx, wind_dev, a->nd_wind, a->periods, dargs.data(), nd, 0, &ks));
-    struct KGuard {
-        pkb_kset* k;
-        ~KGuard() { delete k; }
-    } kguard{ks};
+}
+
+// Phase 2 and outputs of one solve whose per-day kernels are problems k0 .. k0 + ndays - 1 of ks.
+static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int k0, pkb_result** out) {
+    const int nd = a->ndays;
+    const double negval = a->negval > 0 ? a->negval : 1e-8;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     int mmax = 0;
-    for (int i = 0; i < nd; ++i) mmax = std::max(mmax, ks->hmeta[i].rad);      // Run.py:426-429
+    for (int i = 0; i < nd; ++i) mmax = std::max(mmax, ks->hmeta[k0 + i].rad);      // Run.py:426-429
     const int D = 2 * ks->rad_res + 1;
 
     pkb_result* res = new pkb_result();
@@ -1438,7 +1427,7 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     res->max_shape = 2 * mmax + 1;
     res->have_coo = false;
     res->window_steps = 0;
-    res->kmeta = ks->hmeta;
+    res->kmeta.assign(ks->hmeta.begin() + k0, ks->hmeta.begin() + k0 + nd);
     res->smeta.assign(nd, StepMeta());
     for (auto& sm : res->smeta) memset(&sm, 0, sizeof sm);
 
@@ -1471,8 +1460,8 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     DBuf<StepMeta> dsm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
-    auto kern = [&](int i) { return (const double*)(ks->acc.p + nW * i); };
-    auto krad = [&](int i) { return ks->hmeta[i].rad; };
+    auto kern = [&](int i) { return (const double*)(ks->acc.p + nW * (k0 + i)); };
+    auto krad = [&](int i) { return ks->hmeta[k0 + i].rad; };
 
     // Row spectra of the daily kernels, a block of days per launch, ahead of the
     // chain (phase 1 left every kernel on the device): off the critical path.
@@ -1674,6 +1663,95 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     if (!a->keep_dense_device && !a->want_dense_host) res->dense.release();
     rguard.r = nullptr;
     *out = res;
+    return 0;
+}
+
+extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out) {
+    if (!ctx || !a || !out || !a->wind) return fail(PKB_EINVAL, "pkb_solve: NULL argument");
+    *out = nullptr;
+    TRY(check_solve_args(a));
+    CU(cudaSetDevice(ctx->device));
+    const int nd = a->ndays;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    // ---- phase 1 (Run.py:412-425) ------------------------------------------
+    DBuf<double> dwind;
+    const double* wind_dev = a->wind;
+    if (!a->wind_on_device) {
+        const size_t nw = (size_t)a->nd_wind * a->periods * 3;
+        TRY(dwind.alloc(ctx, nw));
+        CU(cudaMemcpyAsync(dwind.p, a->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        wind_dev = dwind.p;
+    }
+    std::vector<pkb_day_args> dargs(nd);
+    solve_day_args(a, dargs.data());
+    pkb_kset* ks = nullptr;
+    TRY(kernels_build_dev(ctx, wind_dev, a->nd_wind, a->periods, dargs.data(), nd, 0, &ks));
+    struct KGuard {
+        pkb_kset* k;
+        ~KGuard() { delete k; }
+    } kguard{ks};
+    return solve_chain(ctx, a, ks, 0, out);
+}
+
+// Likelihood batch: `nprop` independent proposals of the same solve (shared wind, domain and release
+// settings; the 15 block variables of Bayes_Run.py:186-196 differ), returning the model at K sample
+// cells for every proposal and day.  Kernel construction is batched over groups of proposals (one
+// launch set for up to PKB_BATCH_GROUP x ndays (proposal, day) problems instead of one per proposal);
+// the chains then run one after the other on those device-resident kernels.
+#define PKB_BATCH_GROUP 32
+extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells, int K,
+                               double* out, int* status) {
+    if (!ctx || !base || !base->wind || !proposals || !cells || !out) return fail(PKB_EINVAL, "pkb_solve_batch: NULL argument");
+    if (nprop < 0 || K < 1) return fail(PKB_EINVAL, "pkb_solve_batch: bad sizes");
+    TRY(check_solve_args(base));
+    CU(cudaSetDevice(ctx->device));
+    const int nd = base->ndays;
+    DBuf<double> dwind;
+    const double* wind_dev = base->wind;
+    if (!base->wind_on_device) {
+        const size_t nw = (size_t)base->nd_wind * base->periods * 3;
+        TRY(dwind.alloc(ctx, nw));
+        CU(cudaMemcpyAsync(dwind.p, base->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        wind_dev = dwind.p;
+    }
+    // bound the group so that the accumulation windows (worst case the whole domain per problem) stay below ~8 GB
+    const size_t dom = 2 * (size_t)base->day.rad_res + 1;
+    int group = (int)std::max<size_t>(1, std::min<size_t>(PKB_BATCH_GROUP, ((size_t)8 << 30) / (dom * dom * sizeof(double) * nd)));
+    for (int p0 = 0; p0 < nprop; p0 += group) {
+        const int np = std::min(group, nprop - p0);
+        std::vector<pkb_solve_args> sa(np, *base);
+        std::vector<pkb_day_args> dargs((size_t)np * nd);
+        for (int p = 0; p < np; ++p) {
+            const double* q = proposals + 15 * (size_t)(p0 + p);      // g_aw g_bw f_a1 f_b1 f_a2 f_b2 sig_x sig_y corr sig_xl sig_yl corr_l lam n_periods mu_r
+            pkb_solve_args& s = sa[p];
+            s.wind = wind_dev;
+            s.wind_on_device = 1;
+            s.day.hparams[0] = q[12];
+            for (int j = 0; j < 6; ++j) s.day.hparams[1 + j] = q[j];
+            for (int j = 0; j < 3; ++j) { s.day.dparams[j] = q[6 + j]; s.day.dlparams[j] = q[9 + j]; }
+            s.day.n_periods = (int)llround(q[13]);
+            s.day.mu_r = q[14];
+            s.want_coo = 0; s.want_dense_host = 0; s.keep_dense_device = 1;
+            solve_day_args(&s, dargs.data() + (size_t)p * nd);
+        }
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        pkb_kset* ks = nullptr;
+        TRY(kernels_build_dev(ctx, wind_dev, base->nd_wind, base->periods, dargs.data(), np * nd, 0, &ks));
+        struct KGuard {
+            pkb_kset* k;
+            ~KGuard() { delete k; }
+        } kguard{ks};
+        if (status)
+            for (int i = 0; i < np * nd; ++i) status[(size_t)p0 * nd + i] = ks->hmeta[i].status;
+        for (int p = 0; p < np; ++p) {
+            pkb_result* r = nullptr;
+            TRY(solve_chain(ctx, &sa[p], ks, p * nd, &r));
+            const int rc = pkb_result_sample(r, cells, K, out + (size_t)(p0 + p) * nd * K);
+            pkb_result_destroy(r);
+            if (rc) return rc;
+        }
+    }
     return 0;
 }
 

@@ -61,6 +61,26 @@ def test_unpack_proposal_order():
         batch.unpack_proposal(DEFAULT[:-1])
 
 
+def test_solve_batch_matches_single_solves(pkb):
+    """pkb_solve_batch (kernel construction batched over proposals) against one
+    Run.solve per proposal sampled at the same cells."""
+    import warnings
+    from parasitoids_b200 import batch
+    w, props = _wind(), _proposals(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        got = batch.solve_batch(w, props, CELLS, **SOLVE_KW)
+        for b in range(5):
+            hp, dp, dl, mu_r, n_periods = batch.unpack_proposal(props[b])
+            res = pkb.Run.solve(w, SOLVE_KW['ndays'], hp, dp, dl, mu_r, n_periods, SOLVE_KW['rad_dist'], SOLVE_KW['rad_res'],
+                                prob_model=False, r_dur=SOLVE_KW['r_dur'], r_number=SOLVE_KW['r_number'], r_start=SOLVE_KW['r_start'],
+                                want_coo=False, keep_device=True)
+            ref = res.sample(CELLS)
+            res.close()
+            assert ((got[b] != 0) != (ref != 0)).sum() == 0
+            assert np.allclose(got[b], ref, rtol=1e-12, atol=1e-15)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
