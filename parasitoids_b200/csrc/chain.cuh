@@ -111,7 +111,7 @@ __device__ __forceinline__ void hermitian_split(cplx zk, cplx zn, cplx& A, cplx&
 #define PKB_UNPACK_U 2   // column PAIRS in flight per thread in the pack / unpack loops (deeper did not help: not latency bound)
 #endif
 #ifndef PKB_PREFETCH
-#define PKB_PREFETCH 1    // bit 0: rows_fwd, bit 1: rows_inv prefetch their next job into L2 (measured: bit 1 is no gain)
+#define PKB_PREFETCH 0    // bit 0: rows_fwd, bit 1: rows_inv prefetch their next job into L2 (measured with 3 CTAs per SM: neither pays)
 #endif
 // column PAIRS in flight per thread in the pack / unpack loops (covers N <= 5120 at 256 threads in one sweep)
 

@@ -913,6 +913,9 @@ extern "C" int pkb_mvn_cdf(pkb_ctx* ctx, double cell_length, const double mu[2],
 // phase 2: the chain
 // ---------------------------------------------------------------------------
 #define PKB_MAX_COHORTS 16
+#ifndef PKB_EMIT_T
+#define PKB_EMIT_T 256     // threads of the side-stream emission CTAs
+#endif
 
 struct pkb_chain {
     pkb_ctx* ctx;
@@ -1582,7 +1585,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
-            LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
+            LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, PKB_EMIT_T, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
                       res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
             if (a->want_coo) res->counted[n] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
