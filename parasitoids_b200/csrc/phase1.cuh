@@ -241,10 +241,10 @@ __device__ __forceinline__ int py_slice_len(int start, int stop, int n) {
 }
 
 // ---------------------------------------------------------------------------
-// grid = (periods, problems), block = 256, dyn smem = (6*nmax + PKB_LATTICE_CAP) doubles
+// grid = (periods, problems), block = 64 / 128 / 256 by lattice size (pkb200.cu), dyn smem = (6*nmax + tile_cap) doubles, tile_cap = min(PKB_LATTICE_CAP, nmax^2)
 // acc: per problem (2*racc+1)^2 window centred on the release cell
 __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
-                         const double* __restrict__ hprob, int periods, int nmax, double* __restrict__ acc, int racc,
+                         const double* __restrict__ hprob, int periods, int nmax, int tile_cap, double* __restrict__ acc, int racc,
                          double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(double, red, 256);
@@ -306,7 +306,7 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
     }
     __syncthreads();
 
-    const int rows_per_tile = PKB_LATTICE_CAP / n - 1;   // cell rows (y) per tile
+    const int rows_per_tile = tile_cap / n - 1;          // cell rows (y) per tile
     const int shift = dp.rad_res - racc;                 // acc window origin in domain coords
     const int W = 2 * racc + 1;
     double* accp = acc + (size_t)prob * W * W;
