@@ -8,6 +8,7 @@ import pytest
 from scipy import signal, sparse
 
 from oracle import cs_oracle as CO
+from oracle import pm_oracle as PO
 import helpers as H
 
 
@@ -335,3 +336,46 @@ def test_window_steps_match_whole_torus_steps(pkb):
             assert ((a != 0) != (b != 0)).sum() == 0
             # population grids are probabilities scaled by r_number
             assert np.abs(a - b).max() <= 1e-15 * kw.get('r_number', 1.0)
+
+
+def _oracle_solve(w, nd, args, rad_res):
+    wind_data = {d: w[d] for d in range(w.shape[0])}     # the whole series: late take-offs of a day drift into the next
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        pmfs = [PO.prob_mass(d, wind_data, *args) for d in range(nd)]
+    D = 2 * rad_res + 1
+    sol = [H.recentre(pmfs[0], rad_res)]
+    if nd > 1:
+        CO.get_solutions(sol, pmfs, list(range(nd)), nd, D, [max(p.shape[0] for p in pmfs)] * 2)
+    return sol
+
+
+def test_fused_solve_edge_cases(pkb):
+    """Degenerate inputs of the fused solve against the oracle: a single day (no chain step at
+    all), dead calm (every kernel is the local-diffusion blob only), and a gale that carries
+    most take-offs out of the domain (loss bookkeeping + renormalisation, ParasitoidModel.py:546-558)."""
+    nd, periods, rad_res, rad_dist = 3, 48, 30, 1500.0
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    calm = np.zeros((nd, periods, 3))
+    gale = np.zeros((nd, periods, 3))
+    gale[:, :, 0] = 2.5
+    gale[:, :, 1] = -1.0
+    gale[:, :, 2] = np.hypot(gale[:, :, 0], gale[:, :, 1])
+    breeze = np.zeros((nd, periods, 3))
+    breeze[:, :, 0] = 0.3 * np.sin(np.linspace(0, 9, nd * periods)).reshape(nd, periods)
+    breeze[:, :, 2] = np.abs(breeze[:, :, 0])
+    for name, w, ndays in (('one day', breeze, 1), ('calm', calm, nd), ('gale', gale, nd)):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res = pkb.Run.solve(w, ndays, *args, want_coo=True, want_dense=True)
+        ref = _oracle_solve(w, ndays, args, rad_res)
+        sols = res.coo_list()
+        assert len(sols) == ndays
+        for d in range(ndays):
+            H.assert_thresholded_parity(res.dense(d), ref[d].toarray(), what='%s day %d' % (name, d))
+            assert abs(sols[d].sum() - 1) < H.MASS
+        res.close()
+    with pytest.raises(pkb._lib.PkbError):
+        pkb.Run.solve(breeze, nd + 1, *args)            # more days than wind
+    with pytest.raises(pkb._lib.PkbError):
+        pkb.Run.solve(breeze, nd, *args, prob_model=False, r_dur=nd + 1)
