@@ -10,22 +10,30 @@
 // 4279 = 11*389), so instead of a length-P transform the step is evaluated as a
 // LINEAR convolution on a 7-smooth torus N >= P + 2m (m = kernel radius) and
 // folded mod P in real space -- identical to the circular convolution mod P in
-// exact arithmetic, for any P.  One step is three streaming passes:
+// exact arithmetic, for any P.  One step is three streaming passes, each a
+// PERSISTENT kernel (grid = resident CTAs per SM x SM count, every CTA loops over
+// its jobs; one job = one transform held in one shared-memory buffer):
 //
 //   k_rows_fwd   real rows of the state  -> half-spectrum rows (two real rows
-//                per complex FFT), written TRANSPOSED (Yt[kc][row])
-//   k_cols       per spectral column: forward FFT, multiply with the kernel's
-//                column spectrum, inverse FFT -- all three fused in shared
-//                memory (Yt -> Wt), columns are contiguous in HBM
+//                per complex FFT), written into the tiled transposed array Yt
+//   k_cols       per spectral column: forward FFT of the kernel column (parked
+//                in an L2-resident scratch), forward FFT of the state column,
+//                product, inverse FFT -- one CTA, one pass over the column
+//                (Yt -> Wt)
 //   k_rows_inv   half-spectrum rows -> real rows, fold mod P, write the new
-//                state and the per-row boundary/threshold statistics
+//                state and the per-row boundary/threshold statistics; the CTA
+//                that finishes last reduces them to the step's flag / sums
 //
-// plus k_kernel_rows (row spectra of the day's kernel), k_step_finalize
-// (flag / sum / count -> control block) and the emit kernels.
+// plus k_kernel_rows(_batch) (row spectra of the daily kernels), the emission
+// kernels (r_small_vals, cohort superposition), the COO compaction kernels and
+// the direct stencil for tiny kernels.  While the state's exact support still
+// fits inside the domain a step runs on a torus sized for that support window
+// (ChainDims::win).  DESIGN.md sections 3-5 give the layout and the numbers.
 #pragma once
 #include "fft_smem.cuh"
 
-// launch-bound knobs (tools/chainbench.cu builds variants with -D)
+// launch bounds: at most 256 threads and 128 registers (2 x 256, 3 x 160 or 4 x 128 resident threads per SM,
+// chosen per plan in pkb200.cu:get_plan); tools/chainbench.cu builds variants with -D
 #ifndef PKB_ROWS_T
 #define PKB_ROWS_T 256
 #endif
