@@ -293,6 +293,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='synthetic_4097x4097_60d', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
+                    help='library option (pkb_set_option), e.g. fuse_rows=0; recorded in config')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
@@ -332,6 +334,9 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from parasitoids_b200 import Run, _lib, batch
     ctx = _lib.ctx(local)
+    for kv in args.opt:
+        key, val = kv.split('=')
+        ctx.set_option(key, float(val))
 
     # N > 1: a likelihood batch of one parameter proposal per rank (proposal 0 = the defaults),
     # sharded by parasitoids_b200.batch.solve_batch; the only collective is its all_gather
@@ -511,6 +516,8 @@ def main():
                            'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'roofline_chain': roofline_chain}
+        if args.opt:
+            line['config']['options'] = list(args.opt)
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))

@@ -161,8 +161,17 @@ __device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan,
 }
 
 // grid = persistent, block = T
+// pre_m >= 0: the k_rows_inv that produced S (filter radius pre_m) has already transformed the
+// complete interior row pairs of the new state into Yt (fused_pair below); unless that state turned
+// out flagged -- then its truncated form must be transformed from scratch -- only the border
+// pairs are left for this kernel.
+__host__ __device__ __forceinline__ bool fused_pair(int r0, int P, int m) {
+    return r0 >= m + (m & 1) && r0 + 1 < P - m;       // both rows interior, pair on an even row
+}
+// the fusion needs room for the reduction scratch in the (zero) tail of the transform buffer
+__host__ __device__ __forceinline__ bool rows_fusable(int N, int P) { return N - 48 >= P; }
 __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
-                                       cplx* __restrict__ Yt, FftPlan plan) {
+                                       cplx* __restrict__ Yt, FftPlan plan, int pre_m) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
@@ -172,7 +181,13 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
     const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
     const int njobs = (lim + 1) / 2;
     if (d.win) S += (size_t)d.wr0 * d.ldS + d.wc0;     // rows / columns below are relative to the window
-    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+    const bool skip_interior = pre_m >= 0 && !d.win && !ctrl->trunc;
+    // border pairs only: [0, lo/2) and [hi_job, njobs), the interior pairs in between are done
+    const int lo_job = skip_interior ? (pre_m + (pre_m & 1)) / 2 : njobs;
+    const int hi_job = skip_interior ? (d.P - pre_m) / 2 : njobs;       // first pair with r0 + 1 >= P - pre_m
+    const int nwork = skip_interior ? lo_job + (njobs - hi_job) : njobs;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int job = (skip_interior && w >= lo_job) ? hi_job + (w - lo_job) : w;
         const int r0 = 2 * job;
         const bool two = r0 + 1 < lim;
         const double* s0 = S + (size_t)r0 * d.ldS;
@@ -183,7 +198,7 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
         };
         {   // next job's two rows -> L2 while this one is transformed
             const int nr0 = 2 * (job + (int)gridDim.x);
-            if ((PKB_PREFETCH & 1) && nr0 < lim) {
+            if ((PKB_PREFETCH & 1) && !skip_interior && nr0 < lim) {
                 const char* nxt = reinterpret_cast<const char*>(S + (size_t)nr0 * d.ldS);
                 const int nbytes = (nr0 + 1 < lim ? 2 : 1) * d.ldS * (int)sizeof(double);
                 for (int o = tid * 128; o < nbytes; o += T * 128) prefetch_l2(nxt + o);
@@ -458,13 +473,17 @@ __device__ __forceinline__ void rows_inv_decode(int job, int m, int P, int N, in
 // fold onto the same output row mod P (their sum is re + im).
 __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
-                                       ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc) {
+                                       ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc,
+                                       cplx* __restrict__ Yt_next) {
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
     // reduction scratch and the "last CTA" flag live at the start of the transform buffer, which is
     // idle whenever they are used (after a job's output loop; fft_smem_bytes() >= 1 KB)
-    double* red = reinterpret_cast<double*>(raw);
+    // (at the END of the buffer when the next step's forward row transform is fused in: the packed
+    //  row pair at the start of the buffer is still needed then, and the tail beyond column P is read as zero)
+    const bool fuse = Yt_next != nullptr && !d.win && rows_fusable(plan.N, d.P);
+    double* red = reinterpret_cast<double*>(raw) + (fuse ? 2 * (plan.N - 48) : 0);
     int* last = reinterpret_cast<int*>(red + PKB_RED_DOUBLES);
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
@@ -592,6 +611,20 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             rstat[tid ? out_b : out_a] = rs;
         }
         __syncthreads();
+        if (fuse && !fold && out_b >= 0 && fused_pair(out_a, P, m)) {
+            // The buffer still holds the new row pair packed as re + i im (columns folded, unscaled):
+            // exactly the input of the NEXT step's forward row transform.  Scale on load (tail read as zero)
+            // and transform here -- the pair never has to be read back from HBM.  (Speculative: if this
+            // state ends up flagged, k_rows_fwd redoes every row from the truncated state.)
+            auto ld = [&](int c) -> cplx {
+                if (c >= P) return zero;
+                const cplx z = x[c];
+                return cmake(z.x * scale, z.y * scale);
+            };
+            fft_forward_from(x, tws, plan, tid, T, ld, false);
+            unpack_store(x, plan, Nc, Yt_next, d.ldY, out_a, true, tid, T);
+            __syncthreads();
+        }
     }
     // the CTA that finishes last reduces the row statistics of the whole state
     if (tid == 0) {

@@ -99,6 +99,7 @@ struct pkb_ctx {
     int stencil_max_radius;
     int fft_threads;
     int use_windows;        // fused solve: support-window steps (option "windows", default on)
+    int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int sm_count;
     int max_smem;
 };
@@ -314,6 +315,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->stencil_max_radius = 3;
     ctx->fft_threads = PKB_ROWS_T;
     ctx->use_windows = 1;
+    ctx->use_fusion = 1;
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->prof_on = false;
@@ -389,6 +391,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "stencil_max_radius")) {
         if (value < -1 || value > 24) return fail(PKB_EINVAL, "stencil_max_radius must be in [-1, 24]");
         ctx->stencil_max_radius = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "fuse_rows")) {
+        ctx->use_fusion = value != 0;
         return 0;
     }
     if (!strcmp(key, "windows")) {
@@ -1035,7 +1041,8 @@ extern "C" int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N) {
 // K is a device window Wk x Wk with support radius m.  krt: row spectra buffer to
 // (re)use; krt_ready: it already holds the spectra of K.
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
-                     cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr) {
+                     cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
+                     int pre_m = -1) {
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
@@ -1070,19 +1077,19 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
     if (win) {
         if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
-        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
+        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1);
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
-    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan);
+    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m);
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
            ch->Wt.p, ch->cscr.p, plan);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
-           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
+           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr);
     return 0;
 }
 
@@ -1145,9 +1152,11 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
     return 0;
 }
 
-static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr) {
+static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr,
+                           bool fuse_next = false, int pre_m = -1) {
     const int nxt = ch->cur ^ 1;
-    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win));
+    TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win,
+                  fuse_next, pre_m));
     ch->cur = nxt;
     return 0;
 }
@@ -1566,6 +1575,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             }
         }
     }
+    int fused_m = -1;       // >= 0: the previous step's k_rows_inv already transformed the interior row pairs (its filter radius)
     auto window_spectra = [&](int n, cplx** out) -> int {
         *out = nullptr;
         if (win_slot[n] < 0) return 0;
@@ -1586,7 +1596,11 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             else TRY(window_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp));
+            // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
+            const bool fuse = ctx->use_fusion && rows_fusable(ch->plan.N, ch->d.P) && !wp && !wmode && n + 1 < nd && krad(n) > ctx->stencil_max_radius &&
+                              krad(n + 1) > ctx->stencil_max_radius;
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m));
+            fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
@@ -1644,7 +1658,10 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             cplx* kday = nullptr;
             if (!wp) TRY(day_spectra(n, &kday));
             else TRY(window_spectra(n, &kday));
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp));
+            const bool fuse = ctx->use_fusion && rows_fusable(ch->plan.N, ch->d.P) && rd == 1 && !wp && !wmode && n + 1 < nd && krad(n) > ctx->stencil_max_radius &&
+                              krad(n + 1) > ctx->stencil_max_radius;
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m));
+            fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
             for (int c = 0; c < rd; ++c) {

@@ -379,3 +379,47 @@ def test_fused_solve_edge_cases(pkb):
         pkb.Run.solve(breeze, nd + 1, *args)            # more days than wind
     with pytest.raises(pkb._lib.PkbError):
         pkb.Run.solve(breeze, nd, *args, prob_model=False, r_dur=nd + 1)
+
+
+def test_fused_row_passes_match_separate_passes(pkb):
+    """Option fuse_rows: the inverse row pass of a whole-torus step also runs the forward row
+    transform of the next step on the row pair it still holds (k_rows_inv -> Yt), speculatively --
+    a state that turns out flagged is transformed again from its truncated form.  Same arithmetic
+    on the same numbers, so the solutions must agree to the run-to-run noise of kernel construction
+    (its fp64 atomics commute only to an ulp) with and without it, flagged (steady breeze towards the
+    edge) or not."""
+    rng = np.random.default_rng(5)
+    nd, periods, rad_res, rad_dist = 7, 96, 60, 3000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        x = np.cumsum(rng.normal(0, 0.05, nd * periods)).reshape(nd, periods)
+        w[:, :, c] = 0.3 * np.sin(np.linspace(0, 6, nd * periods)).reshape(nd, periods) + x * 0.2
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    drift = w.copy()
+    drift[:, :, 0] = np.abs(drift[:, :, 0]) + 0.4       # mass reaches the boundary: flags trip
+    drift[:, :, 2] = np.hypot(drift[:, :, 0], drift[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    ctx.set_option('windows', 0)                        # whole-torus steps from the first day on
+    flagged = 0
+    try:
+        for wind in (w, drift):
+            for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=1, r_number=1000.0)):
+                out = {}
+                for fuse in (1, 0):
+                    ctx.set_option('fuse_rows', fuse)
+                    with warnings.catch_warnings():
+                        warnings.simplefilter('ignore')
+                        res = pkb.Run.solve(wind, nd, *args, want_coo=False, want_dense=True, **kw)
+                    out[fuse] = ([res.dense(d) for d in range(nd)], res.flags())
+                    res.close()
+                assert out[1][1] == out[0][1]
+                flagged += sum(1 for f in out[1][1] if f)
+                for d in range(nd):
+                    a, b = out[1][0][d], out[0][0][d]
+                    assert ((a != 0) != (b != 0)).sum() == 0
+                    assert np.abs(a - b).max() <= 1e-15 * kw.get('r_number', 1.0), 'day %d' % d
+    finally:
+        ctx.set_option('fuse_rows', 1)
+        ctx.set_option('windows', 1)
+    assert flagged > 0, 'no flagged step in the drift case'
