@@ -741,6 +741,42 @@ __global__ void k_emit_population(CohortArgs ca, ChainDims d, double r_number, d
     }
 }
 
+// Sample-cell emission (likelihood batches, pkb_solve_batch): the same per-cell rules as k_copy_domain /
+// k_emit_dense / k_emit_population, evaluated only at the K (row, col) cells the caller reads -- the
+// dense [D][D] day is never materialised.  grid = ceil(K / 256), block = 256
+__global__ void k_copy_domain_cells(const double* __restrict__ S, ChainDims d, const int* __restrict__ cells, int K, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) out[k] = S[(size_t)cells[2 * k] * d.ldS + cells[2 * k + 1]];
+}
+__global__ void k_emit_dense_cells(const double* __restrict__ S, ChainDims d, const StepMeta* __restrict__ meta, double negval, int prob_model,
+                                   int strict, const int* __restrict__ cells, int K, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double add = prob_model ? meta->add : 0.0;
+    const double v = S[(size_t)cells[2 * k] * d.ldS + cells[2 * k + 1]];
+    const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
+    out[k] = keep ? v + add : 0.0;
+}
+__global__ void k_emit_population_cells(CohortArgs ca, ChainDims d, double r_number, double centre_extra, int add_centre, double negval,
+                                        int first_day, const int* __restrict__ cells, int K, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int r = cells[2 * k], c = cells[2 * k + 1], mid = d.D / 2;
+    double v;
+    if (first_day) {
+        const double p = ca.S[0][(size_t)r * d.ldS + c];
+        const double t = (p != 0.0 && !(p < negval)) ? p : 0.0;
+        v = (t * r_number) * ca.w[0];
+    } else {
+        double acc = 0.0;
+        for (int j = 0; j < ca.n; ++j) acc += ca.S[j][(size_t)r * d.ldS + c] * ca.w[j];
+        v = acc * r_number;
+        v = (v != 0.0 && !(v < negval)) ? v : 0.0;
+    }
+    if (add_centre && r == mid && c == mid) v += centre_extra;
+    out[k] = v;
+}
+
 // out[day][k] = G[day][cells[k]]   grid = ndays, block = 256
 __global__ void k_sample(const double* __restrict__ G, int D, const int* __restrict__ cells, int K, double* __restrict__ out) {
     const double* g = G + (size_t)blockIdx.x * D * D;

@@ -100,6 +100,11 @@ struct pkb_ctx {
     int fft_threads;
     int use_windows;        // fused solve: support-window steps (option "windows", default on)
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
+    int occ_cap;            // resident CTAs per SM the persistent grids are sized for (4; tuning hook PKB_FFT_OCC)
+    int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
+    int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
+    std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
+    cudaEvent_t ev_lane;
     int sm_count;
     int max_smem;
 };
@@ -316,6 +321,11 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->fft_threads = PKB_ROWS_T;
     ctx->use_windows = 1;
     ctx->use_fusion = 1;
+    ctx->batch_lanes = 2;
+    ctx->use_step_torus = 1;
+    ctx->occ_cap = 4;
+    if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
+    CU(cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->prof_on = false;
@@ -354,6 +364,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (pkb_ctx* lane : ctx->lanes) pkb_destroy(lane);
+    cudaEventDestroy(ctx->ev_lane);
     for (auto& kv : ctx->plans) {
         cudaFree(kv.second.tw0);
         cudaFree(kv.second.twb);
@@ -395,6 +407,15 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fuse_rows")) {
         ctx->use_fusion = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "step_torus")) {
+        ctx->use_step_torus = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "batch_lanes")) {
+        if (value < 1 || value > 8) return fail(PKB_EINVAL, "batch_lanes must be 1..8");
+        ctx->batch_lanes = (int)value;
         return 0;
     }
     if (!strcmp(key, "windows")) {
@@ -626,8 +647,8 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_rows_fwd, p.threads, sm1));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, k_rows_inv, p.threads, sm1));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_cols, p.cols_threads, sm1));
-        p.grid_rows = std::min(4, std::min(occ_r, occ_i)) * ctx->sm_count;
-        p.grid_cols = std::min(4, occ_c) * ctx->sm_count;
+        p.grid_rows = std::min(ctx->occ_cap, std::min(occ_r, occ_i)) * ctx->sm_count;
+        p.grid_cols = std::min(ctx->occ_cap, occ_c) * ctx->sm_count;
     }
     ctx->plans[N] = rec;
     *out = p;
@@ -983,7 +1004,7 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ch->grid_cols = ch->plan.grid_cols;
     // k_cols parking space: any plan up to this torus side needs at most N + R_last * threads slots per CTA
     ch->cscr_per_cta = (size_t)d.N + 21 * 256 + 256;
-    TRY(ch->cscr.alloc(ctx, (size_t)4 * ctx->sm_count * ch->cscr_per_cta));
+    TRY(ch->cscr.alloc(ctx, (size_t)ctx->occ_cap * ctx->sm_count * ch->cscr_per_cta));
     const size_t ns = (size_t)d.P * d.ldS;
     TRY(ch->S[0].alloc(ctx, ns));
     TRY(ch->S[1].alloc(ctx, ns));
@@ -1040,6 +1061,28 @@ extern "C" int pkb_chain_dims(pkb_chain* ch, int* D, int* P, int* N) {
 // ctrl->trunc, so the pad is only physically zeroed where a caller can see it).
 // K is a device window Wk x Wk with support radius m.  krt: row spectra buffer to
 // (re)use; krt_ready: it already holds the spectra of K.
+// Torus of a whole-torus step with a filter of radius m.  The linear convolution of the P x P state
+// with a (2m+1)^2 kernel needs N >= P + 2m for THIS m, not for the chain's largest kernel: days
+// with a small kernel run on a smaller 7-smooth torus (same fold mod P afterwards, same result to
+// rounding).  Falls back to the chain's torus when the smaller plan cannot use the chain's buffers.
+static int step_torus(pkb_chain* ch, int m, ChainDims* d, FftPlan* plan) {
+    pkb_ctx* ctx = ch->ctx;
+    *d = ch->d;
+    *plan = ch->plan;
+    if (!ctx->use_step_torus) return 0;
+    const int Nd = pkb_smooth_len(std::max(2, ch->d.P + 2 * m));
+    if (Nd >= ch->d.N) return 0;
+    FftPlan p;
+    TRY(get_plan(ctx, Nd, &p));
+    if (p.grid_rows < 1 || p.grid_cols < 1) return 0;
+    if ((size_t)p.cols_kb * plan_radix(p, p.nstage - 1) * p.cols_threads > ch->cscr_per_cta) return 0;
+    d->N = Nd;
+    d->Nc = Nd / 2 + 1;
+    d->ldW = (Nd + 1) / 2 * 2;
+    *plan = p;
+    return 0;
+}
+
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
                      int pre_m = -1) {
@@ -1055,9 +1098,11 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         return 0;
     }
     // geometry of this step: the chain's torus, or a smaller one around the state's support window
-    ChainDims d = ch->d;
-    FftPlan plan = ch->plan;
+    ChainDims d;
+    FftPlan plan;
+    TRY(step_torus(ch, m, &d, &plan));
     if (win) {
+        d = ch->d;
         d.win = 1; d.wr0 = win[0]; d.wc0 = win[1]; d.wn = win[2];
         d.N = pkb_smooth_len(std::max(2, d.wn + 2 * m));
         d.Nc = d.N / 2 + 1;
@@ -1425,8 +1470,18 @@ static void solve_day_args(const pkb_solve_args* a, pkb_day_args* dargs) {
 }
 
 // Phase 2 and outputs of one solve whose per-day kernels are problems k0 .. k0 + ndays - 1 of ks.
-static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int k0, pkb_result** out) {
+// Likelihood batches read the model only at K sample cells: with a sink the emission kernels evaluate
+// just those cells into out[nd][K] (device), no dense day is materialised, no result object is returned
+// and the chain is left enqueued on ctx's streams (the caller synchronises once per group of proposals).
+struct SampleSink {
+    const int* cells;       // device [K][2]
+    int K;
+    double* out;            // device [nd][K]
+};
+static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int k0, pkb_result** out, const SampleSink* sink = nullptr) {
     const int nd = a->ndays;
+    if (sink && a->want_coo) return fail(PKB_EINVAL, "sample-cell emission excludes COO output");
+    const int sgrid = sink ? (sink->K + 255) / 256 : 0;
     const double negval = a->negval > 0 ? a->negval : 1e-8;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -1461,7 +1516,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     res->P = d.P;
     res->N = d.N;
     const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
-    TRY(res->dense.alloc(ctx, nD * nd));
+    if (!sink) TRY(res->dense.alloc(ctx, nD * nd));
     res->counted.assign(nd, 0);
     if (a->want_coo) {
         TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
@@ -1493,16 +1548,35 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         *out = nullptr;
         if (krad(n) <= ctx->stencil_max_radius) return 0;
         if (kr_first < 0 || n >= kr_first + kr_chunk) {
-            KrBatch kb;
-            memset(&kb, 0, sizeof kb);
             kr_first = n;
-            kb.nd = std::min(kr_chunk, nd - n);
-            for (int i = 0; i < kb.nd; ++i) {
-                kb.m[i] = krad(n + i);
-                kb.job0[i + 1] = kb.job0[i] + (kb.m[i] > ctx->stencil_max_radius ? kb.m[i] + 1 : 0);
+            const int cnt = std::min(kr_chunk, nd - n);
+            // one launch per distinct step torus among the block's days (step_torus: a handful of sizes)
+            std::vector<int> tor(cnt);
+            std::vector<ChainDims> dims(cnt);
+            std::vector<FftPlan> plans(cnt);
+            for (int i = 0; i < cnt; ++i) {
+                TRY(step_torus(ch, krad(n + i), &dims[i], &plans[i]));
+                tor[i] = dims[i].N;
             }
-            LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[kb.nd], ch->grid_rows), ch->plan.threads, fft_smem_bytes(ch->plan), kern(n),
-                   nW, ks->W, kb, d, krt_all.p, krt_stride, ch->plan);
+            std::vector<int> sizes(tor);
+            std::sort(sizes.begin(), sizes.end());
+            sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+            for (int Nd : sizes) {
+                KrBatch kb;
+                memset(&kb, 0, sizeof kb);
+                kb.nd = cnt;
+                int rep = -1;
+                for (int i = 0; i < cnt; ++i) {
+                    kb.m[i] = krad(n + i);
+                    const bool mine = tor[i] == Nd && kb.m[i] > ctx->stencil_max_radius;
+                    if (mine) rep = i;
+                    kb.job0[i + 1] = kb.job0[i] + (mine ? kb.m[i] + 1 : 0);
+                }
+                if (rep < 0 || kb.job0[cnt] == 0) continue;
+                const FftPlan& pl = plans[rep];
+                LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[cnt], pl.grid_rows), pl.threads, fft_smem_bytes(pl), kern(n), nW, ks->W, kb,
+                       dims[rep], krt_all.p, krt_stride, pl);
+            }
         }
         *out = krt_all.p + krt_stride * (n - kr_first);
         return 0;
@@ -1575,6 +1649,15 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             }
         }
     }
+    // steps n and n + 1 both whole-torus FFT steps on the SAME torus: the inverse row pass of step n can
+    // also run the forward row pass of step n + 1
+    auto fusable = [&](int n) -> bool {
+        if (!ctx->use_fusion || krad(n) <= ctx->stencil_max_radius || krad(n + 1) <= ctx->stencil_max_radius) return false;
+        ChainDims da, db;
+        FftPlan pa, pb;
+        if (step_torus(ch, krad(n), &da, &pa) || step_torus(ch, krad(n + 1), &db, &pb)) return false;
+        return da.N == db.N && rows_fusable(da.N, da.P);
+    };
     int fused_m = -1;       // >= 0: the previous step's k_rows_inv already transformed the interior row pairs (its filter radius)
     auto window_spectra = [&](int n, cplx** out) -> int {
         *out = nullptr;
@@ -1587,7 +1670,8 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
-        LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
+        if (sink) LAUNCH(ctx, k_copy_domain_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, sink->cells, sink->K, sink->out);
+        else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
         TRY(emitted(0, ctx->stream));
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
             const int* wp = step_window(n);
@@ -1597,16 +1681,19 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
-            const bool fuse = ctx->use_fusion && rows_fusable(ch->plan.N, ch->d.P) && !wp && !wmode && n + 1 < nd && krad(n) > ctx->stencil_max_radius &&
-                              krad(n + 1) > ctx->stencil_max_radius;
+            const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
-            LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, PKB_EMIT_T, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
-                      res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
+            if (sink)
+                LAUNCH_ON(ctx, ctx->aux, k_emit_dense_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval,
+                          1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * n);
+            else
+                LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, PKB_EMIT_T, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
+                          res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
             if (a->want_coo) res->counted[n] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
             TRY(emitted(n, ctx->aux));
@@ -1636,7 +1723,16 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         // day 0 (CalcSol.py:236-237)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         ca.n = 1; ca.S[0] = ch->S[ch->cur].p; ca.w[0] = a->r_dist[0];
-        LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, rn * (1 - a->r_dist[0]), 1, negval, 1, res->dense.p, (double*)nullptr);
+        auto emit_pop = [&](int day, double centre_extra, int add_centre, int first_day) -> int {
+            if (sink)
+                LAUNCH(ctx, k_emit_population_cells, sgrid, 256, 0, ca, d, rn, centre_extra, add_centre, negval, first_day, sink->cells, sink->K,
+                       sink->out + (size_t)sink->K * day);
+            else
+                LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, centre_extra, add_centre, negval, first_day, res->dense.p + nD * day,
+                       (double*)nullptr);
+            return 0;
+        };
+        TRY(emit_pop(0, rn * (1 - a->r_dist[0]), 1, 1));
         TRY(emitted(0, ctx->stream));
         // release days (CalcSol.py:296-306)
         for (int day = 1; day < rd; ++day) {
@@ -1649,7 +1745,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                 wsum += a->r_dist[c];
             }
             ca.n = day + 1;
-            LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, (1 - wsum) * rn, 1, negval, 0, res->dense.p + nD * day, (double*)nullptr);
+            TRY(emit_pop(day, (1 - wsum) * rn, 1, 0));
             TRY(emitted(day, ctx->stream));
         }
         // post-release days (CalcSol.py:308-323)
@@ -1658,8 +1754,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             cplx* kday = nullptr;
             if (!wp) TRY(day_spectra(n, &kday));
             else TRY(window_spectra(n, &kday));
-            const bool fuse = ctx->use_fusion && rows_fusable(ch->plan.N, ch->d.P) && rd == 1 && !wp && !wmode && n + 1 < nd && krad(n) > ctx->stencil_max_radius &&
-                              krad(n + 1) > ctx->stencil_max_radius;
+            const bool fuse = rd == 1 && !wp && !wmode && n + 1 < nd && fusable(n);
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1669,11 +1764,18 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                 ca.w[c] = a->r_dist[c];
             }
             ca.n = rd;
-            LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, 0.0, 0, negval, 0, res->dense.p + nD * n, (double*)nullptr);
+            TRY(emit_pop(n, 0.0, 0, 0));
             TRY(emitted(n, ctx->stream));
         }
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (sink) {
+        // everything above is ordered on ctx->stream (the side streams were joined): the buffers released
+        // on return are reused stream-ordered by the next chain of this context
+        TRY(check_launches(ctx, "pkb_solve_batch chain"));
+        if (out) *out = nullptr;
+        return 0;
+    }
 
     // ---- outputs (the chain is enqueued, not finished: compaction and D2H overlap it) ----
     if (a->want_coo) TRY(coo_collect(ctx, res));
@@ -1723,8 +1825,11 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
 // Likelihood batch: `nprop` independent proposals of the same solve (shared wind, domain and release
 // settings; the 15 block variables of Bayes_Run.py:186-196 differ), returning the model at K sample
 // cells for every proposal and day.  Kernel construction is batched over groups of proposals (one
-// launch set for up to PKB_BATCH_GROUP x ndays (proposal, day) problems instead of one per proposal);
-// the chains then run one after the other on those device-resident kernels.
+// launch set for up to PKB_BATCH_GROUP x ndays (proposal, day) problems instead of one per proposal).
+// The chains of a group are then enqueued round-robin on `batch_lanes` child contexts (own streams,
+// buffer pools and plans): a Kalbar-sized chain step is a handful of short persistent kernels whose
+// last wave leaves most SMs idle, and a second chain in flight fills those tails.  Every chain emits
+// only the K sample cells (SampleSink); the host synchronises once per group.
 #define PKB_BATCH_GROUP 32
 extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells, int K,
                                double* out, int* status) {
@@ -1733,6 +1838,9 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
     TRY(check_solve_args(base));
     CU(cudaSetDevice(ctx->device));
     const int nd = base->ndays;
+    const size_t dom = 2 * (size_t)base->day.rad_res + 1;
+    for (int k = 0; k < 2 * K; ++k)
+        if (cells[k] < 0 || cells[k] >= (int)dom) return fail(PKB_EINVAL, "pkb_solve_batch: cell index %d outside the domain", cells[k]);
     DBuf<double> dwind;
     const double* wind_dev = base->wind;
     if (!base->wind_on_device) {
@@ -1741,9 +1849,48 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         CU(cudaMemcpyAsync(dwind.p, base->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         wind_dev = dwind.p;
     }
+    DBuf<int> dcells;
+    TRY(dcells.alloc(ctx, 2 * (size_t)K));
+    CU(cudaMemcpyAsync(dcells.p, cells, sizeof(int) * 2 * K, cudaMemcpyHostToDevice, ctx->stream));
+    // lanes: child contexts on the same device, created on first use and kept
+    const int nlanes = std::max(1, std::min(ctx->batch_lanes, nprop));
+    while ((int)ctx->lanes.size() < nlanes) {
+        pkb_ctx* lane = nullptr;
+        TRY(pkb_create(ctx->device, &lane));
+        ctx->lanes.push_back(lane);
+    }
+    for (int l = 0; l < nlanes; ++l) {
+        pkb_ctx* lane = ctx->lanes[l];
+        lane->stencil_max_radius = ctx->stencil_max_radius;
+        lane->fft_threads = ctx->fft_threads;
+        lane->use_windows = ctx->use_windows;
+        lane->use_fusion = ctx->use_fusion;
+        lane->use_step_torus = ctx->use_step_torus;
+        lane->prof_on = ctx->prof_on;
+    }
+    // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel
+    // profile into the parent (what pkb_launch_count / pkb_profile_get report)
+    auto drain = [&]() -> int {
+        int rc = 0;
+        for (int l = 0; l < nlanes; ++l) {
+            pkb_ctx* lane = ctx->lanes[l];
+            const int r1 = sync_check(lane, "pkb_solve_batch lane");
+            if (r1 && !rc) rc = r1;
+            ctx->launches += lane->launches;
+            lane->launches = 0;
+            for (auto& kv : lane->prof_acc) {
+                auto& acc = ctx->prof_acc[kv.first];
+                acc.first += kv.second.first;
+                acc.second += kv.second.second;
+            }
+            lane->prof_acc.clear();
+        }
+        return rc;
+    };
     // bound the group so that the accumulation windows (worst case the whole domain per problem) stay below ~8 GB
-    const size_t dom = 2 * (size_t)base->day.rad_res + 1;
     int group = (int)std::max<size_t>(1, std::min<size_t>(PKB_BATCH_GROUP, ((size_t)8 << 30) / (dom * dom * sizeof(double) * nd)));
+    DBuf<double> dout;
+    TRY(dout.alloc(ctx, (size_t)std::min(group, std::max(nprop, 1)) * nd * K));
     for (int p0 = 0; p0 < nprop; p0 += group) {
         const int np = std::min(group, nprop - p0);
         std::vector<pkb_solve_args> sa(np, *base);
@@ -1758,7 +1905,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
             for (int j = 0; j < 3; ++j) { s.day.dparams[j] = q[6 + j]; s.day.dlparams[j] = q[9 + j]; }
             s.day.n_periods = (int)llround(q[13]);
             s.day.mu_r = q[14];
-            s.want_coo = 0; s.want_dense_host = 0; s.keep_dense_device = 1;
+            s.want_coo = 0; s.want_dense_host = 0; s.keep_dense_device = 0;
             solve_day_args(&s, dargs.data() + (size_t)p * nd);
         }
         CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1770,13 +1917,20 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         } kguard{ks};
         if (status)
             for (int i = 0; i < np * nd; ++i) status[(size_t)p0 * nd + i] = ks->hmeta[i].status;
-        for (int p = 0; p < np; ++p) {
-            pkb_result* r = nullptr;
-            TRY(solve_chain(ctx, &sa[p], ks, p * nd, &r));
-            const int rc = pkb_result_sample(r, cells, K, out + (size_t)(p0 + p) * nd * K);
-            pkb_result_destroy(r);
-            if (rc) return rc;
+        // the lanes start once the kernels (and, first group, the cells) are on the device
+        CU(cudaEventRecord(ctx->ev_lane, ctx->stream));
+        for (int l = 0; l < nlanes; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l]->stream, ctx->ev_lane, 0));
+        int rc = 0;
+        for (int p = 0; p < np && !rc; ++p) {
+            SampleSink sink = {dcells.p, K, dout.p + (size_t)p * nd * K};
+            rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nd, nullptr, &sink);
         }
+        // one synchronisation per group (also before `ks` and the lanes' buffers go away on an error)
+        const int rc2 = drain();
+        if (rc) return rc;
+        if (rc2) return rc2;
+        CU(cudaMemcpyAsync(out + (size_t)p0 * nd * K, dout.p, sizeof(double) * np * nd * K, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(sync_check(ctx, "pkb_solve_batch outputs"));
     }
     return 0;
 }

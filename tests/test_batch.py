@@ -61,24 +61,36 @@ def test_unpack_proposal_order():
         batch.unpack_proposal(DEFAULT[:-1])
 
 
-def test_solve_batch_matches_single_solves(pkb):
-    """pkb_solve_batch (kernel construction batched over proposals) against one
-    Run.solve per proposal sampled at the same cells."""
+@pytest.mark.parametrize('prob_model,lanes', [(False, 2), (False, 1), (True, 3)])
+def test_solve_batch_matches_single_solves(pkb, prob_model, lanes):
+    """pkb_solve_batch (kernel construction batched over proposals, chains enqueued round-robin on
+    `batch_lanes` child contexts, sample-cell emission only) against one Run.solve per proposal
+    sampled at the same cells of its dense output, for the population and the probability model."""
     import warnings
     from parasitoids_b200 import batch
     w, props = _wind(), _proposals(5)
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore')
-        got = batch.solve_batch(w, props, CELLS, **SOLVE_KW)
-        for b in range(5):
-            hp, dp, dl, mu_r, n_periods = batch.unpack_proposal(props[b])
-            res = pkb.Run.solve(w, SOLVE_KW['ndays'], hp, dp, dl, mu_r, n_periods, SOLVE_KW['rad_dist'], SOLVE_KW['rad_res'],
-                                prob_model=False, r_dur=SOLVE_KW['r_dur'], r_number=SOLVE_KW['r_number'], r_start=SOLVE_KW['r_start'],
-                                want_coo=False, keep_device=True)
-            ref = res.sample(CELLS)
-            res.close()
-            assert ((got[b] != 0) != (ref != 0)).sum() == 0
-            assert np.allclose(got[b], ref, rtol=1e-12, atol=1e-15)
+    kw = dict(SOLVE_KW)
+    if prob_model:
+        kw.update(prob_model=True, r_dur=1, r_number=1.0, r_start=None)
+    ctx = pkb._lib.ctx()
+    ctx.set_option('batch_lanes', lanes)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            l0 = ctx.launch_count()
+            got = batch.solve_batch(w, props, CELLS, **kw)
+            assert ctx.launch_count() - l0 > 5 * kw['ndays']      # the lanes' launches are folded into the parent's count
+            for b in range(5):
+                hp, dp, dl, mu_r, n_periods = batch.unpack_proposal(props[b])
+                res = pkb.Run.solve(w, kw['ndays'], hp, dp, dl, mu_r, n_periods, kw['rad_dist'], kw['rad_res'],
+                                    prob_model=prob_model, r_dur=kw['r_dur'], r_number=kw['r_number'], r_start=kw['r_start'],
+                                    want_coo=False, keep_device=True)
+                ref = res.sample(CELLS)
+                res.close()
+                assert ((got[b] != 0) != (ref != 0)).sum() == 0
+                assert np.allclose(got[b], ref, rtol=1e-12, atol=1e-15)
+    finally:
+        ctx.set_option('batch_lanes', 2)
 
 
 def _free_port():

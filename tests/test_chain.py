@@ -321,16 +321,14 @@ def test_window_steps_match_whole_torus_steps(pkb):
         out = {}
         for windows in (1, 0):
             ctx.set_option('windows', windows)
-            l0 = ctx.launch_count()
             with warnings.catch_warnings():
                 warnings.simplefilter('ignore')
                 res = pkb.Run.solve(w, nd, *args, want_coo=False, want_dense=True, **kw)
-            out[windows] = ([res.dense(d) for d in range(nd)], res.flags(), res.N, ctx.launch_count() - l0)
+            out[windows] = ([res.dense(d) for d in range(nd)], res.flags(), res.N, res.window_steps())
             res.close()
         ctx.set_option('windows', 1)
         assert out[1][1] == out[0][1]
-        # windowed steps compute their own kernel row spectra (one extra launch each): they were taken
-        assert out[1][3] > out[0][3], 'no step ran in window mode'
+        assert out[1][3] > 0 and out[0][3] == 0, 'no step ran in window mode'
         for d in range(nd):
             a, b = out[1][0][d], out[0][0][d]
             assert ((a != 0) != (b != 0)).sum() == 0
@@ -423,3 +421,45 @@ def test_fused_row_passes_match_separate_passes(pkb):
         ctx.set_option('fuse_rows', 1)
         ctx.set_option('windows', 1)
     assert flagged > 0, 'no flagged step in the drift case'
+
+
+def test_step_torus_matches_chain_torus(pkb):
+    """Option step_torus: a whole-torus step runs on the smallest 7-smooth torus >= P + 2m of THAT day's
+    kernel instead of the chain's (sized for the largest kernel); the fold mod P makes both the same
+    circular convolution (CalcSol.py:66), so the solutions agree to rounding -- both models, flagged
+    days included, against each other and (probability model) against the oracle."""
+    rng = np.random.default_rng(9)
+    nd, periods, rad_res, rad_dist = 7, 96, 60, 3000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        x = np.cumsum(rng.normal(0, 0.05, nd * periods)).reshape(nd, periods)
+        w[:, :, c] = 0.3 * np.sin(np.linspace(0, 6, nd * periods)).reshape(nd, periods) + x * 0.2
+    w[:, :, 1] *= np.linspace(0.2, 2.0, nd)[:, None]          # kernel radii differ from day to day
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    ctx.set_option('windows', 0)
+    try:
+        for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=2, r_number=1000.0)):
+            out = {}
+            for st in (1, 0):
+                ctx.set_option('step_torus', st)
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    res = pkb.Run.solve(w, nd, *args, want_coo=False, want_dense=True, **kw)
+                out[st] = ([res.dense(d) for d in range(nd)], res.flags(), res.radii(), res.N, res.P)
+                res.close()
+            radii, N, P = out[1][2], out[1][3], out[1][4]
+            lib = pkb._lib.lib()
+            assert any(lib.pkb_smooth_len(P + 2 * m) < N for m in radii[1:]), 'no day would run on a smaller torus'
+            assert out[1][1] == out[0][1]
+            scale = kw.get('r_number', 1.0)
+            for d in range(nd):
+                H.assert_thresholded_parity(out[1][0][d] / scale, out[0][0][d] / scale, what='day %d' % d, max_abs=1e-15)
+            if kw['prob_model']:
+                ref = _oracle_solve(w, nd, args, rad_res)
+                for d in range(nd):
+                    H.assert_thresholded_parity(out[1][0][d], ref[d].toarray(), what='oracle day %d' % d)
+    finally:
+        ctx.set_option('step_torus', 1)
+        ctx.set_option('windows', 1)
