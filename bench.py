@@ -467,7 +467,7 @@ def main():
                     'traffic': None if batch_mode else traffic_from_profiles(dom), 'peak_source': peak_src, 'launches': cnt,
                     'avg_launch_ms': ms / cnt, 'algorithmic_bytes_per_launch': share[dom]}
     roofline_chain = None
-    if nsteps_chain and not batch_mode:      # batch mode: proposals differ in torus size; the per-kernel roofline above still applies
+    if nsteps_chain and not batch_mode and chain_total_ms > 0:      # batch mode: proposals differ in torus size; the per-kernel roofline above still applies
         nflag = sum(1 for f in flags if f)
         bytes_solve = sum(chain_bytes(P, D, f) for f in flags[1:])
         # whole chain phase of the solve (library events around phase 2, pass A): kernels, gaps and overlap included

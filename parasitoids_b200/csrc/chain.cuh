@@ -46,8 +46,13 @@
 #ifndef PKB_COLS_B
 #define PKB_COLS_B 2
 #endif
+#ifdef PKB_MAXNREG      // explicit register cap instead of launch bounds (tuning builds: 3 x 224 threads need <= 96)
+#define PKB_ROWS_LB __maxnreg__(PKB_MAXNREG)
+#define PKB_COLS_LB __maxnreg__(PKB_MAXNREG)
+#else
 #define PKB_ROWS_LB __launch_bounds__(PKB_ROWS_T, PKB_ROWS_B)
 #define PKB_COLS_LB __launch_bounds__(PKB_COLS_T, PKB_COLS_B)
+#endif
 #define PKB_COLS_TMAX PKB_COLS_T
 
 namespace pkb {
@@ -134,11 +139,12 @@ __device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan,
     bool synced = false;
     for (int j0 = tid; j0 < npair || !synced; j0 += PKB_UNPACK_U * T) {
         int4 pr[PKB_UNPACK_U];
+        int col[PKB_UNPACK_U];       // column pair handled by this slot
 #pragma unroll
         for (int u = 0; u < PKB_UNPACK_U; ++u) {
             const int j = j0 + u * T;
-            // pair[] has N + 2 entries; the last odd column reads a valid dummy
-            pr[u] = j < npair ? __ldg(reinterpret_cast<const int4*>(plan.pair) + j) : make_int4(0, 0, 0, 0);
+            pr[u] = j < npair ? __ldg(plan.spair + j) : make_int4(0, 0, 0, 0);
+            col[u] = j < npair ? __ldg(plan.slot + j) : 0;
         }
         if (!synced) {
             __syncthreads();
@@ -152,7 +158,7 @@ __device__ __forceinline__ void unpack_store(const cplx* x, const FftPlan& plan,
                 cplx A0, B0, A1, B1;
                 hermitian_split(zk0, zn0, A0, B0);
                 hermitian_split(zk1, zn1, A1, B1);
-                cplx* o = dst + spec_index(2 * j, r, ld);
+                cplx* o = dst + spec_index(2 * col[u], r, ld);
                 st_pair(o, A0, A1);
                 if (two) st_pair(o + PKB_CB, B0, B1);
             }
@@ -525,14 +531,20 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         const int npair = (Nc + 1) / 2;
         for (int j0 = tid; j0 < npair; j0 += PKB_UNPACK_U * T) {
             int4 pr[PKB_UNPACK_U];
+            int col[PKB_UNPACK_U];       // column pair handled by this slot (FftPlan::slot)
             cplx a[2 * PKB_UNPACK_U], b[2 * PKB_UNPACK_U];
 #pragma unroll
             for (int u = 0; u < PKB_UNPACK_U; ++u) {
                 const int j = j0 + u * T;
+                col[u] = j < npair ? __ldg(plan.slot + j) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < PKB_UNPACK_U; ++u) {
+                const int j = j0 + u * T;
                 if (j < npair) {
-                    pr[u] = __ldg(reinterpret_cast<const int4*>(plan.pair) + j);
-                    ld_pair(Wt + spec_index(2 * j, ra, d.ldW), a[2 * u], a[2 * u + 1]);
-                    if (rb >= 0) ld_pair(Wt + spec_index(2 * j, rb, d.ldW), b[2 * u], b[2 * u + 1]);
+                    pr[u] = __ldg(plan.spair + j);
+                    ld_pair(Wt + spec_index(2 * col[u], ra, d.ldW), a[2 * u], a[2 * u + 1]);
+                    if (rb >= 0) ld_pair(Wt + spec_index(2 * col[u], rb, d.ldW), b[2 * u], b[2 * u + 1]);
                     else { b[2 * u] = zero; b[2 * u + 1] = zero; }
                 } else {
                     pr[u] = make_int4(0, 0, 0, 0);
@@ -545,7 +557,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                 if (j < npair) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int k = 2 * j + h;
+                        const int k = 2 * col[u] + h;
                         if (k >= Nc) break;
                         const cplx av = a[2 * u + h], bv = b[2 * u + h];
                         const int pk = h ? pr[u].z : pr[u].x, pn = h ? pr[u].w : pr[u].y;

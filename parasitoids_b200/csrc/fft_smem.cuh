@@ -41,6 +41,13 @@ struct FftPlan {
     const cplx* twb;            // stages 1.., one after the other: exp(-2 pi i k / M_s), k in [0, M_s / R_s) -> shared memory
     const int2* pair;           // pair[k] = (pos(k), pos((N - k) mod N)), pos = index of bin k after the forward pass
     const int* perm;            // perm[k] = pos(k)
+    // Hermitian pack / unpack loops (row kernels): thread slot s handles the column pair (2c, 2c+1), c = slot[s];
+    // spair[s] = (pos(2c), pos(N - 2c), pos(2c + 1), pos(N - 2c - 1)).  The slots are a permutation of the
+    // pairs inside windows of 64, chosen on the host so that the 8 threads of a quarter-warp touch 8
+    // different 16-byte bank groups: pos(k) of consecutive k differ by N / R_0 (392 at N = 4704, a multiple of
+    // 8 elements), which in natural order put 5-6 of every 8 accesses on one bank group.
+    const int* slot;
+    const int4* spair;
 };
 
 __host__ __device__ __forceinline__ int plan_radix(const FftPlan& p, int s) { return (int)((p.rpack >> (4 * s)) & 15ull); }
@@ -233,11 +240,26 @@ template <int R, bool INV, bool GTW, class Load, class Store>
 __device__ __forceinline__ void fft_stage(int N, int M, const cplx* twk, int tid, int T, Load ld, Store st) {
     const int Ms = M / R;
     const int nb = N / R;
-    const unsigned magic = div_magic(Ms);
+    // Butterfly j of the stage = (block b, offset k).  Consecutive threads normally take consecutive k
+    // (contiguous 16-byte elements: conflict free while Ms >= 8).  Once M is odd (all even radices
+    // consumed, e.g. M = 49 of 12.8.7.7) consecutive b are M elements apart and M is coprime to the 8
+    // 16-byte bank groups, so b runs fastest there instead: a quarter-warp then hits 8 distinct bank
+    // groups where the k-fastest order gave 2-way conflicts on every access (ncu: 1.9-2.0 wavefronts
+    // per ideal wavefront on that stage), and all of its threads read the same base twiddle.
+    const int nblk = N / M;
+#ifdef PKB_NO_BFAST
+    const bool bfast = false;
+#else
+    const bool bfast = !GTW && (M & 1) && Ms > 1 && nblk >= 8;
+#endif
+    const int dv = bfast ? nblk : Ms;
+    const unsigned magic = div_magic(dv);
 #pragma unroll 1
     for (int j = tid; j < nb; j += T) {
-        const int b = fast_div(j, Ms, magic);
-        const int k = j - b * Ms;
+        const int hi = fast_div(j, dv, magic);
+        const int lo = j - hi * dv;
+        const int b = bfast ? lo : hi;
+        const int k = bfast ? hi : lo;
         const int base = b * M + k;
         cplx v[R];
 #pragma unroll

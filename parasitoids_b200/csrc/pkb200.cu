@@ -69,6 +69,8 @@ struct PlanRec {
     cplx* twb;
     int2* pair;
     int* perm;
+    int* slot;
+    int4* spair;
 };
 
 struct pkb_ctx {
@@ -371,6 +373,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
         cudaFree(kv.second.twb);
         cudaFree(kv.second.pair);
         cudaFree(kv.second.perm);
+        cudaFree(kv.second.slot);
+        cudaFree(kv.second.spair);
     }
     for (auto& kv : ctx->dev_free)
         for (void* p : kv.second) cudaFree(p);
@@ -639,6 +643,62 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     p.twb = rec.twb;
     p.pair = rec.pair;
     p.perm = rec.perm;
+    {
+        // Slot order of the Hermitian pack / unpack loops (FftPlan::slot).  Windows of 64 column pairs
+        // are re-ordered greedily so that every aligned run of 8 slots (a quarter-warp, one 128-byte
+        // shared-memory wavefront) takes pairs whose pos(2c) fall into 8 different 16-byte bank groups;
+        // kept only if it lowers the wavefront count over all four accesses of a slot.
+        const int Nc = N / 2 + 1, npair = (Nc + 1) / 2;
+        auto quad = [&](int c) {
+            const int k0 = 2 * c, k1 = std::min(2 * c + 1, N - 1);
+            return make_int4(perm[k0], perm[(N - k0) % N], perm[k1], perm[(N - k1) % N]);
+        };
+        auto cost = [&](const std::vector<int>& order) {
+            long long tot = 0;
+            for (int s0 = 0; s0 < npair; s0 += 8) {
+                int cnt[4][8] = {{0}};
+                for (int s1 = s0; s1 < std::min(npair, s0 + 8); ++s1) {
+                    const int4 q = quad(order[s1]);
+                    cnt[0][q.x & 7]++; cnt[1][q.y & 7]++; cnt[2][q.z & 7]++; cnt[3][q.w & 7]++;
+                }
+                for (int a = 0; a < 4; ++a) tot += *std::max_element(cnt[a], cnt[a] + 8);
+            }
+            return tot;
+        };
+        std::vector<int> ident(npair), order;
+        for (int c = 0; c < npair; ++c) ident[c] = c;
+        const int win = 64;
+        for (int w0 = 0; w0 < npair; w0 += win) {
+            const int w1 = std::min(npair, w0 + win);
+            std::vector<int> bucket[8];
+            for (int c = w1 - 1; c >= w0; --c) bucket[perm[2 * c] & 7].push_back(c);      // (popped from the back: ascending)
+            int left = w1 - w0;
+            while (left > 0) {
+                int ids[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                std::stable_sort(ids, ids + 8, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+                const int take = std::min(8, left);
+                int got = 0;
+                for (int i = 0; i < 8 && got < take; ++i)
+                    if (!bucket[ids[i]].empty()) { order.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
+                while (got < take)                     // fewer than 8 bank groups left: the run cannot be conflict free
+                    for (int i = 0; i < 8 && got < take; ++i)
+                        if (!bucket[ids[i]].empty()) { order.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
+                left -= take;
+            }
+        }
+        if (getenv("PKB_NO_SLOTS") || cost(order) >= cost(ident)) order = ident;
+        std::vector<int4> sp(npair);
+        for (int s1 = 0; s1 < npair; ++s1) sp[s1] = quad(order[s1]);
+        CU(cudaMalloc((void**)&rec.slot, sizeof(int) * npair));
+        CU(cudaMalloc((void**)&rec.spair, sizeof(int4) * npair));
+        CU(cudaMemcpy(rec.slot, order.data(), sizeof(int) * npair, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rec.spair, sp.data(), sizeof(int4) * npair, cudaMemcpyHostToDevice));
+        p.slot = rec.slot;
+        p.spair = rec.spair;
+        if (getenv("PKB_PLAN_DEBUG"))
+            fprintf(stderr, "plan N=%d: pack/unpack wavefronts per 4 accesses: natural %lld, slots %lld (ideal %d)\n", N, cost(ident), cost(order),
+                    4 * ((npair + 7) / 8));
+    }
     p.grid_rows = p.grid_cols = 0;
     if (fft_smem_bytes(p) <= (size_t)ctx->max_smem) {
         // resident CTAs per SM of the persistent kernels at this plan's footprint (at most 4)
@@ -1876,6 +1936,16 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
             pkb_ctx* lane = ctx->lanes[l];
             const int r1 = sync_check(lane, "pkb_solve_batch lane");
             if (r1 && !rc) rc = r1;
+            // pkb_timing: chain phase of the last chain of lane 0, kernel construction of the last group
+            float ms = 0.f;
+            if (l == 0 && !r1 && cudaEventElapsedTime(&ms, lane->ev[1], lane->ev[2]) == cudaSuccess) {
+                ctx->timing[1] = ms;
+                ctx->timing[2] = 0.0;
+                if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing[0] = ms;
+                ctx->timing[3] = ctx->timing[0] + ctx->timing[1];
+            } else {
+                cudaGetLastError();      // (an unrecorded event is not a launch failure)
+            }
             ctx->launches += lane->launches;
             lane->launches = 0;
             for (auto& kv : lane->prof_acc) {
@@ -1918,6 +1988,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         if (status)
             for (int i = 0; i < np * nd; ++i) status[(size_t)p0 * nd + i] = ks->hmeta[i].status;
         // the lanes start once the kernels (and, first group, the cells) are on the device
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
         CU(cudaEventRecord(ctx->ev_lane, ctx->stream));
         for (int l = 0; l < nlanes; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l]->stream, ctx->ev_lane, 0));
         int rc = 0;

@@ -14,6 +14,10 @@ PY
 }
 c4() { tag=$1; shift; timeout 200 python bench.py --no-cpu-baseline "$@" < /dev/null > gpurun_out/u_c4_$tag.json 2> gpurun_out/u_c4_$tag.err; sum gpurun_out/u_c4_$tag.json c4_$tag; }
 c5() { tag=$1; shift; env "$@" timeout 200 python bench.py --workload kalbar_batch512 --steps 1 --warmup 1 --no-cpu-baseline $C5OPT < /dev/null > gpurun_out/u_c5_$tag.json 2> gpurun_out/u_c5_$tag.err; sum gpurun_out/u_c5_$tag.json c5_$tag; }
+cb() { echo "== $*"; for k in 361 241; do env $2 timeout 60 tools/chainbench_$1 4097 $k 10 < /dev/null; done; env $2 timeout 60 tools/chainbench_$1 801 641 20 < /dev/null; }
+cb nobfast PKB_NO_SLOTS=1
+cb bfast PKB_NO_SLOTS=1
+cb bfast A=1
 timeout 300 python -m pytest tests -m gpu -x -q < /dev/null > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 c4 default
 c4 nosteptorus --opt step_torus=0
