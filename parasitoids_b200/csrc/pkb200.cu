@@ -104,6 +104,7 @@ struct pkb_ctx {
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int occ_cap;            // resident CTAs per SM the persistent grids are sized for (4; tuning hook PKB_FFT_OCC)
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
+    int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
     int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
     std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
     cudaEvent_t ev_lane;
@@ -323,7 +324,8 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->fft_threads = PKB_ROWS_T;
     ctx->use_windows = 1;
     ctx->use_fusion = 1;
-    ctx->batch_lanes = 2;
+    ctx->batch_lanes = 4;
+    ctx->batch_group = 32;
     ctx->use_step_torus = 1;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
@@ -415,6 +417,11 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "step_torus")) {
         ctx->use_step_torus = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "batch_group")) {
+        if (value < 1 || value > 1024) return fail(PKB_EINVAL, "batch_group must be 1..1024");
+        ctx->batch_group = (int)value;
         return 0;
     }
     if (!strcmp(key, "batch_lanes")) {
@@ -1958,10 +1965,37 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         return rc;
     };
     // bound the group so that the accumulation windows (worst case the whole domain per problem) stay below ~8 GB
-    int group = (int)std::max<size_t>(1, std::min<size_t>(PKB_BATCH_GROUP, ((size_t)8 << 30) / (dom * dom * sizeof(double) * nd)));
-    DBuf<double> dout;
-    TRY(dout.alloc(ctx, (size_t)std::min(group, std::max(nprop, 1)) * nd * K));
-    for (int p0 = 0; p0 < nprop; p0 += group) {
+    int group = (int)std::max<size_t>(1, std::min<size_t>(ctx->batch_group, ((size_t)8 << 30) / (dom * dom * sizeof(double) * nd)));
+    // Groups are pipelined: the kernels of group g+1 are built on the parent's stream (and its small
+    // sizing D2H waited for) while the lanes still run the chains of group g; only then are the lanes
+    // drained and group g's samples copied out.  Two kernel sets and two output buffers are alive at a time.
+    DBuf<double> dout[2];
+    const size_t out_group = (size_t)std::min(group, std::max(nprop, 1)) * nd * K;
+    TRY(dout[0].alloc(ctx, out_group));
+    if (nprop > group) TRY(dout[1].alloc(ctx, out_group));
+    struct Pending {
+        pkb_kset* ks = nullptr;
+        int p0 = 0, np = 0, buf = 0;
+        int rc = 0;           // first error while its chains were enqueued
+        bool live = false;
+    } pend;
+    // wait for the group in flight, copy its samples out, release its kernels
+    auto finish = [&]() -> int {
+        if (!pend.live) return 0;
+        int rc = drain();
+        if (pend.rc) rc = pend.rc;
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(out + (size_t)pend.p0 * nd * K, dout[pend.buf].p, sizeof(double) * pend.np * nd * K,
+                                            cudaMemcpyDeviceToHost, ctx->stream);
+            if (e != cudaSuccess) rc = fail(PKB_ECUDA, "pkb_solve_batch: output copy failed: %s", cudaGetErrorString(e));
+            else rc = sync_check(ctx, "pkb_solve_batch outputs");
+        }
+        delete pend.ks;
+        pend = Pending();
+        return rc;
+    };
+    int gi = 0;
+    for (int p0 = 0; p0 < nprop; p0 += group, ++gi) {
         const int np = std::min(group, nprop - p0);
         std::vector<pkb_solve_args> sa(np, *base);
         std::vector<pkb_day_args> dargs((size_t)np * nd);
@@ -1978,32 +2012,37 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
             s.want_coo = 0; s.want_dense_host = 0; s.keep_dense_device = 0;
             solve_day_args(&s, dargs.data() + (size_t)p * nd);
         }
-        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        cudaEventRecord(ctx->ev[0], ctx->stream);
         pkb_kset* ks = nullptr;
-        TRY(kernels_build_dev(ctx, wind_dev, base->nd_wind, base->periods, dargs.data(), np * nd, 0, &ks));
-        struct KGuard {
-            pkb_kset* k;
-            ~KGuard() { delete k; }
-        } kguard{ks};
+        const int rcb = kernels_build_dev(ctx, wind_dev, base->nd_wind, base->periods, dargs.data(), np * nd, 0, &ks);
+        if (rcb) {
+            const std::string msg = g_err;      // (finish() may overwrite the message)
+            finish();
+            g_err = msg;
+            return rcb;
+        }
         if (status)
             for (int i = 0; i < np * nd; ++i) status[(size_t)p0 * nd + i] = ks->hmeta[i].status;
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        const int rcf = finish();              // the previous group (its chains overlapped the kernel construction above)
+        if (rcf) { delete ks; return rcf; }
         // the lanes start once the kernels (and, first group, the cells) are on the device
-        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-        CU(cudaEventRecord(ctx->ev_lane, ctx->stream));
-        for (int l = 0; l < nlanes; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l]->stream, ctx->ev_lane, 0));
-        int rc = 0;
-        for (int p = 0; p < np && !rc; ++p) {
-            SampleSink sink = {dcells.p, K, dout.p + (size_t)p * nd * K};
-            rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nd, nullptr, &sink);
+        cudaEventRecord(ctx->ev_lane, ctx->stream);
+        for (int l = 0; l < nlanes; ++l) cudaStreamWaitEvent(ctx->lanes[l]->stream, ctx->ev_lane, 0);
+        pend.ks = ks; pend.p0 = p0; pend.np = np; pend.buf = gi & 1; pend.live = true;
+        for (int p = 0; p < np && !pend.rc; ++p) {
+            SampleSink sink = {dcells.p, K, dout[pend.buf].p + (size_t)p * nd * K};
+            pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nd, nullptr, &sink);
         }
-        // one synchronisation per group (also before `ks` and the lanes' buffers go away on an error)
-        const int rc2 = drain();
-        if (rc) return rc;
-        if (rc2) return rc2;
-        CU(cudaMemcpyAsync(out + (size_t)p0 * nd * K, dout.p, sizeof(double) * np * nd * K, cudaMemcpyDeviceToHost, ctx->stream));
-        TRY(sync_check(ctx, "pkb_solve_batch outputs"));
+        if (pend.rc) {
+            const std::string msg = g_err;
+            const int rc = pend.rc;
+            finish();
+            g_err = msg;
+            return rc;
+        }
     }
-    return 0;
+    return finish();
 }
 
 extern "C" int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape) {

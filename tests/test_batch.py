@@ -61,11 +61,12 @@ def test_unpack_proposal_order():
         batch.unpack_proposal(DEFAULT[:-1])
 
 
-@pytest.mark.parametrize('prob_model,lanes', [(False, 2), (False, 1), (True, 3)])
-def test_solve_batch_matches_single_solves(pkb, prob_model, lanes):
+@pytest.mark.parametrize('prob_model,lanes,group', [(False, 2, 32), (False, 1, 2), (True, 3, 2)])
+def test_solve_batch_matches_single_solves(pkb, prob_model, lanes, group):
     """pkb_solve_batch (kernel construction batched over proposals, chains enqueued round-robin on
     `batch_lanes` child contexts, sample-cell emission only) against one Run.solve per proposal
-    sampled at the same cells of its dense output, for the population and the probability model."""
+    sampled at the same cells of its dense output, for the population and the probability model;
+    group = 2 splits the five proposals into three pipelined kernel-construction groups."""
     import warnings
     from parasitoids_b200 import batch
     w, props = _wind(), _proposals(5)
@@ -74,6 +75,7 @@ def test_solve_batch_matches_single_solves(pkb, prob_model, lanes):
         kw.update(prob_model=True, r_dur=1, r_number=1.0, r_start=None)
     ctx = pkb._lib.ctx()
     ctx.set_option('batch_lanes', lanes)
+    ctx.set_option('batch_group', group)
     try:
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -90,7 +92,8 @@ def test_solve_batch_matches_single_solves(pkb, prob_model, lanes):
                 assert ((got[b] != 0) != (ref != 0)).sum() == 0
                 assert np.allclose(got[b], ref, rtol=1e-12, atol=1e-15)
     finally:
-        ctx.set_option('batch_lanes', 2)
+        ctx.set_option('batch_lanes', 4)
+        ctx.set_option('batch_group', 32)
 
 
 def _free_port():
