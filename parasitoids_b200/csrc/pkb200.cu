@@ -651,7 +651,7 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
     p.pair = rec.pair;
     p.perm = rec.perm;
     {
-        // Slot order of the Hermitian pack / unpack loops (FftPlan::slot).  Windows of 64 column pairs
+        // Slot order of the Hermitian pack / unpack loops (FftPlan::slot).  Windows of 64 (up to 1024) column pairs
         // are re-ordered greedily so that every aligned run of 8 slots (a quarter-warp, one 128-byte
         // shared-memory wavefront) takes pairs whose pos(2c) fall into 8 different 16-byte bank groups;
         // kept only if it lowers the wavefront count over all four accesses of a slot.
@@ -674,26 +674,40 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         };
         std::vector<int> ident(npair), order;
         for (int c = 0; c < npair; ++c) ident[c] = c;
-        const int win = 64;
-        for (int w0 = 0; w0 < npair; w0 += win) {
-            const int w1 = std::min(npair, w0 + win);
-            std::vector<int> bucket[8];
-            for (int c = w1 - 1; c >= w0; --c) bucket[perm[2 * c] & 7].push_back(c);      // (popped from the back: ascending)
-            int left = w1 - w0;
-            while (left > 0) {
-                int ids[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-                std::stable_sort(ids, ids + 8, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
-                const int take = std::min(8, left);
-                int got = 0;
-                for (int i = 0; i < 8 && got < take; ++i)
-                    if (!bucket[ids[i]].empty()) { order.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
-                while (got < take)                     // fewer than 8 bank groups left: the run cannot be conflict free
+        auto greedy = [&](int win) {
+            std::vector<int> ord;
+            ord.reserve(npair);
+            for (int w0 = 0; w0 < npair; w0 += win) {
+                const int w1 = std::min(npair, w0 + win);
+                std::vector<int> bucket[8];
+                for (int c = w1 - 1; c >= w0; --c) bucket[perm[2 * c] & 7].push_back(c);      // (popped from the back: ascending)
+                int left = w1 - w0;
+                while (left > 0) {
+                    int ids[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                    std::stable_sort(ids, ids + 8, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+                    const int take = std::min(8, left);
+                    int got = 0;
                     for (int i = 0; i < 8 && got < take; ++i)
-                        if (!bucket[ids[i]].empty()) { order.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
-                left -= take;
+                        if (!bucket[ids[i]].empty()) { ord.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
+                    while (got < take)                     // fewer than 8 bank groups left: the run cannot be conflict free
+                        for (int i = 0; i < 8 && got < take; ++i)
+                            if (!bucket[ids[i]].empty()) { ord.push_back(bucket[ids[i]].back()); bucket[ids[i]].pop_back(); ++got; }
+                    left -= take;
+                }
             }
-        }
-        if (getenv("PKB_NO_SLOTS") || cost(order) >= cost(ident)) order = ident;
+            return ord;
+        };
+        // smallest window that gets within 1.75 x the conflict-free count (the bank group of pos(2c) may only
+        // change every R_0 R_1 bins, e.g. 80 at 10.8.8.7), else the best one found
+        const long long ideal = 4LL * ((npair + 7) / 8);
+        order = ident;
+        long long best = cost(ident);
+        if (!getenv("PKB_NO_SLOTS"))
+            for (int win = 64; win <= 1024 && 4 * best > 7 * ideal; win *= 2) {
+                std::vector<int> cand = greedy(win);
+                const long long cst = cost(cand);
+                if (cst < best) { best = cst; order.swap(cand); }
+            }
         std::vector<int4> sp(npair);
         for (int s1 = 0; s1 < npair; ++s1) sp[s1] = quad(order[s1]);
         CU(cudaMalloc((void**)&rec.slot, sizeof(int) * npair));
@@ -703,8 +717,8 @@ static int get_plan(pkb_ctx* ctx, int N, FftPlan* out) {
         p.slot = rec.slot;
         p.spair = rec.spair;
         if (getenv("PKB_PLAN_DEBUG"))
-            fprintf(stderr, "plan N=%d: pack/unpack wavefronts per 4 accesses: natural %lld, slots %lld (ideal %d)\n", N, cost(ident), cost(order),
-                    4 * ((npair + 7) / 8));
+            fprintf(stderr, "plan N=%d: pack/unpack wavefronts per 4 accesses: natural %lld, slots %lld (ideal %lld)\n", N, cost(ident), cost(order),
+                    ideal);
     }
     p.grid_rows = p.grid_cols = 0;
     if (fft_smem_bytes(p) <= (size_t)ctx->max_smem) {
