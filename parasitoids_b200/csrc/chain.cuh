@@ -96,7 +96,17 @@ __host__ __device__ __forceinline__ size_t spec_size(int ncols, int ld) {
 struct ChainCtrl {
     int trunc;   // state is zero outside [0,D)^2: only that block is read
     int flag;    // boundary flag of the last step
-    int pad_[2];
+    int fused;   // the k_rows_inv that produced this state also transformed its interior row pairs for the next step
+    int pad_;
+};
+
+// Geometry of a step whose SOURCE state is truncated (ChainCtrl::trunc: zero outside [0,D)^2).  Its linear
+// convolution with a radius-m kernel spans D + 2m cells only, so such a step can run on a torus
+// N_t >= D + 2m < P + 2m.  Whether the source is truncated is only known on the device, so every
+// whole-torus launch carries both geometries and picks one at its start (uniformly over the grid).
+struct TruncGeom {
+    int N, Nc, ldW;          // torus side, spectral columns, Wt leading dimension (0: no smaller torus, use the step's own)
+    int cols_kb;             // k_cols geometry of that plan at the launch's CTA size
 };
 
 struct StepMeta {   // one per emitted solution
@@ -177,7 +187,11 @@ __host__ __device__ __forceinline__ bool fused_pair(int r0, int P, int m) {
 // the fusion needs room for the reduction scratch in the (zero) tail of the transform buffer
 __host__ __device__ __forceinline__ bool rows_fusable(int N, int P) { return N - 48 >= P; }
 __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
-                                       cplx* __restrict__ Yt, FftPlan plan, int pre_m) {
+                                       cplx* __restrict__ Yt, FftPlan plan, int pre_m, TruncGeom tg, FftPlan plan_t) {
+    if (tg.N && ctrl->trunc) {      // truncated source: the smaller torus (TruncGeom)
+        d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
+        plan = plan_t;
+    }
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
@@ -187,7 +201,7 @@ __global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d
     const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
     const int njobs = (lim + 1) / 2;
     if (d.win) S += (size_t)d.wr0 * d.ldS + d.wc0;     // rows / columns below are relative to the window
-    const bool skip_interior = pre_m >= 0 && !d.win && !ctrl->trunc;
+    const bool skip_interior = pre_m >= 0 && !d.win && !ctrl->trunc && ctrl->fused;
     // border pairs only: [0, lo/2) and [hi_job, njobs), the interior pairs in between are done
     const int lo_job = skip_interior ? (pre_m + (pre_m & 1)) / 2 : njobs;
     const int hi_job = skip_interior ? (d.P - pre_m) / 2 : njobs;       // first pair with r0 + 1 >= P - pre_m
@@ -324,7 +338,15 @@ __device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, int 
 // Krt, only 2m+1 of them non-zero), forward FFT of the state column (inputs
 // straight from Yt), product, inverse FFT, rows needed by the fold straight to Wt.
 __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
-                                   const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan) {
+                                   const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan,
+                                   TruncGeom tg, FftPlan plan_t, const cplx* __restrict__ Krt_t) {
+    const bool tr = tg.N && ctrl->trunc;      // truncated source on its smaller torus (TruncGeom)
+    if (tr) {
+        d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
+        plan = plan_t;
+        plan.cols_kb = tg.cols_kb;
+        Krt = Krt_t;
+    }
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
@@ -334,7 +356,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
     const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
     const int N = d.N, nq = 2 * m + 1;
     const int L = plan.nstage, R0 = plan_radix(plan, 0), RL = plan_radix(plan, L - 1), nbl = N / RL;
-    const int hi = (d.win ? d.wn : d.P) + m;   // rows [0, extent + m) and [N-m, N) are needed downstream
+    const int hi = (d.win ? d.wn : (tr ? d.D : d.P)) + m;   // rows [0, extent + m) and [N-m, N) are needed downstream
     cplx* myscr = scr + (size_t)blockIdx.x * ((size_t)plan.cols_kb * RL * T);
     const int off_last = plan.ntw - 1;   // table offset of the last stage (one entry)
     for (int c = blockIdx.x; c < d.Nc; c += gridDim.x) {
@@ -473,6 +495,34 @@ __device__ __forceinline__ void rows_inv_decode(int job, int m, int P, int N, in
     }
 }
 
+// Truncated source on its own torus N_t (TruncGeom): linear-convolution row j lives in Wt row j for
+// j in [0, E), E = D + m, and in row N_t + j for j in [-m, 0); nothing else is non-zero.  Output row r of
+// the P torus = lin[r] (r < E) + lin[r - P] (r >= Lo, Lo = P - m).  Rows [0, min(E, Lo)) and [max(E, Lo), P)
+// have one source each and are paired two per transform; in between the rows either have both sources
+// (E > Lo: "fold" jobs, one row per transform) or none (E <= Lo: "zero" jobs, two rows each, no transform).
+__host__ __device__ __forceinline__ int rows_inv_jobs_trunc(int P, int D, int m) {
+    const int E = D + m, Lo = P - m;
+    const int a1 = E < Lo ? E : Lo, b1 = E < Lo ? Lo : E;
+    return (a1 + 1) / 2 + (E > Lo ? b1 - a1 : (b1 - a1 + 1) / 2) + (P - b1 + 1) / 2;
+}
+// kind: 0 pair, 1 fold, 2 zero
+__device__ __forceinline__ void rows_inv_decode_trunc(int job, int m, int P, int D, int Nt, int& ra, int& rb, int& out_a, int& out_b, int& kind) {
+    const int E = D + m, Lo = P - m;
+    const int a1 = E < Lo ? E : Lo, b1 = E < Lo ? Lo : E;
+    const int nA = (a1 + 1) / 2, nM = E > Lo ? b1 - a1 : (b1 - a1 + 1) / 2;
+    if (job < nA) {
+        kind = 0; out_a = 2 * job; out_b = out_a + 1 < a1 ? out_a + 1 : -1; ra = out_a; rb = out_b;
+    } else if (job < nA + nM) {
+        const int j = job - nA;
+        if (E > Lo) { kind = 1; out_a = a1 + j; out_b = -1; ra = out_a; rb = Nt - (P - out_a); }
+        else { kind = 2; out_a = a1 + 2 * j; out_b = out_a + 1 < b1 ? out_a + 1 : -1; ra = rb = -1; }
+    } else {
+        const int j = job - nA - nM;
+        kind = 0; out_a = b1 + 2 * j; out_b = out_a + 1 < P ? out_a + 1 : -1;
+        ra = Nt - (P - out_a); rb = out_b >= 0 ? Nt - (P - out_b) : -1;
+    }
+}
+
 // grid = persistent over rows_inv_jobs(P, m) jobs, block = T
 // A job is one inverse transform.  "Pair" jobs carry two interior output rows as
 // real and imaginary part; "fold" jobs carry the two linear-convolution rows that
@@ -480,7 +530,12 @@ __device__ __forceinline__ void rows_inv_decode(int job, int m, int P, int N, in
 __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc,
-                                       cplx* __restrict__ Yt_next) {
+                                       cplx* __restrict__ Yt_next, const ChainCtrl* __restrict__ src_ctrl, TruncGeom tg, FftPlan plan_t) {
+    const bool tr = tg.N && !d.win && src_ctrl->trunc;      // truncated source on its smaller torus (TruncGeom)
+    if (tr) {
+        d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
+        plan = plan_t;
+    }
     PKB_DYN_SMEM(raw);
     cplx* x = reinterpret_cast<cplx*>(raw);
     cplx* tws = x + plan.N;
@@ -488,7 +543,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     // idle whenever they are used (after a job's output loop; fft_smem_bytes() >= 1 KB)
     // (at the END of the buffer when the next step's forward row transform is fused in: the packed
     //  row pair at the start of the buffer is still needed then, and the tail beyond column P is read as zero)
-    const bool fuse = Yt_next != nullptr && !d.win && rows_fusable(plan.N, d.P);
+    const bool fuse = Yt_next != nullptr && !d.win && !tr && rows_fusable(plan.N, d.P);
     double* red = reinterpret_cast<double*>(raw) + (fuse ? 2 * (plan.N - 48) : 0);
     int* last = reinterpret_cast<int*>(red + PKB_RED_DOUBLES);
     const int tid = threadIdx.x, T = blockDim.x;
@@ -496,13 +551,20 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     __syncthreads();
     const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
     const int wout = d.wn + 2 * m;                       // window mode: side of the result
-    const int njobs = d.win ? (wout + 1) / 2 : rows_inv_jobs(P, m);
+    const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : rows_inv_jobs(P, m));
     const double scale = 1.0 / ((double)N * (double)N);
     const cplx zero = cmake(0.0, 0.0);
+    const int E = D + m, Lo = P - m;                     // truncated mode: extent of the positive rows / columns, first folded one
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         int ra, rb, out_a, out_b;
         bool fold;
-        if (d.win) {
+        bool zjob = false;                               // truncated mode: rows without any source (no transform)
+        if (tr) {
+            int kind;
+            rows_inv_decode_trunc(job, m, P, D, N, ra, rb, out_a, out_b, kind);
+            fold = kind == 1;
+            zjob = kind == 2;
+        } else if (d.win) {
             // linear rows j = -m + 2 job and j + 1 (mod N in Wt) -> state rows wr0 + j
             const int ja = 2 * job - m, jb = ja + 1;
             fold = false;
@@ -515,7 +577,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         }
         {   // next job's Wt rows -> L2 while this one is transformed
             const int nj = job + (int)gridDim.x;
-            if ((PKB_PREFETCH & 2) && !d.win && nj < njobs) {
+            if ((PKB_PREFETCH & 2) && !d.win && !tr && nj < njobs) {
                 int na, nb, oa, ob;
                 bool nf;
                 rows_inv_decode(nj, m, P, N, na, nb, oa, ob, nf);
@@ -528,7 +590,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         }
         // scatter the Hermitian pair Z = A + iB into digit-reversed order; each thread
         // handles two adjacent columns (32-byte loads per row)
-        const int npair = (Nc + 1) / 2;
+        const int npair = zjob ? 0 : (Nc + 1) / 2;
         for (int j0 = tid; j0 < npair; j0 += PKB_UNPACK_U * T) {
             int4 pr[PKB_UNPACK_U];
             int col[PKB_UNPACK_U];       // column pair handled by this slot (FftPlan::slot)
@@ -572,9 +634,9 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             }
         }
         __syncthreads();
-        fft_inverse_to(x, tws, plan, tid, T, SmemStore{x});
+        if (!zjob) fft_inverse_to(x, tws, plan, tid, T, SmemStore{x});
         __syncthreads();
-        if (!d.win) {
+        if (!d.win && !tr) {
             // fold the columns mod P in place (2m <= P, so the two ranges are disjoint)
             for (int c = tid; c < m; c += T) {
                 x[c] = cadd(x[c], x[c + P]);
@@ -594,7 +656,14 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
         const int Dc = D - col0;                                     // first pad column, relative to col0
         for (int c = tid; c < ncols; c += T) {
-            const cplx z = x[d.win ? (c < m ? c - m + N : c - m) : c];
+            cplx z;
+            if (tr) {
+                // columns fold like the rows: lin[c] (c < E) + lin[c - P] (c >= Lo), straight from the transform
+                z = (c < E && !zjob) ? x[c] : zero;
+                if (c >= Lo && !zjob) z = cadd(z, x[N - (P - c)]);
+            } else {
+                z = x[d.win ? (c < m ? c - m + N : c - m) : c];
+            }
             const double va = (fold ? z.x + z.y : z.x) * scale;
             dst_a[c] = va;
             if (pad_a || c >= Dc) st[0] = fmax(st[0], va);
@@ -647,7 +716,10 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     if (last[0]) {
         __threadfence();
         step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, tid, T);
-        if (tid == 0) *done = 0;
+        if (tid == 0) {
+            ctrl->fused = fuse ? 1 : 0;
+            *done = 0;
+        }
     }
 }
 

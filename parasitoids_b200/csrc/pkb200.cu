@@ -102,6 +102,7 @@ struct pkb_ctx {
     int fft_threads;
     int use_windows;        // fused solve: support-window steps (option "windows", default on)
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
+    int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
     int occ_cap;            // resident CTAs per SM the persistent grids are sized for (4; tuning hook PKB_FFT_OCC)
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
@@ -327,6 +328,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->batch_lanes = 4;
     ctx->batch_group = 32;
     ctx->use_step_torus = 1;
+    ctx->use_trunc_torus = 1;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
     CU(cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
@@ -413,6 +415,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fuse_rows")) {
         ctx->use_fusion = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "trunc_torus")) {
+        ctx->use_trunc_torus = value != 0;
         return 0;
     }
     if (!strcmp(key, "step_torus")) {
@@ -1039,6 +1045,7 @@ struct pkb_chain {
     DBuf<double> S[2];
     int cur;
     DBuf<cplx> Yt, Wt, Krt;
+    DBuf<cplx> Krt_t;       // kernel row spectra on the truncated-source torus (TruncGeom), when a caller brings none
     DBuf<cplx> cscr;        // k_cols: per-CTA parking space for the filter column spectrum
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
     size_t cscr_per_cta;
@@ -1164,9 +1171,39 @@ static int step_torus(pkb_chain* ch, int m, ChainDims* d, FftPlan* plan) {
     return 0;
 }
 
+// Geometry for a truncated source (TruncGeom in chain.cuh) next to the step's own (d, plan): torus
+// >= D + 2m, used by the kernels when the source state turns out truncated.  tg->N == 0: none.
+static int trunc_torus(pkb_chain* ch, int m, const ChainDims& d, const FftPlan& plan, TruncGeom* tg, FftPlan* plan_t) {
+    pkb_ctx* ctx = ch->ctx;
+    memset(tg, 0, sizeof *tg);
+    *plan_t = plan;
+    if (!ctx->use_trunc_torus) return 0;
+    const int Nt = pkb_smooth_len(std::max(2, d.D + 2 * m));
+    if (Nt >= d.N) return 0;
+    FftPlan p;
+    TRY(get_plan(ctx, Nt, &p));
+    if (p.grid_rows < 1 || p.grid_cols < 1) return 0;
+    // the launch is configured for the step's own plan: CTA sizes, shared memory and column scratch must cover this one too
+    const int RL = plan_radix(p, p.nstage - 1);
+    const int kb = (Nt / RL + plan.cols_threads - 1) / plan.cols_threads;
+    if ((size_t)kb * RL * plan.cols_threads > ch->cscr_per_cta) return 0;
+    tg->N = Nt;
+    tg->Nc = Nt / 2 + 1;
+    tg->ldW = (Nt + 1) / 2 * 2;
+    tg->cols_kb = kb;
+    *plan_t = p;
+    return 0;
+}
+// ChainDims of the truncated-source torus (kernel row spectra are built with these)
+static ChainDims trunc_dims(const ChainDims& d, const TruncGeom& tg) {
+    ChainDims t = d;
+    t.N = tg.N; t.Nc = tg.Nc; t.ldW = tg.ldW;
+    return t;
+}
+
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
-                     int pre_m = -1) {
+                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr) {
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
@@ -1194,28 +1231,41 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         if (plan.grid_rows < 1 || plan.grid_cols < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", d.N);
         if (!krt_ready) krt = ch->Krt.p;     // (spectra prepared for another torus do not apply: callers pass per-window ones)
     }
+    // second geometry for a truncated source (main chain steps only)
+    TruncGeom tg;
+    FftPlan plan_t;
+    memset(&tg, 0, sizeof tg);
+    plan_t = plan;
+    if (!win && allow_trunc) TRY(trunc_torus(ch, m, d, plan, &tg, &plan_t));
     // persistent grids: (resident CTAs per SM) x (SM count), capped by the job count
     const int T = plan.threads;
-    const size_t sm1 = fft_smem_bytes(plan);
+    const size_t sm1 = std::max(fft_smem_bytes(plan), fft_smem_bytes(plan_t));
     const int rows_in = win ? d.wn : d.P;
     if ((size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads > ch->cscr_per_cta)
         return fail(PKB_ELIMIT, "column scratch too small for torus side %d", d.N);
-    const int njobs = win ? (d.wn + 2 * m + 1) / 2 : rows_inv_jobs(d.P, m);
+    const int njobs = win ? (d.wn + 2 * m + 1) / 2 : std::max(rows_inv_jobs(d.P, m), tg.N ? rows_inv_jobs_trunc(d.P, d.D, m) : 0);
     if (win) {
         if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
-        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1);
+        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1, tg, plan_t);
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
-                  m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan);
+                  m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
-    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m);
+    if (tg.N && !krt_t) {
+        // no spectra for the truncated-source torus from the caller: built here (whether they are needed is only known on the device)
+        if (!ch->Krt_t.p) TRY(ch->Krt_t.alloc(ctx, spec_size(ch->d.Nc + 1, ch->d.ldK)));
+        krt_t = ch->Krt_t.p;
+        LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan_t.grid_rows), plan_t.threads, fft_smem_bytes(plan_t), K, Wk, m, trunc_dims(d, tg), krt_t, plan_t);
+    }
+    if (!tg.N) krt_t = krt;
+    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m, tg, plan_t);
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
-           ch->Wt.p, ch->cscr.p, plan);
+           ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
-           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr);
+           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t);
     return 0;
 }
 
@@ -1279,10 +1329,10 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
 }
 
 static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr,
-                           bool fuse_next = false, int pre_m = -1) {
+                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr) {
     const int nxt = ch->cur ^ 1;
     TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win,
-                  fuse_next, pre_m));
+                  fuse_next, pre_m, true, krt_t));
     ch->cur = nxt;
     return 0;
 }
@@ -1621,45 +1671,65 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     // chain (phase 1 left every kernel on the device): off the critical path.
     const size_t krt_stride = spec_size(d.Nc + 1, d.ldK);
     const int kr_chunk = (int)std::max<size_t>(1, std::min<size_t>(PKB_KR_MAXD, ((size_t)4 << 30) / (krt_stride * sizeof(cplx))));
-    DBuf<cplx> krt_all;
+    DBuf<cplx> krt_all, krt_all_t;      // (_t: on the truncated-source torus of each day, trunc_torus)
     TRY(krt_all.alloc(ctx, krt_stride * std::min(kr_chunk, nd)));
+    if (ctx->use_trunc_torus) TRY(krt_all_t.alloc(ctx, krt_stride * std::min(kr_chunk, nd)));
     int kr_first = -1;      // first day held in krt_all
-    auto day_spectra = [&](int n, cplx** out) -> int {
-        // spectra of day n (nullptr: the stencil path needs none)
+    auto day_spectra = [&](int n, cplx** out, cplx** out_t) -> int {
+        // spectra of day n (nullptr: the stencil path needs none; *out_t nullptr: no smaller truncated-source torus)
         *out = nullptr;
+        *out_t = nullptr;
         if (krad(n) <= ctx->stencil_max_radius) return 0;
         if (kr_first < 0 || n >= kr_first + kr_chunk) {
             kr_first = n;
             const int cnt = std::min(kr_chunk, nd - n);
-            // one launch per distinct step torus among the block's days (step_torus: a handful of sizes)
-            std::vector<int> tor(cnt);
-            std::vector<ChainDims> dims(cnt);
-            std::vector<FftPlan> plans(cnt);
+            // one launch per distinct torus among the block's days (step_torus / trunc_torus: a handful of sizes)
+            std::vector<int> tor(cnt), tor_t(cnt);
+            std::vector<ChainDims> dims(cnt), dims_t(cnt);
+            std::vector<FftPlan> plans(cnt), plans_t(cnt);
             for (int i = 0; i < cnt; ++i) {
                 TRY(step_torus(ch, krad(n + i), &dims[i], &plans[i]));
                 tor[i] = dims[i].N;
+                TruncGeom tg;
+                TRY(trunc_torus(ch, krad(n + i), dims[i], plans[i], &tg, &plans_t[i]));
+                tor_t[i] = krt_all_t.p ? tg.N : 0;
+                dims_t[i] = tg.N ? trunc_dims(dims[i], tg) : dims[i];
             }
-            std::vector<int> sizes(tor);
-            std::sort(sizes.begin(), sizes.end());
-            sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
-            for (int Nd : sizes) {
-                KrBatch kb;
-                memset(&kb, 0, sizeof kb);
-                kb.nd = cnt;
-                int rep = -1;
-                for (int i = 0; i < cnt; ++i) {
-                    kb.m[i] = krad(n + i);
-                    const bool mine = tor[i] == Nd && kb.m[i] > ctx->stencil_max_radius;
-                    if (mine) rep = i;
-                    kb.job0[i + 1] = kb.job0[i] + (mine ? kb.m[i] + 1 : 0);
+            auto batch = [&](const std::vector<int>& tr, const std::vector<ChainDims>& dm, const std::vector<FftPlan>& pls, cplx* dst) -> int {
+                std::vector<int> sizes(tr);
+                std::sort(sizes.begin(), sizes.end());
+                sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+                for (int Nd : sizes) {
+                    if (Nd == 0) continue;
+                    KrBatch kb;
+                    memset(&kb, 0, sizeof kb);
+                    kb.nd = cnt;
+                    int rep = -1;
+                    for (int i = 0; i < cnt; ++i) {
+                        kb.m[i] = krad(n + i);
+                        const bool mine = tr[i] == Nd && kb.m[i] > ctx->stencil_max_radius;
+                        if (mine) rep = i;
+                        kb.job0[i + 1] = kb.job0[i] + (mine ? kb.m[i] + 1 : 0);
+                    }
+                    if (rep < 0 || kb.job0[cnt] == 0) continue;
+                    const FftPlan& pl = pls[rep];
+                    LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[cnt], pl.grid_rows), pl.threads, fft_smem_bytes(pl), kern(n), nW, ks->W, kb,
+                           dm[rep], dst, krt_stride, pl);
                 }
-                if (rep < 0 || kb.job0[cnt] == 0) continue;
-                const FftPlan& pl = plans[rep];
-                LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[cnt], pl.grid_rows), pl.threads, fft_smem_bytes(pl), kern(n), nW, ks->W, kb,
-                       dims[rep], krt_all.p, krt_stride, pl);
-            }
+                return 0;
+            };
+            TRY(batch(tor, dims, plans, krt_all.p));
+            if (krt_all_t.p) TRY(batch(tor_t, dims_t, plans_t, krt_all_t.p));
         }
         *out = krt_all.p + krt_stride * (n - kr_first);
+        if (krt_all_t.p) {
+            ChainDims dd;
+            FftPlan pp, pt;
+            TruncGeom tg;
+            TRY(step_torus(ch, krad(n), &dd, &pp));
+            TRY(trunc_torus(ch, krad(n), dd, pp, &tg, &pt));
+            if (tg.N) *out_t = krt_all_t.p + krt_stride * (n - kr_first);
+        }
         return 0;
     };
 
@@ -1757,13 +1827,14 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
             const int* wp = step_window(n);
             cplx* krt = nullptr;
-            if (!wp) TRY(day_spectra(n, &krt));
+            cplx* krt_t = nullptr;
+            if (!wp) TRY(day_spectra(n, &krt, &krt_t));
             else TRY(window_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
             const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
@@ -1833,10 +1904,11 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         for (int n = rd; n < nd; ++n) {
             const int* wp = rd == 1 ? step_window(n) : nullptr;
             cplx* kday = nullptr;
-            if (!wp) TRY(day_spectra(n, &kday));
+            cplx* kday_t = nullptr;
+            if (!wp) TRY(day_spectra(n, &kday, &kday_t));
             else TRY(window_spectra(n, &kday));
             const bool fuse = rd == 1 && !wp && !wmode && n + 1 < nd && fusable(n);
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
@@ -1947,6 +2019,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         lane->use_windows = ctx->use_windows;
         lane->use_fusion = ctx->use_fusion;
         lane->use_step_torus = ctx->use_step_torus;
+        lane->use_trunc_torus = ctx->use_trunc_torus;
         lane->prof_on = ctx->prof_on;
     }
     // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel

@@ -463,3 +463,49 @@ def test_step_torus_matches_chain_torus(pkb):
     finally:
         ctx.set_option('step_torus', 1)
         ctx.set_option('windows', 1)
+
+
+def test_trunc_torus_matches_full_torus(pkb):
+    """Option trunc_torus: a step whose source state was truncated by the boundary flag (CalcSol.py:200-201)
+    spans only D + 2m cells, so it runs on a torus >= D + 2m instead of >= P + 2m; the kernels pick the
+    geometry on the device from the flag.  Same circular convolution mod P, so the solutions agree to
+    rounding with the option off and with the oracle -- both models, with flags tripping."""
+    rng = np.random.default_rng(5)
+    nd, periods, rad_res, rad_dist = 7, 96, 60, 3000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        x = np.cumsum(rng.normal(0, 0.05, nd * periods)).reshape(nd, periods)
+        w[:, :, c] = 0.3 * np.sin(np.linspace(0, 6, nd * periods)).reshape(nd, periods) + x * 0.2
+    w[:, :, 0] = np.abs(w[:, :, 0]) + 0.4               # mass reaches the boundary: flags trip
+    w[:, :, 1] *= np.linspace(0.2, 2.0, nd)[:, None]    # kernel radii differ from day to day
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    lib = pkb._lib.lib()
+    try:
+        for windows in (0, 1):
+            ctx.set_option('windows', windows)
+            for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=1, r_number=1000.0), dict(prob_model=False, r_dur=2, r_number=1000.0)):
+                out = {}
+                for tt in (1, 0):
+                    ctx.set_option('trunc_torus', tt)
+                    with warnings.catch_warnings():
+                        warnings.simplefilter('ignore')
+                        res = pkb.Run.solve(w, nd, *args, want_coo=False, want_dense=True, **kw)
+                    out[tt] = ([res.dense(d) for d in range(nd)], res.flags(), res.radii(), res.dom_len, res.P)
+                    res.close()
+                flags, radii, D, P = out[1][1:]
+                assert out[0][1] == flags
+                # a flagged state is followed by a step whose truncated-source torus is smaller than its own
+                assert any(flags[n - 1] and lib.pkb_smooth_len(D + 2 * radii[n]) < lib.pkb_smooth_len(P + 2 * radii[n])
+                           for n in range(2, nd)), 'no step could have used the smaller torus'
+                scale = kw.get('r_number', 1.0)
+                for d in range(nd):
+                    H.assert_thresholded_parity(out[1][0][d] / scale, out[0][0][d] / scale, what='day %d' % d, max_abs=1e-15)
+                if kw['prob_model']:
+                    ref = _oracle_solve(w, nd, args, rad_res)
+                    for d in range(nd):
+                        H.assert_thresholded_parity(out[1][0][d], ref[d].toarray(), what='oracle day %d' % d)
+    finally:
+        ctx.set_option('trunc_torus', 1)
+        ctx.set_option('windows', 1)
