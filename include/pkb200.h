@@ -80,8 +80,14 @@ int pkb_version(void);
 int pkb_create(int device, pkb_ctx** out);
 int pkb_destroy(pkb_ctx* ctx);
 int pkb_sync(pkb_ctx* ctx);
-/* option keys: "stencil_max_radius" (direct-convolution switch point),
- * "fft_threads", "windows" (0/1: support-window chain steps in pkb_solve, default 1) */
+/* option keys: "stencil_max_radius" (direct-convolution switch point), "fft_threads",
+ * "windows" (0/1: support-window chain steps in pkb_solve, default 1),
+ * "fuse_rows" (0/1: inverse row pass also runs the next step's forward row pass, default 1),
+ * "step_torus" (0/1: whole-torus steps on the smallest 7-smooth torus >= P + 2m of that day's kernel, default 1),
+ * "trunc_torus" (0/1: steps from a truncated (flagged) state on a torus >= dom_len + 2m, default 1),
+ * "batch_lanes" (1..8: proposals of pkb_solve_batch in flight at once, default 4),
+ * "batch_group" (proposals per kernel-construction group of pkb_solve_batch, default 32).
+ * All of them select between implementations of the same arithmetic; results agree to rounding. */
 int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
 /* device time in ms of the phases of the last pkb_solve: [0] phase 1,
  * [1] chain, [2] output compaction + D2H, [3] total */
