@@ -737,24 +737,44 @@ __global__ void k_set_ctrl(ChainCtrl* __restrict__ ctrl, int trunc, int flag) {
 __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const StepMeta* __restrict__ meta, double negval, int prob_model,
                              int strict, double* __restrict__ out, int* __restrict__ rownnz) {
     PKB_SHARED(int, cnt, 1);
-    const int r = blockIdx.x;
     const double add = prob_model ? meta->add : 0.0;
-    const double* src = S + (size_t)r * d.ldS;
-    double* dst = out + (size_t)r * d.D;
-    if (rownnz && threadIdx.x == 0) cnt[0] = 0;
-    if (rownnz) __syncthreads();
-    int n = 0;
-    for (int c = threadIdx.x; c < d.D; c += blockDim.x) {
-        const double v = src[c];
-        const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
-        const double o = keep ? v + add : 0.0;
-        dst[c] = o;
-        n += o != 0.0 ? 1 : 0;
-    }
-    if (rownnz) {       // per-row non-zero count for the COO compaction (saves a pass over the output)
-        if (n) atomicAdd(&cnt[0], n);
-        __syncthreads();
-        if (threadIdx.x == 0) rownnz[r] = cnt[0];
+    // rows blockIdx.x, blockIdx.x + gridDim.x, ...: one CTA per row (grid = D), or a few small persistent
+    // CTAs that trickle through the day next to the FFT kernels of the following step (fused solve)
+    for (int r = blockIdx.x; r < d.D; r += gridDim.x) {
+        const double* src = S + (size_t)r * d.ldS;
+        double* dst = out + (size_t)r * d.D;
+        if (rownnz) {
+            __syncthreads();                 // (the previous row's count has been read)
+            if (threadIdx.x == 0) cnt[0] = 0;
+            __syncthreads();
+        }
+        int n = 0;
+        const int T = blockDim.x;
+        int c = threadIdx.x;
+        for (; c + 3 * T < d.D; c += 4 * T) {          // four independent loads in flight per thread
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = src[c + u * T];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool keep = strict ? (v[u] > negval) : (v[u] != 0.0 && !(v[u] < negval));
+                const double o = keep ? v[u] + add : 0.0;
+                dst[c + u * T] = o;
+                n += o != 0.0 ? 1 : 0;
+            }
+        }
+        for (; c < d.D; c += T) {
+            const double v = src[c];
+            const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
+            const double o = keep ? v + add : 0.0;
+            dst[c] = o;
+            n += o != 0.0 ? 1 : 0;
+        }
+        if (rownnz) {       // per-row non-zero count for the COO compaction (saves a pass over the output)
+            if (n) atomicAdd(&cnt[0], n);
+            __syncthreads();
+            if (threadIdx.x == 0) rownnz[r] = cnt[0];
+        }
     }
 }
 

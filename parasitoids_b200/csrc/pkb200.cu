@@ -103,6 +103,8 @@ struct pkb_ctx {
     int use_windows;        // fused solve: support-window steps (option "windows", default on)
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
+    int emit_ctas;          // fused solve: side-stream emission as this many persistent 64-thread CTAs (option "emit_ctas"; 0, the
+                            // default: one 256-thread CTA per row -- the small persistent CTAs measured slower)
     int occ_cap;            // resident CTAs per SM the persistent grids are sized for (4; tuning hook PKB_FFT_OCC)
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
@@ -334,6 +336,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     CU(cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
+    ctx->emit_ctas = 0;
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
@@ -415,6 +418,11 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fuse_rows")) {
         ctx->use_fusion = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "emit_ctas")) {
+        if (value < 0 || value > 65535) return fail(PKB_EINVAL, "emit_ctas must be 0..65535");
+        ctx->emit_ctas = (int)value;
         return 0;
     }
     if (!strcmp(key, "trunc_torus")) {
@@ -1057,6 +1065,7 @@ struct pkb_chain {
     DBuf<double> kup;       // uploaded filter window, (2*mmax+1)^2
     DBuf<double> coh[PKB_MAX_COHORTS];
     DBuf<cplx> kcache[PKB_MAX_COHORTS];   // cached row spectra of the release-day filters (fused solve)
+    DBuf<cplx> kcache_t[PKB_MAX_COHORTS]; // the same on each filter's truncated-source torus (trunc_torus)
     int kcache_m[PKB_MAX_COHORTS];
     double negval;          // threshold the row statistics were taken with
     bool stats_valid;
@@ -1203,7 +1212,7 @@ static ChainDims trunc_dims(const ChainDims& d, const TruncGeom& tg) {
 
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
-                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr) {
+                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true) {
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
@@ -1258,8 +1267,10 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         // no spectra for the truncated-source torus from the caller: built here (whether they are needed is only known on the device)
         if (!ch->Krt_t.p) TRY(ch->Krt_t.alloc(ctx, spec_size(ch->d.Nc + 1, ch->d.ldK)));
         krt_t = ch->Krt_t.p;
-        LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan_t.grid_rows), plan_t.threads, fft_smem_bytes(plan_t), K, Wk, m, trunc_dims(d, tg), krt_t, plan_t);
+        krt_t_ready = false;
     }
+    if (tg.N && !krt_t_ready)
+        LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan_t.grid_rows), plan_t.threads, fft_smem_bytes(plan_t), K, Wk, m, trunc_dims(d, tg), krt_t, plan_t);
     if (!tg.N) krt_t = krt;
     LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m, tg, plan_t);
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
@@ -1386,7 +1397,8 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
 
 // cohorts of earlier release days: cohort j = state (*) F[nf-1] (*) ... (*) F[j]
 // F[j]: device window (Wk[j], radius m[j]); krt[j]/ready[j]: optional cached spectra.
-static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, const int* m, int nf, cplx* const* krt, bool* ready) {
+static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, const int* m, int nf, cplx* const* krt, bool* ready,
+                          cplx* const* krt_t = nullptr, bool* ready_t = nullptr) {
     if (nf > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "at most %d earlier release days are supported", PKB_MAX_COHORTS);
     pkb_ctx* ctx = ch->ctx;
     const ChainDims& d = ch->d;
@@ -1396,8 +1408,12 @@ static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, 
         if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
         cplx* kr = krt ? krt[j] : ch->Krt.p;
         const bool rdy = krt && ready && ready[j];
-        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, F[j], Wk[j], m[j], kr, rdy, 1 + j, 1));   // CalcSol.py:103-105 (same-shape re-FFT)
+        // CalcSol.py:103-105 (same-shape re-FFT); with cached spectra on the truncated-source torus that geometry travels along too
+        const bool tt = krt_t && ready_t && krt_t[j];
+        TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, F[j], Wk[j], m[j], kr, rdy, 1 + j, 1, nullptr, false, -1, tt, tt ? krt_t[j] : nullptr,
+                      tt && ready_t[j]));
         if (ready) ready[j] = true;
+        if (tt) ready_t[j] = true;
         src = ch->coh[j].p;
         src_ctrl = ch->ctrl.p + 1 + j;
     }
@@ -1844,7 +1860,8 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                 LAUNCH_ON(ctx, ctx->aux, k_emit_dense_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval,
                           1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * n);
             else
-                LAUNCH_ON(ctx, ctx->aux, k_emit_dense, D, PKB_EMIT_T, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
+                LAUNCH_ON(ctx, ctx->aux, k_emit_dense, ctx->emit_ctas > 0 ? std::min(D, ctx->emit_ctas) : D, ctx->emit_ctas > 0 ? 64 : PKB_EMIT_T, 0,
+                          (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
                           res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
             if (a->want_coo) res->counted[n] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
@@ -1858,14 +1875,19 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         const double* F[PKB_MAX_COHORTS];
         int Wk[PKB_MAX_COHORTS], mm[PKB_MAX_COHORTS];
         cplx* krt[PKB_MAX_COHORTS];
-        bool ready[PKB_MAX_COHORTS];
+        cplx* krt_t[PKB_MAX_COHORTS];
+        bool ready[PKB_MAX_COHORTS], ready_t[PKB_MAX_COHORTS];
         for (int j = 0; j < rd; ++j) {
-            F[j] = kern(j); Wk[j] = ks->W; mm[j] = krad(j); ready[j] = false; krt[j] = nullptr;
+            F[j] = kern(j); Wk[j] = ks->W; mm[j] = krad(j); ready[j] = false; krt[j] = nullptr; ready_t[j] = false; krt_t[j] = nullptr;
             if (krad(j) > D / 2) return fail(PKB_ELIMIT, "kernel radius %d is larger than the domain radius", krad(j));
         }
         for (int j = 0; j + 1 < rd; ++j) {
             TRY(ch->kcache[j].alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
             krt[j] = ch->kcache[j].p;
+            if (ctx->use_trunc_torus) {
+                TRY(ch->kcache_t[j].alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
+                krt_t[j] = ch->kcache_t[j].p;
+            }
         }
         // r_spread[j] as a state (Run.py:469-474); `spread` holds the latest one
         DBuf<double> spread;
@@ -1889,7 +1911,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         // release days (CalcSol.py:296-306)
         for (int day = 1; day < rd; ++day) {
             TRY(set_state_kernel_dev(ch, kern(day), ks->W, krad(day)));
-            TRY(back_solve_dev(ch, F, Wk, mm, day, krt, ready));
+            TRY(back_solve_dev(ch, F, Wk, mm, day, krt, ready, krt_t, ready_t));
             double wsum = 0.0;
             for (int c = 0; c <= day; ++c) {
                 ca.S[c] = c < day ? ch->coh[c].p : ch->S[ch->cur].p;
@@ -1911,7 +1933,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-            TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready));
+            TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready, krt_t, ready_t));
             for (int c = 0; c < rd; ++c) {
                 ca.S[c] = c < rd - 1 ? ch->coh[c].p : ch->S[ch->cur].p;
                 ca.w[c] = a->r_dist[c];
