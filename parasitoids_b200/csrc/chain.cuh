@@ -28,7 +28,14 @@
 // kernels (r_small_vals, cohort superposition), the COO compaction kernels and
 // the direct stencil for tiny kernels.  While the state's exact support still
 // fits inside the domain a step runs on a torus sized for that support window
-// (ChainDims::win).  DESIGN.md sections 3-5 give the layout and the numbers.
+// (ChainDims::win).  Whole-torus steps of the fused solve carry up to three
+// refinements, all picked per step and all the same circular convolution mod P
+// to rounding: the step's own torus N >= P + 2m for THAT day's m
+// (pkb200.cu:step_torus); a second geometry N_t >= D + 2m that the kernels switch
+// to on the device when the source state is truncated (TruncGeom); and, between
+// two steps on one torus, the next step's forward row pass run by k_rows_inv on
+// the row pair it still holds (Yt_next, ChainCtrl::fused).  DESIGN.md sections
+// 3-5 give the layout and the numbers.
 #pragma once
 #include "fft_smem.cuh"
 
