@@ -331,9 +331,9 @@ def main():
         raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     if world > 1:
-        # (NCCL_DEBUG=VERSION, some images' default, prints "NCCL version ..." on stdout next to the JSON line)
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL writes its debug output (at NCCL_DEBUG=VERSION/WARN the "NCCL version ..." line) to stdout,
+        # next to the one JSON line the driver parses: send it to stderr instead
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from parasitoids_b200 import Run, _lib, batch
     ctx = _lib.ctx(local)
