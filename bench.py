@@ -331,10 +331,20 @@ def main():
         raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its debug output (at NCCL_DEBUG=VERSION/WARN the "NCCL version ..." line) to stdout,
-        # next to the one JSON line the driver parses: send it to stderr instead
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # With NCCL_DEBUG >= VERSION (this image's default) NCCL printf()s "NCCL version ..." to stdout when the
+        # first communicator is created -- next to the one JSON line the driver parses.  File descriptor 1 points
+        # at stderr while that happens (init + one barrier), then it is restored.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from parasitoids_b200 import Run, _lib, batch
     ctx = _lib.ctx(local)
     for kv in args.opt:

@@ -537,7 +537,8 @@ __device__ __forceinline__ void rows_inv_decode_trunc(int job, int m, int P, int
 __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc,
-                                       cplx* __restrict__ Yt_next, const ChainCtrl* __restrict__ src_ctrl, TruncGeom tg, FftPlan plan_t) {
+                                       cplx* __restrict__ Yt_next, const ChainCtrl* __restrict__ src_ctrl, TruncGeom tg, FftPlan plan_t,
+                                       int desc_order) {
     const bool tr = tg.N && !d.win && src_ctrl->trunc;      // truncated source on its smaller torus (TruncGeom)
     if (tr) {
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
@@ -562,7 +563,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     const double scale = 1.0 / ((double)N * (double)N);
     const cplx zero = cmake(0.0, 0.0);
     const int E = D + m, Lo = P - m;                     // truncated mode: extent of the positive rows / columns, first folded one
-    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+    // Whole-torus mode: jobs are taken in DESCENDING order.  The fold jobs (job < 2m) are the short ones --
+    // one output row and never a fused forward transform -- so they go last and the partial final round of
+    // the persistent grid is made of short jobs instead of the longest ones.
+    const bool descending = desc_order && !d.win && !tr;
+    for (int it = blockIdx.x; it < njobs; it += gridDim.x) {
+        const int job = descending ? njobs - 1 - it : it;
         int ra, rb, out_a, out_b;
         bool fold;
         bool zjob = false;                               // truncated mode: rows without any source (no transform)
@@ -583,8 +589,8 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
         }
         {   // next job's Wt rows -> L2 while this one is transformed
-            const int nj = job + (int)gridDim.x;
-            if ((PKB_PREFETCH & 2) && !d.win && !tr && nj < njobs) {
+            const int nj = job - (int)gridDim.x;        // (descending order)
+            if ((PKB_PREFETCH & 2) && !d.win && !tr && nj >= 0) {
                 int na, nb, oa, ob;
                 bool nf;
                 rows_inv_decode(nj, m, P, N, na, nb, oa, ob, nf);

@@ -105,6 +105,7 @@ struct pkb_ctx {
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
     int emit_ctas;          // fused solve: side-stream emission as this many persistent 64-thread CTAs (option "emit_ctas"; 0, the
                             // default: one 256-thread CTA per row -- the small persistent CTAs measured slower)
+    int rows_desc;          // k_rows_inv takes its jobs in descending order (short fold jobs last; option "rows_desc", default 1)
     int occ_cap;            // resident CTAs per SM the persistent grids are sized for (4; tuning hook PKB_FFT_OCC)
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
@@ -337,6 +338,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->emit_ctas = 0;
+    ctx->rows_desc = 1;
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
@@ -418,6 +420,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fuse_rows")) {
         ctx->use_fusion = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "rows_desc")) {
+        ctx->rows_desc = value != 0;
         return 0;
     }
     if (!strcmp(key, "emit_ctas")) {
@@ -1259,7 +1265,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
@@ -1276,7 +1282,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
            ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
-           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t);
+           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
     return 0;
 }
 
@@ -2042,6 +2048,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         lane->use_fusion = ctx->use_fusion;
         lane->use_step_torus = ctx->use_step_torus;
         lane->use_trunc_torus = ctx->use_trunc_torus;
+        lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
     }
     // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel
