@@ -112,6 +112,7 @@ struct pkb_ctx {
     int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
     std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
     cudaEvent_t ev_lane;
+    cudaEvent_t ev_kr[2];      // fused solve: kernel row spectra batched on the side stream (before / after)
     int sm_count;
     int max_smem;
 };
@@ -335,6 +336,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
     CU(cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_kr[i], cudaEventDisableTiming));
     CU(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     ctx->max_smem = kMaxSmem - kStaticSmemReserve;
     ctx->emit_ctas = 0;
@@ -377,6 +379,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (pkb_ctx* lane : ctx->lanes) pkb_destroy(lane);
     cudaEventDestroy(ctx->ev_lane);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_kr[i]);
     for (auto& kv : ctx->plans) {
         cudaFree(kv.second.tw0);
         cudaFree(kv.second.twb);
@@ -1697,7 +1700,13 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     TRY(krt_all.alloc(ctx, krt_stride * std::min(kr_chunk, nd)));
     if (ctx->use_trunc_torus) TRY(krt_all_t.alloc(ctx, krt_stride * std::min(kr_chunk, nd)));
     int kr_first = -1;      // first day held in krt_all
-    auto day_spectra = [&](int n, cplx** out, cplx** out_t) -> int {
+    bool kr_wait = false;   // the current block was launched on the side stream: the chain waits for ev_kr[1] before its first use
+    struct KrJoin {         // (also on error returns: the main stream joins the side-stream batch before krt_all* are released)
+        pkb_ctx* c;
+        bool* w;
+        ~KrJoin() { if (*w) cudaStreamWaitEvent(c->stream, c->ev_kr[1], 0); }
+    } kr_join{ctx, &kr_wait};
+    auto day_spectra = [&](int n, cplx** out, cplx** out_t, bool side = false) -> int {
         // spectra of day n (nullptr: the stencil path needs none; *out_t nullptr: no smaller truncated-source torus)
         *out = nullptr;
         *out_t = nullptr;
@@ -1705,6 +1714,12 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         if (kr_first < 0 || n >= kr_first + kr_chunk) {
             kr_first = n;
             const int cnt = std::min(kr_chunk, nd - n);
+            cudaStream_t strm = ctx->stream;
+            if (side) {      // ahead of the chain, next to its first (support-window) steps: the kernels exist once phase 1 is done
+                CU(cudaEventRecord(ctx->ev_kr[0], ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_kr[0], 0));
+                strm = ctx->aux;
+            }
             // one launch per distinct torus among the block's days (step_torus / trunc_torus: a handful of sizes)
             std::vector<int> tor(cnt), tor_t(cnt);
             std::vector<ChainDims> dims(cnt), dims_t(cnt);
@@ -1735,13 +1750,21 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                     }
                     if (rep < 0 || kb.job0[cnt] == 0) continue;
                     const FftPlan& pl = pls[rep];
-                    LAUNCH(ctx, k_kernel_rows_batch, std::min(kb.job0[cnt], pl.grid_rows), pl.threads, fft_smem_bytes(pl), kern(n), nW, ks->W, kb,
-                           dm[rep], dst, krt_stride, pl);
+                    LAUNCH_ON(ctx, strm, k_kernel_rows_batch, std::min(kb.job0[cnt], pl.grid_rows), pl.threads, fft_smem_bytes(pl), kern(n), nW, ks->W,
+                              kb, dm[rep], dst, krt_stride, pl);
                 }
                 return 0;
             };
             TRY(batch(tor, dims, plans, krt_all.p));
             if (krt_all_t.p) TRY(batch(tor_t, dims_t, plans_t, krt_all_t.p));
+            if (side) {
+                CU(cudaEventRecord(ctx->ev_kr[1], ctx->aux));
+                kr_wait = true;
+            }
+        }
+        if (kr_wait && !side) {     // first use by the chain of a block that was launched on the side stream
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kr[1], 0));
+            kr_wait = false;
         }
         *out = krt_all.p + krt_stride * (n - kr_first);
         if (krt_all_t.p) {
@@ -1840,6 +1863,17 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         return 0;
     };
 
+    {   // row spectra of the first block of days: on the side stream, hidden behind the first steps of the chain
+        const int first = a->prob_model ? 1 : a->r_dur;
+        int nf = -1;
+        for (int n = first; n < nd && nf < 0; ++n)
+            if (krad(n) > ctx->stencil_max_radius) nf = n;
+        // (the block starts at the first day the chain will ask for, exactly as the lazy path would)
+        if (nf >= 0 && nf == first) {
+            cplx *k0 = nullptr, *k1 = nullptr;
+            TRY(day_spectra(nf, &k0, &k1, true));
+        }
+    }
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
@@ -1948,6 +1982,10 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(emit_pop(n, 0.0, 0, 0));
             TRY(emitted(n, ctx->stream));
         }
+    }
+    if (kr_wait) {      // spectra launched on the side stream and never used: still join before their buffers are released
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kr[1], 0));
+        kr_wait = false;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (sink) {
