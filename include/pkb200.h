@@ -199,6 +199,8 @@ typedef struct pkb_solve_args {
     int want_dense_host;     /* copy dense solutions to host */
     int want_coo;            /* build COO (row-major) on device and copy to host */
     int keep_dense_device;   /* keep [ndays][D][D] on device (bench / gather) */
+    int keep_pre_device;     /* parity export: also keep every day's UN-thresholded domain grid (the `A[:D,:D]` of
+                              * CalcSol.py:189-190 / the cohort sum of :322 before r_small_vals) for pkb_result_pre */
 } pkb_solve_args;
 
 int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
@@ -216,8 +218,13 @@ int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int
  * identically zero outside the window while the spread has not reached the domain edge) */
 int pkb_result_window_steps(pkb_result* r, int* n);
 int pkb_result_day_meta(pkb_result* r, int day, pkb_day_meta* kmeta, pkb_step_meta* smeta);
+/* population model with r_dur > 1: flag / sums of the back_solve step (CalcSol.py:99-105) that produced cohort
+ * `cohort` (0 = first release day) on `day`; zeros when that cohort was not back-solved on that day */
+int pkb_result_cohort_meta(pkb_result* r, int day, int cohort, pkb_step_meta* smeta);
 /* dense solution of one day: device->host copy on demand */
 int pkb_result_dense(pkb_result* r, int day, double* out);
+/* dense UN-thresholded grid of one day (needs keep_pre_device) */
+int pkb_result_pre(pkb_result* r, int day, double* out);
 /* COO of all days (host pointers owned by the result, valid until destroy) */
 int pkb_result_coo(pkb_result* r, const long long** day_offsets /*[ndays+1]*/, const int** rows, const int** cols,
                    const double** vals);

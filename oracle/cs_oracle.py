@@ -20,6 +20,11 @@ from scipy import fft as sfft
 
 from .pm_oracle import r_small_vals  # noqa: F401  (CalcSol.py:112-136)
 
+# Threads pocketfft may use for the 2-D transforms (scipy.fft ``workers``).  None = 1 = what scipy.fftpack does in
+# the reference; the full-size parity tests set -1: every 1-D transform is computed by the same code whichever
+# thread runs it, so the results are bit-identical and only the wall time changes.
+WORKERS = None
+
 
 def pad_shape_of(shape, filt_shape):
     """CalcSol.py:20-21."""
@@ -32,14 +37,14 @@ def fft2(A, filt_shape):
     P = pad_shape_of(A.shape, filt_shape)
     buf = np.zeros(P)
     buf[:A.shape[0], :A.shape[1]] = A.toarray()
-    return sfft.fft2(buf)
+    return sfft.fft2(buf, workers=WORKERS)
 
 
 def ifft2_dense(A_hat, Ashape):
     """CalcSol.py:28-41 without the COO conversion.
 
     Returns (dense real P x P, flag)."""
-    A = sfft.ifft2(A_hat).real
+    A = sfft.ifft2(A_hat, workers=WORKERS).real
     r, c = int(Ashape[0]), int(Ashape[1])
     pads = []
     for blk in (A[r:, c:], A[:r, c:], A[r:, :c]):
@@ -73,7 +78,7 @@ def wrap_kernel(B, pad_shape):
 
 def fftconv2(A_hat, B):
     """CalcSol.py:45-66 -- A_hat *= FFT(wrap-shifted B), in place."""
-    A_hat *= sfft.fft2(wrap_kernel(B, A_hat.shape))
+    A_hat *= sfft.fft2(wrap_kernel(B, A_hat.shape), workers=WORKERS)
 
 
 def back_solve(prev_spread, cursol_hat, dom_shape, fixed=True, dense=False):
@@ -82,14 +87,14 @@ def back_solve(prev_spread, cursol_hat, dom_shape, fixed=True, dense=False):
     hat = np.array(cursol_hat)
     P = cursol_hat.shape
     for B in prev_spread[::-1]:
-        hat = sfft.fft2(wrap_kernel(B, P)) * hat
+        hat = sfft.fft2(wrap_kernel(B, P), workers=WORKERS) * hat
         A, flag = ifft2_dense(hat, dom_shape)
         sol = A[:int(dom_shape[0]), :int(dom_shape[1])]
         if flag:
             if fixed:
                 buf = np.zeros(P)
                 buf[:sol.shape[0], :sol.shape[1]] = sol
-                hat = sfft.fft2(buf)
+                hat = sfft.fft2(buf, workers=WORKERS)
             else:
                 hat = fft2(sparse.coo_matrix(sol), P)      # reference defect
         out.append(sol.copy() if dense else sparse.coo_matrix(sol))
@@ -115,7 +120,7 @@ def get_solutions(modelsol, pmf_list, days, ndays, dom_len, max_shape,
         if flag:
             buf = np.zeros(hat.shape)
             buf[:dom_len, :dom_len] = dom
-            hat = sfft.fft2(buf)
+            hat = sfft.fft2(buf, workers=WORKERS)
     if details is not None:
         details['pre'] = pre
         details['flags'] = flags
@@ -160,7 +165,7 @@ def get_populations(r_spread, pmf_list, days, ndays, dom_len, max_shape,
         if flag:
             buf = np.zeros(hat.shape)
             buf[:dom_len, :dom_len] = cur[-1]
-            hat = sfft.fft2(buf)
+            hat = sfft.fft2(buf, workers=WORKERS)
         cur[:-1] = back_solve(r_spread[:-1], hat, D, fixed=fixed, dense=True)
         tot = sum(cur[d] * dist(d + 1) for d in range(r_dur)) * r_number
         pre.append(np.array(tot))

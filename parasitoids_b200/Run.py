@@ -216,12 +216,29 @@ class SolveResult(object):
     def flags(self):
         return [bool(self.day_meta(d)[1].flag) for d in range(self.ndays)]
 
+    def cohort_flags(self, day, ncoh):
+        """Boundary flags of the ``back_solve`` steps of ``day`` in the reference's call order
+        (CalcSol.py:97-105: latest earlier release day first), population model with r_dur > 1."""
+        out = []
+        for j in range(ncoh - 1, -1, -1):
+            sm = _abi.StepMeta()
+            _lib.check(_lib.lib().pkb_result_cohort_meta(self.h, day, j, C.byref(sm)))
+            out.append(bool(sm.flag))
+        return out
+
     def radii(self):
         return [self.day_meta(d)[0].rad for d in range(self.ndays)]
 
     def dense(self, day):
         out = np.empty((self.dom_len, self.dom_len))
         _lib.check(_lib.lib().pkb_result_dense(self.h, day, _lib.dptr(out)))
+        return out
+
+    def pre(self, day):
+        """Un-thresholded domain grid of one day (``solve(..., keep_pre=True)``): what ``ifft2`` returns before
+        ``r_small_vals`` (CalcSol.py:189-190), or the cohort sum of CalcSol.py:322 for the population model."""
+        out = np.empty((self.dom_len, self.dom_len))
+        _lib.check(_lib.lib().pkb_result_pre(self.h, day, _lib.dptr(out)))
         return out
 
     def coo_arrays(self):
@@ -266,7 +283,7 @@ class SolveResult(object):
 
 
 def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur, r_number,
-                r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape):
+                r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre=False):
     """Fill a ``pkb_solve_args``; returns it with the arrays it points into (keep them alive)."""
     a = _abi.SolveArgs()
     if wind_device_ptr is not None:
@@ -291,17 +308,18 @@ def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_di
     a.want_dense_host = 1 if want_dense else 0
     a.want_coo = 1 if want_coo else 0
     a.keep_dense_device = 1 if keep_device else 0
+    a.keep_pre_device = 1 if keep_pre else 0
     return a, (keep, w)
 
 
 def solve(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model=True,
           r_dur=1, r_number=1.0, r_dist=None, r_start=None, want_coo=True, want_dense=False, keep_device=False,
-          wind_device_ptr=None, wind_shape=None, device=None):
+          wind_device_ptr=None, wind_shape=None, device=None, keep_pre=False):
     """Fused forward solve.  ``wind``: ndarray (nd_wind, periods, 3) of
     consecutive days (or None with ``wind_device_ptr``/``wind_shape`` for a
     wind array already resident on the device).  Returns a ``SolveResult``."""
     a, keep = _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur,
-                          r_number, r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape)
+                          r_number, r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre)
     h = C.c_void_p()
     _lib.check(_lib.lib().pkb_solve(_lib.ctx(device).h, C.byref(a), C.byref(h)))
     del keep

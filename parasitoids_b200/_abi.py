@@ -45,7 +45,8 @@ class SolveArgs(C.Structure):
     _fields_ = [('wind', C.c_void_p), ('wind_on_device', C.c_int), ('nd_wind', C.c_int), ('periods', C.c_int),
                 ('ndays', C.c_int), ('day', DayArgs), ('prob_model', C.c_int), ('r_dur', C.c_int),
                 ('r_number', C.c_double), ('r_dist', c_double_p), ('r_start', C.c_double), ('negval', C.c_double),
-                ('want_dense_host', C.c_int), ('want_coo', C.c_int), ('keep_dense_device', C.c_int)]
+                ('want_dense_host', C.c_int), ('want_coo', C.c_int), ('keep_dense_device', C.c_int),
+                ('keep_pre_device', C.c_int)]
 
 
 _H = C.c_void_p        # opaque handles
@@ -93,7 +94,9 @@ _SIGS = {
     'pkb_result_info': (C.c_int, [_H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'pkb_result_window_steps': (C.c_int, [_H, c_int_p]),
     'pkb_result_day_meta': (C.c_int, [_H, C.c_int, C.POINTER(DayMeta), C.POINTER(StepMeta)]),
+    'pkb_result_cohort_meta': (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(StepMeta)]),
     'pkb_result_dense': (C.c_int, [_H, C.c_int, c_double_p]),
+    'pkb_result_pre': (C.c_int, [_H, C.c_int, c_double_p]),
     'pkb_result_coo': (C.c_int, [_H, C.POINTER(c_ll_p), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p)]),
     'pkb_result_sample': (C.c_int, [_H, c_int_p, C.c_int, c_double_p]),
     'pkb_result_device_ptr': (C.c_int, [_H, _HP]),

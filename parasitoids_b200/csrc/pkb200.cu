@@ -1509,6 +1509,7 @@ struct pkb_result {
     DBuf<double> pre;       // optional [ndays][D][D] un-thresholded (parity export)
     std::vector<DayMeta> kmeta;
     std::vector<StepMeta> smeta;
+    std::vector<StepMeta> cmeta;   // [ndays][PKB_MAX_COHORTS]: back_solve steps of each day (population model, r_dur > 1)
     DBuf<int> rownnz;       // [ndays][D] non-zeros per output row (COO compaction)
     DBuf<long long> rowoff; // [ndays][D] exclusive scan of rownnz within each day
     DBuf<long long> daytot; // [ndays][2]: (0, non-zeros of the day)
@@ -1673,6 +1674,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     res->N = d.N;
     const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
     if (!sink) TRY(res->dense.alloc(ctx, nD * nd));
+    if (!sink && a->keep_pre_device) TRY(res->pre.alloc(ctx, nD * nd));      // parity export (pkb_result_pre)
     res->counted.assign(nd, 0);
     if (a->want_coo) {
         TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
@@ -1686,9 +1688,20 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         }
     }
     auto emitted = [&](int day, cudaStream_t strm) -> int { return a->want_coo ? coo_day_ready(ctx, res, day, strm) : 0; };
-    DBuf<StepMeta> dsm;
+    DBuf<StepMeta> dsm, dcm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
+    const bool want_cmeta = !sink && !a->prob_model && a->r_dur > 1;
+    if (want_cmeta) {
+        TRY(dcm.alloc(ctx, (size_t)nd * PKB_MAX_COHORTS));
+        CU(cudaMemsetAsync(dcm.p, 0, sizeof(StepMeta) * nd * PKB_MAX_COHORTS, ctx->stream));
+    }
+    // back_solve steps of `day` (cohorts 0 .. nc-1, slots 1 .. nc of the chain's meta block) -> cmeta[day][.]
+    auto keep_cmeta = [&](int day, int nc) -> int {
+        if (want_cmeta && nc > 0)
+            CU(cudaMemcpyAsync(dcm.p + (size_t)day * PKB_MAX_COHORTS, ch->meta.p + 1, sizeof(StepMeta) * nc, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    };
     auto kern = [&](int i) { return (const double*)(ks->acc.p + nW * (k0 + i)); };
     auto krad = [&](int i) { return ks->hmeta[k0 + i].rad; };
 
@@ -1879,6 +1892,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         if (sink) LAUNCH(ctx, k_copy_domain_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, sink->cells, sink->K, sink->out);
         else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
+        if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p);
         TRY(emitted(0, ctx->stream));
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
             const int* wp = step_window(n);
@@ -1893,6 +1907,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * n);
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
@@ -1943,7 +1958,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                        sink->out + (size_t)sink->K * day);
             else
                 LAUNCH(ctx, k_emit_population, D, 256, 0, ca, d, rn, centre_extra, add_centre, negval, first_day, res->dense.p + nD * day,
-                       (double*)nullptr);
+                       res->pre.p ? res->pre.p + nD * day : (double*)nullptr);
             return 0;
         };
         TRY(emit_pop(0, rn * (1 - a->r_dist[0]), 1, 1));
@@ -1952,6 +1967,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         for (int day = 1; day < rd; ++day) {
             TRY(set_state_kernel_dev(ch, kern(day), ks->W, krad(day)));
             TRY(back_solve_dev(ch, F, Wk, mm, day, krt, ready, krt_t, ready_t));
+            TRY(keep_cmeta(day, day));
             double wsum = 0.0;
             for (int c = 0; c <= day; ++c) {
                 ca.S[c] = c < day ? ch->coh[c].p : ch->S[ch->cur].p;
@@ -1974,6 +1990,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready, krt_t, ready_t));
+            TRY(keep_cmeta(n, rd - 1));
             for (int c = 0; c < rd; ++c) {
                 ca.S[c] = c < rd - 1 ? ch->coh[c].p : ch->S[ch->cur].p;
                 ca.w[c] = a->r_dist[c];
@@ -2000,6 +2017,10 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     if (a->want_coo) TRY(coo_collect(ctx, res));
     // (pageable destination: this copy blocks the host until the chain has finished, so it comes last)
     CU(cudaMemcpyAsync(res->smeta.data(), dsm.p, sizeof(StepMeta) * nd, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_cmeta) {
+        res->cmeta.resize((size_t)nd * PKB_MAX_COHORTS);
+        CU(cudaMemcpyAsync(res->cmeta.data(), dcm.p, sizeof(StepMeta) * nd * PKB_MAX_COHORTS, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     TRY(sync_check(ctx, "pkb_solve outputs"));
     float ms = 0.f;
@@ -2222,6 +2243,14 @@ extern "C" int pkb_result_day_meta(pkb_result* r, int day, pkb_day_meta* kmeta, 
     return 0;
 }
 
+extern "C" int pkb_result_cohort_meta(pkb_result* r, int day, int cohort, pkb_step_meta* smeta) {
+    if (!r || !smeta || day < 0 || day >= r->ndays || cohort < 0 || cohort >= PKB_MAX_COHORTS)
+        return fail(PKB_EINVAL, "pkb_result_cohort_meta: bad argument");
+    if (r->cmeta.empty()) memset(smeta, 0, sizeof(StepMeta));
+    else memcpy(smeta, &r->cmeta[(size_t)day * PKB_MAX_COHORTS + cohort], sizeof(StepMeta));
+    return 0;
+}
+
 extern "C" int pkb_result_dense(pkb_result* r, int day, double* out) {
     if (!r || !out || day < 0 || day >= r->ndays) return fail(PKB_EINVAL, "pkb_result_dense: bad argument");
     if (!r->dense.p) return fail(PKB_ESTATE, "pkb_result_dense: dense solutions were not kept (want_dense_host / keep_dense_device)");
@@ -2230,6 +2259,16 @@ extern "C" int pkb_result_dense(pkb_result* r, int day, double* out) {
     const size_t nD = (size_t)r->D * r->D;
     CU(cudaMemcpyAsync(out, r->dense.p + nD * day, nD * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx, "pkb_result_dense");
+}
+
+extern "C" int pkb_result_pre(pkb_result* r, int day, double* out) {
+    if (!r || !out || day < 0 || day >= r->ndays) return fail(PKB_EINVAL, "pkb_result_pre: bad argument");
+    if (!r->pre.p) return fail(PKB_ESTATE, "pkb_result_pre: the solve was run without keep_pre_device");
+    pkb_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t nD = (size_t)r->D * r->D;
+    CU(cudaMemcpyAsync(out, r->pre.p + nD * day, nD * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_result_pre");
 }
 
 extern "C" int pkb_result_coo(pkb_result* r, const long long** day_offsets, const int** rows, const int** cols, const double** vals) {
