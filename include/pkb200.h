@@ -36,8 +36,7 @@ extern "C" {
 #define PKB_ST_PMF_NEG2 16     /* :589 */
 #define PKB_ST_TOT_GT1 32      /* :590 */
 #define PKB_ST_WARNED 64       /* RuntimeWarning, :547-558 */
-#define PKB_ST_BORDERLINE 128  /* ring-growth test within 1e-13 of cdf_eps (:348) */
-#define PKB_ST_SUPPORT_OVF 256
+#define PKB_ST_BORDERLINE 128  /* ring-growth test (:348) within ring_tol of cdf_eps: decided by the reference-order running sum */
 
 typedef struct pkb_ctx pkb_ctx;       /* one device + stream + plan cache */
 typedef struct pkb_kset pkb_kset;     /* device-resident set of per-day kernels */
@@ -67,10 +66,10 @@ typedef struct pkb_day_meta {
 } pkb_day_meta;
 
 typedef struct pkb_step_meta {
-    double padmax, ksum, add, vmin;
+    double padmax, ksum, add, padabs;   /* padmax: max over the pad (the flag compares it with 1e-8); padabs: max |value| there */
     long long kcnt;
     int flag;     /* boundary flag, CalcSol.py:36-40 */
-    int pad_;
+    int spec;     /* this step started from the stored spectrum of the state (option "spectral") */
 } pkb_step_meta;
 
 const char* pkb_last_error(void);
@@ -85,6 +84,10 @@ int pkb_sync(pkb_ctx* ctx);
  * "fuse_rows" (0/1: inverse row pass also runs the next step's forward row pass, default 1),
  * "step_torus" (0/1: whole-torus steps on the smallest 7-smooth torus >= P + 2m of that day's kernel, default 1),
  * "trunc_torus" (0/1: steps from a truncated (flagged) state on a torus >= dom_len + 2m, default 1),
+ * "spectral" (0/1: spectral-resident chain steps while the content outside the domain is below 1e-14, default 1;
+ *             the one option whose results differ by more than rounding: by at most 1e-12, see chain.cuh),
+ * "ring_tol" (support-ring decisions of get_mvn_cdf_values closer than this to cdf_eps are re-taken with the reference's
+ *             own running sum, ParasitoidModel.py:345-373; default 1e-12, 1.0 forces that path everywhere),
  * "batch_lanes" (1..8: proposals of pkb_solve_batch in flight at once, default 4),
  * "batch_group" (proposals per kernel-construction group of pkb_solve_batch, default 32).
  * All of them select between implementations of the same arithmetic; results agree to rounding. */

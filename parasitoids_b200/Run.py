@@ -226,6 +226,10 @@ class SolveResult(object):
             out.append(bool(sm.flag))
         return out
 
+    def spectral_steps(self):
+        """Days whose chain step started from the stored spectrum of the state (option ``spectral``)."""
+        return [d for d in range(self.ndays) if self.day_meta(d)[1].spec]
+
     def radii(self):
         return [self.day_meta(d)[0].rad for d in range(self.ndays)]
 

@@ -21,7 +21,6 @@ ST_PMF_NEG2 = 16
 ST_TOT_GT1 = 32
 ST_WARNED = 64
 ST_BORDERLINE = 128
-ST_SUPPORT_OVF = 256
 
 
 class DayArgs(C.Structure):
@@ -37,8 +36,8 @@ class DayMeta(C.Structure):
 
 
 class StepMeta(C.Structure):
-    _fields_ = [('padmax', C.c_double), ('ksum', C.c_double), ('add', C.c_double), ('vmin', C.c_double),
-                ('kcnt', C.c_longlong), ('flag', C.c_int), ('pad_', C.c_int)]
+    _fields_ = [('padmax', C.c_double), ('ksum', C.c_double), ('add', C.c_double), ('padabs', C.c_double),
+                ('kcnt', C.c_longlong), ('flag', C.c_int), ('spec', C.c_int)]
 
 
 class SolveArgs(C.Structure):

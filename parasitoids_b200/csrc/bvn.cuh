@@ -174,4 +174,32 @@ __device__ inline double square_prob(const BvnPar& p, double cell, int h, double
     return mvn_rect(p, lo, up, lo, up, mux, muy);
 }
 
+// Support half-width by the reference's own running sum (ParasitoidModel.py:338-373): centre cell, then per ring
+// the four corners and the four sides in call order, one mvnun per cell, until 1 - val_sum < cdf_eps.  Used only
+// where the one-rectangle form above lands within `ring_tol` of cdf_eps (its value agrees with the running sum to
+// ~1e-15, so only there could the decision differ); single thread, (2 hmax + 1)^2 rectangles at most.
+__device__ inline int ring_halfwidth_ref_order(const BvnPar& p, double cell, double mux, double muy, double cdf_eps, int hmax) {
+    const double r = cell / 2;
+    double val_sum = mvn_rect(p, -r, -r + cell, -r, -r + cell, mux, muy);
+    int h = 0;
+    while (1.0 - val_sum >= cdf_eps && h < hmax) {
+        ++h;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const int ii = a ? h : -h, jj = b ? h : -h;
+                const double xl = ii * cell - r, yl = jj * cell - r;
+                val_sum += mvn_rect(p, xl, xl + cell, yl, yl + cell, mux, muy);
+            }
+        for (int a = 0; a < 2; ++a) {
+            const int ii = a ? h : -h;
+            for (int jj = -h + 1; jj < h; ++jj) {
+                const double l0 = ii * cell - r, l1 = jj * cell - r;
+                val_sum += mvn_rect(p, l0, l0 + cell, l1, l1 + cell, mux, muy);     // cell (ii, jj)
+                val_sum += mvn_rect(p, l1, l1 + cell, l0, l0 + cell, mux, muy);     // cell (jj, ii)
+            }
+        }
+    }
+    return h;
+}
+
 }  // namespace pkb

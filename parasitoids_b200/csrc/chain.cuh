@@ -104,8 +104,26 @@ struct ChainCtrl {
     int trunc;   // state is zero outside [0,D)^2: only that block is read
     int flag;    // boundary flag of the last step
     int fused;   // the k_rows_inv that produced this state also transformed its interior row pairs for the next step
-    int pad_;
+    // Spectral-resident steps (see "Spectral-resident state" below).
+    int spec;    // Shat holds the spectrum of this state and the next whole-torus step may start from it
+    int stored;  // message k_cols -> k_rows_inv of one step: k_cols has written the product spectrum to Shat
+    int hint;    // the content of this state outside the domain is negligible (<= PKB_SPEC_EPS): worth storing Shat next step
+    double eps_sum;   // bound on the deviation from the exact fold mod P accumulated since the state went spectral
+    double eps_max;   // largest outside-domain content seen since then
 };
+
+// Spectral-resident state.  The reference keeps its chain state in Fourier space and only inverse-transforms
+// a copy per day (CalcSol.py:66,189-201).  The exact-P method of this file re-transforms the state every step
+// because the fold mod P is a real-space operation.  When NOTHING of consequence lies outside the domain the
+// fold moves nothing of consequence: with E = max |content outside [0,D)^2|, skipping it changes a later day
+// by at most 2 E per step (the folded cells are convolved with a kernel of unit mass).  So while E stays
+// below PKB_SPEC_EPS and the accumulated bound below PKB_SPEC_BUDGET -- both far under the 1e-10 parity bar
+// and the 1e-8 flag threshold -- the product spectrum that k_cols forms anyway is kept (Shat) and the next
+// step starts from it: no forward row pass, no forward column transform of the state.  The real state is
+// still produced (folded, with flag and sums) every day, so the chain drops back to exact steps the moment
+// the criterion fails -- decided on the device in the last CTA of k_rows_inv, no host round trip.
+#define PKB_SPEC_EPS 1e-14
+#define PKB_SPEC_BUDGET 1e-12
 
 // Geometry of a step whose SOURCE state is truncated (ChainCtrl::trunc: zero outside [0,D)^2).  Its linear
 // convolution with a radius-m kernel spans D + 2m cells only, so such a step can run on a torus
@@ -117,10 +135,10 @@ struct TruncGeom {
 };
 
 struct StepMeta {   // one per emitted solution
-    double padmax, ksum, add, vmin;
+    double padmax, ksum, add, padabs;   // padabs: max |value| outside the domain
     long long kcnt;
     int flag;
-    int pad_;
+    int spec;    // this step started from the stored spectrum (spectral-resident step)
 };
 
 // ---------------------------------------------------------------------------
@@ -193,8 +211,9 @@ __host__ __device__ __forceinline__ bool fused_pair(int r0, int P, int m) {
 }
 // the fusion needs room for the reduction scratch in the (zero) tail of the transform buffer
 __host__ __device__ __forceinline__ bool rows_fusable(int N, int P) { return N - 48 >= P; }
-__global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* __restrict__ ctrl,
-                                       cplx* __restrict__ Yt, FftPlan plan, int pre_m, TruncGeom tg, FftPlan plan_t) {
+__global__ void PKB_ROWS_LB k_rows_fwd(const double* __restrict__ S, ChainDims d, const ChainCtrl* ctrl,
+                                       cplx* __restrict__ Yt, FftPlan plan, int pre_m, TruncGeom tg, FftPlan plan_t, int spec_try) {
+    if (spec_try && ctrl->spec) return;      // spectral-resident step: k_cols starts from Shat, nothing to transform
     if (tg.N && ctrl->trunc) {      // truncated source: the smaller torus (TruncGeom)
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
         plan = plan_t;
@@ -311,13 +330,29 @@ __global__ void PKB_ROWS_LB k_kernel_rows_batch(const double* __restrict__ K0, s
 // what it wrote, laid out [kb][q][tid] so that both directions coalesce).
 // Phase 1 (state column): DFT, product with the parked filter spectrum,
 // inverse DFT, back to the same shared-memory slots.
+// Spectral-resident steps (ChainCtrl::spec): the product spectrum is also written to the column's slice of Shat
+// (phase 3), and a later step reads it from there instead of transforming the state column (phase 2).  Shat uses
+// the parking layout [kb][q][tid] -- only this loop ever touches it, with the same plan and CTA size.
 template <int RL>
-__device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, int tid, int T, int nbl, int phase) {
+__device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, cplx* __restrict__ hcol, int tid, int T, int nbl, int phase) {
     int slot = tid;
 #pragma unroll 1
     for (int j = tid; j < nbl; j += T, slot += RL * T) {
         cplx v[RL];
-        if (phase == 0) {
+        if (phase == 2) {
+            cplx kf[RL];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) kf[q] = scr[slot + q * T];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) v[q] = hcol[slot + q * T];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) v[q] = cmul_f(v[q], kf[q]);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) hcol[slot + q * T] = v[q];
+            idft<RL>(v);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) x[j * RL + q] = v[q];
+        } else if (phase == 0) {
 #pragma unroll
             for (int q = 0; q < RL; ++q) v[q] = x[j * RL + q];
             dft<RL>(v);
@@ -332,6 +367,10 @@ __device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, int 
             dft<RL>(v);
 #pragma unroll
             for (int q = 0; q < RL; ++q) v[q] = cmul_f(v[q], kf[q]);
+            if (phase == 3) {
+#pragma unroll
+                for (int q = 0; q < RL; ++q) hcol[slot + q * T] = v[q];
+            }
             idft<RL>(v);
 #pragma unroll
             for (int q = 0; q < RL; ++q) x[j * RL + q] = v[q];
@@ -344,10 +383,17 @@ __device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, int 
 // Per spectral column: forward FFT of the filter column (inputs straight from
 // Krt, only 2m+1 of them non-zero), forward FFT of the state column (inputs
 // straight from Yt), product, inverse FFT, rows needed by the fold straight to Wt.
+// Shat (optional): spectral-resident state, gridDim-independent slices of hstride complex per column.
 __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
-                                   const ChainCtrl* __restrict__ ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan,
-                                   TruncGeom tg, FftPlan plan_t, const cplx* __restrict__ Krt_t) {
-    const bool tr = tg.N && ctrl->trunc;      // truncated source on its smaller torus (TruncGeom)
+                                   ChainCtrl* ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan,
+                                   TruncGeom tg, FftPlan plan_t, const cplx* __restrict__ Krt_t, cplx* __restrict__ Shat, size_t hstride) {
+    const int c_trunc = ctrl->trunc, c_spec = ctrl->spec, c_hint = ctrl->hint;
+    const bool tr = tg.N && c_trunc;          // truncated source on its smaller torus (TruncGeom)
+    // start from the stored spectrum / keep the product spectrum for the next step (uniform over the grid; `stored`
+    // tells this step's k_rows_inv, which decides whether the next step may start from it)
+    const bool use_spec = Shat != nullptr && c_spec && !tr && !d.win;
+    const bool store = Shat != nullptr && !tr && !d.win && (use_spec || c_hint);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->stored = store ? 1 : 0;
     if (tr) {
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
         plan = plan_t;
@@ -360,7 +406,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
     const int tid = threadIdx.x, T = blockDim.x;
     fft_load_twiddles(tws, plan, tid, T);
     __syncthreads();
-    const int lim = d.win ? d.wn : (ctrl->trunc ? d.D : d.P);
+    const int lim = d.win ? d.wn : (c_trunc ? d.D : d.P);
     const int N = d.N, nq = 2 * m + 1;
     const int L = plan.nstage, R0 = plan_radix(plan, 0), RL = plan_radix(plan, L - 1), nbl = N / RL;
     const int hi = (d.win ? d.wn : (tr ? d.D : d.P)) + m;   // rows [0, extent + m) and [N-m, N) are needed downstream
@@ -371,6 +417,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
         const cplx* ycol = Yt + spec_index(c, 0, d.ldY);
         const cplx* kcol = Krt + spec_index(c, 0, d.ldK);
         cplx* wcol = Wt + spec_index(c, 0, d.ldW);
+        cplx* hcol = store ? Shat + (size_t)c * hstride : nullptr;
         auto ld_filter = [&](int i) -> cplx {
             if (i <= m) return kcol[(size_t)i * PKB_CB];
             if (i >= N - m) return kcol[(size_t)(i - (N - nq)) * PKB_CB];
@@ -382,7 +429,9 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
         };
         for (int phase = 0; phase < 2; ++phase) {
             auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
-            if (L == 1) {
+            if (phase && use_spec) {
+                // the state column's spectrum is in Shat: nothing to transform
+            } else if (L == 1) {
                 for (int i = tid; i < N; i += T) x[i] = ld(i);
                 __syncthreads();
             } else {
@@ -390,7 +439,8 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
                 __syncthreads();
                 fft_fwd_stages(x, tws, plan, 1, L - 1, N / R0, 0, tid, T);
             }
-#define PKB_CALL_(RR) cols_final<RR>(x, myscr, tid, T, nbl, phase)
+            const int fmode = !phase ? 0 : (use_spec ? 2 : (store ? 3 : 1));
+#define PKB_CALL_(RR) cols_final<RR>(x, myscr, hcol, tid, T, nbl, fmode)
             PKB_RADIX_SWITCH(RL, PKB_CALL_)
 #undef PKB_CALL_
             __syncthreads();
@@ -408,7 +458,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
 // ---------------------------------------------------------------------------
 // Per-row statistics written by k_rows_inv, reduced by k_step_finalize.
 struct RowStats {
-    double padmax, ksum, vmin;
+    double padmax, ksum, padabs;
     int kcnt;
     int pad_;
 };
@@ -440,45 +490,68 @@ __device__ __forceinline__ double block_reduce8(double (&v)[8], double* red, int
     return r;
 }
 
-// Flag / kept sum / kept count / minimum of a state from its per-row statistics
+// What the finalising CTA needs to know about the step's SOURCE state and this step's k_cols to decide
+// whether the NEXT step may start from Shat (read at kernel start, before anything is overwritten).
+struct SpecIn {
+    int stored;        // k_cols of this step wrote the product spectrum
+    int was_spec;      // this step itself started from Shat
+    double eps_sum, eps_max;
+};
+
+// Flag / kept sum / kept count / largest outside-domain magnitude of a state from its per-row statistics
 // -> control block and step meta (CalcSol.py:36-37, 134-135).  Whole CTA; fixed
-// summation order for a given block size.  red: 8 * 32 doubles.
-__device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const ChainDims& d, ChainCtrl* __restrict__ ctrl,
-                                                    StepMeta* __restrict__ meta, int apply_trunc, double* red, int tid, int T) {
-    // st[0] pad max, st[1] kept sum, st[2] kept count, st[3] -min
-    double st[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
+// summation order for a given block size.  red: 8 * 32 doubles.  flag_thresh: 1e-8 (CalcSol.py:37), or the
+// caller's negval on the cuda_lib.get_cursol path (cuda_lib.py:117-130).
+__device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const ChainDims& d, ChainCtrl* ctrl,
+                                                    StepMeta* __restrict__ meta, int apply_trunc, double* red, int tid, int T,
+                                                    SpecIn si, double flag_thresh) {
+    // st[0] pad max, st[1] kept sum, st[2] kept count, st[3] max |v| outside the domain
+    double st[8] = {-INFINITY, 0.0, 0.0, 0.0, -INFINITY, 0.0, 0.0, 0.0};
     // contiguous chunks per thread so the summation order over rows is fixed
     const int chunk = (d.P + T - 1) / T;
     const volatile RowStats* rv = rstat;
     for (int r = tid * chunk; r < d.P && r < (tid + 1) * chunk; ++r) {
-        const double pm = rv[r].padmax, ks = rv[r].ksum, vm = rv[r].vmin;
+        const double pm = rv[r].padmax, ks = rv[r].ksum, pa = rv[r].padabs;
         const int kc = rv[r].kcnt;
         st[0] = fmax(st[0], pm);
-        if (r < d.D) { st[1] += ks; st[2] += (double)kc; st[3] = fmax(st[3], -vm); }
+        st[3] = fmax(st[3], pa);
+        if (r < d.D) { st[1] += ks; st[2] += (double)kc; }
     }
     __syncthreads();
     const double rr = block_reduce8(st, red, tid, T);
     if (tid < 4) red[64 + tid] = rr;
     __syncthreads();
     if (tid == 0) {
-        const double bp = red[64], bs = red[65], bc = red[66], bm = -red[67];
-        const int flag = bp > 1e-8 ? 1 : 0;          // CalcSol.py:36-37
-        meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->vmin = bm;
+        const double bp = red[64], bs = red[65], bc = red[66], ba = red[67];
+        const int flag = bp > flag_thresh ? 1 : 0;   // CalcSol.py:36-37
+        meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->padabs = ba;
         meta->add = (1.0 - bs) / bc;                 // CalcSol.py:135
         meta->flag = flag;
+        meta->spec = si.was_spec;
         ctrl->flag = flag;
         // a fresh convolution result is a full P x P state; it becomes a
         // truncated one only where the caller applies CalcSol.py:200-201
         ctrl->trunc = apply_trunc ? flag : 0;
+        // spectral-resident steps: see PKB_SPEC_EPS
+        const bool small = ba <= PKB_SPEC_EPS;
+        const double emax = fmax(si.was_spec ? si.eps_max : 0.0, ba);
+        const double esum = (si.was_spec ? si.eps_sum : 0.0) + 2.0 * emax;
+        const bool spec = si.stored && small && !flag && esum <= PKB_SPEC_BUDGET;
+        ctrl->hint = small ? 1 : 0;
+        ctrl->spec = spec ? 1 : 0;
+        ctrl->stored = 0;
+        ctrl->eps_sum = spec ? esum : 0.0;
+        ctrl->eps_max = spec ? emax : 0.0;
     }
 }
 
 // grid = 1, block = 256 (stencil path and re-thresholding; the FFT path finalises
 // in the last CTA of k_rows_inv)
-__global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta,
-                                int apply_trunc) {
+__global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* ctrl, StepMeta* __restrict__ meta,
+                                int apply_trunc, double flag_thresh) {
     PKB_SHARED(double, red, PKB_RED_DOUBLES);
-    step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x);
+    SpecIn si = {0, 0, 0.0, 0.0};
+    step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x, si, flag_thresh);
 }
 
 // number of inverse-row jobs: 2m fold jobs, an unpaired row m if m is odd, then row pairs
@@ -534,12 +607,17 @@ __device__ __forceinline__ void rows_inv_decode_trunc(int job, int m, int P, int
 // A job is one inverse transform.  "Pair" jobs carry two interior output rows as
 // real and imaginary part; "fold" jobs carry the two linear-convolution rows that
 // fold onto the same output row mod P (their sum is re + im).
+// ctrl (written by the CTA that finishes last) and src_ctrl (read by every CTA at its start) are the SAME object on
+// main-chain steps: neither is __restrict__, and the reads below come before this CTA's contribution to `done`, so
+// they are ordered before the finalising CTA's writes.
 __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, ChainDims d, double* __restrict__ Sout,
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
-                                       ChainCtrl* __restrict__ ctrl, StepMeta* __restrict__ meta, int apply_trunc,
-                                       cplx* __restrict__ Yt_next, const ChainCtrl* __restrict__ src_ctrl, TruncGeom tg, FftPlan plan_t,
+                                       ChainCtrl* ctrl, StepMeta* __restrict__ meta, int apply_trunc,
+                                       cplx* __restrict__ Yt_next, const ChainCtrl* src_ctrl, TruncGeom tg, FftPlan plan_t,
                                        int desc_order) {
-    const bool tr = tg.N && !d.win && src_ctrl->trunc;      // truncated source on its smaller torus (TruncGeom)
+    const volatile ChainCtrl* sc = src_ctrl;
+    const SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max};
+    const bool tr = tg.N && !d.win && sc->trunc;      // truncated source on its smaller torus (TruncGeom)
     if (tr) {
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
         plan = plan_t;
@@ -551,7 +629,8 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     // idle whenever they are used (after a job's output loop; fft_smem_bytes() >= 1 KB)
     // (at the END of the buffer when the next step's forward row transform is fused in: the packed
     //  row pair at the start of the buffer is still needed then, and the tail beyond column P is read as zero)
-    const bool fuse = Yt_next != nullptr && !d.win && !tr && rows_fusable(plan.N, d.P);
+    // (not when this step's k_cols kept the product spectrum: the next step will most likely start from it)
+    const bool fuse = Yt_next != nullptr && !d.win && !tr && !si.stored && rows_fusable(plan.N, d.P);
     double* red = reinterpret_cast<double*>(raw) + (fuse ? 2 * (plan.N - 48) : 0);
     int* last = reinterpret_cast<int*>(red + PKB_RED_DOUBLES);
     const int tid = threadIdx.x, T = blockDim.x;
@@ -664,8 +743,8 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         double* dst_a = Sout + (size_t)out_a * d.ldS + col0;
         double* dst_b = Sout + (size_t)(out_b >= 0 ? out_b : out_a) * d.ldS + col0;
         // st[0..3]: row a (pad max, kept sum, kept count, -min); st[4..7]: row b
-        double st[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
-        if (d.win) { st[0] = st[4] = 0.0; st[3] = st[7] = 0.0; }     // the untouched rest of the row is zero
+        double st[8] = {-INFINITY, 0.0, 0.0, 0.0, -INFINITY, 0.0, 0.0, 0.0};
+        if (d.win) { st[0] = st[4] = 0.0; }                          // the untouched rest of the row is zero
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
         const int Dc = D - col0;                                     // first pad column, relative to col0
         for (int c = tid; c < ncols; c += T) {
@@ -679,19 +758,13 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             }
             const double va = (fold ? z.x + z.y : z.x) * scale;
             dst_a[c] = va;
-            if (pad_a || c >= Dc) st[0] = fmax(st[0], va);
-            else {
-                st[3] = fmax(st[3], -va);
-                if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
-            }
+            if (pad_a || c >= Dc) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
+            else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
             if (out_b >= 0) {
                 const double vb = z.y * scale;
                 dst_b[c] = vb;
-                if (pad_b || c >= Dc) st[4] = fmax(st[4], vb);
-                else {
-                    st[7] = fmax(st[7], -vb);
-                    if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
-                }
+                if (pad_b || c >= Dc) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
+                else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
             }
         }
         __syncthreads();                               // every thread is done reading x: reuse it as scratch
@@ -701,7 +774,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         if (tid == 0 || (tid == 1 && out_b >= 0)) {
             const double* q = red + 64 + 4 * tid;
             RowStats rs;
-            rs.padmax = q[0]; rs.ksum = q[1]; rs.kcnt = (int)q[2]; rs.vmin = -q[3]; rs.pad_ = 0;
+            rs.padmax = q[0]; rs.ksum = q[1]; rs.kcnt = (int)q[2]; rs.padabs = q[3]; rs.pad_ = 0;
             rstat[tid ? out_b : out_a] = rs;
         }
         __syncthreads();
@@ -728,7 +801,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     __syncthreads();
     if (last[0]) {
         __threadfence();
-        step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, tid, T);
+        step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, tid, T, si, 1e-8);
         if (tid == 0) {
             ctrl->fused = fuse ? 1 : 0;
             *done = 0;
@@ -740,8 +813,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
 __global__ void k_apply_trunc(ChainCtrl* __restrict__ ctrl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->trunc = ctrl->flag;
 }
+// control block of a freshly loaded state: nothing outside the domain (hint), no spectrum kept
 __global__ void k_set_ctrl(ChainCtrl* __restrict__ ctrl, int trunc, int flag) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { ctrl->trunc = trunc; ctrl->flag = flag; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctrl->trunc = trunc; ctrl->flag = flag; ctrl->fused = 0;
+        ctrl->spec = 0; ctrl->stored = 0; ctrl->hint = 1; ctrl->eps_sum = 0.0; ctrl->eps_max = 0.0;
+    }
 }
 
 // out[r][c] = r_small_vals(S[:D,:D], prob_model) densely (CalcSol.py:112-136)
@@ -1029,23 +1106,20 @@ __global__ void k_stencil(const double* __restrict__ S, const double* __restrict
 __global__ void k_row_stats(const double* __restrict__ S, ChainDims d, RowStats* __restrict__ rstat, double negval) {
     PKB_SHARED(double, red, 256);
     const int r = blockIdx.x;
-    double pmax = -INFINITY, ks = 0.0, vmn = INFINITY;
+    double pmax = -INFINITY, ks = 0.0, pab = 0.0;
     int kc = 0;
     for (int c = threadIdx.x; c < d.P; c += blockDim.x) {
         const double v = S[(size_t)r * d.ldS + c];
-        if (r >= d.D || c >= d.D) pmax = fmax(pmax, v);
-        else {
-            vmn = fmin(vmn, v);
-            if (!(v < negval)) { ks += v; kc += 1; }
-        }
+        if (r >= d.D || c >= d.D) { pmax = fmax(pmax, v); pab = fmax(pab, fabs(v)); }
+        else if (!(v < negval)) { ks += v; kc += 1; }
     }
     const double bpmax = block_max(pmax, red);
     const double bks = block_sum(ks, red);
     const double bkc = block_sum((double)kc, red);
-    const double bmn = block_min(vmn, red);
+    const double bab = block_max(pab, red);
     if (threadIdx.x == 0) {
         RowStats rs;
-        rs.padmax = bpmax; rs.ksum = bks; rs.vmin = bmn; rs.kcnt = (int)bkc; rs.pad_ = 0;
+        rs.padmax = bpmax; rs.ksum = bks; rs.padabs = bab; rs.kcnt = (int)bkc; rs.pad_ = 0;
         rstat[r] = rs;
     }
 }

@@ -24,12 +24,26 @@ namespace pkb {
 #define PKB_ST_PMF_NEG2 16        // pmf.min() < -1e-8 after local blob     (:589)
 #define PKB_ST_TOT_GT1 32         // total > 1.00001 after local blob       (:590)
 #define PKB_ST_WARNED 64          // RuntimeWarning path taken              (:547-558)
-#define PKB_ST_BORDERLINE 128     // ring-growth test within 1e-13 of cdf_eps
-#define PKB_ST_SUPPORT_OVF 256    // support half-width exceeds kernel limits
+#define PKB_ST_BORDERLINE 128     // ring-growth test within ring_tol of cdf_eps: decided by the reference-order running sum (:345-373)
 
 #define PKB_CDF_EPS 0.001
 #define PKB_LATTICE_CAP 5120      // doubles of shared memory for the corner lattice tile
 #define PKB_BVN_SEG 12            // lattice corners a thread marches along one column (k_period)
+
+// Per-period contributions are accumulated as 64-bit FIXED-POINT numbers (units of 2^-60) with integer atomics:
+// integer addition is associative, so the day's window is bit-identical from run to run whatever order the
+// period CTAs finish in (fp64 atomics gave sums that differed in the last bits, and with them the occasional
+// keep/drop decision at the 1e-8 threshold).  A contribution h[t] * cdf is <= 1 and is rounded to 2^-60 = 8.7e-19;
+// over the 1440 periods of a day that stays below 1e-15 absolute in the worst case, the same order as the rounding of
+// the reference's own `pmf += hprob * cdf` (ParasitoidModel.py:539) on cells of the size that matter.
+#define PKB_ACC_SCALE 1152921504606846976.0        // 2^60
+__device__ __forceinline__ void acc_add_fixed(double* cell, double v) {
+    const long long q = __double2ll_rn(v * PKB_ACC_SCALE);
+    atomicAdd(reinterpret_cast<unsigned long long*>(cell), (unsigned long long)q);
+}
+__device__ __forceinline__ double acc_fixed_to_double(double bits) {
+    return (double)__double_as_longlong(bits) * (1.0 / PKB_ACC_SCALE);
+}
 
 struct DayParams {      // one per (proposal, day) problem
     double lam, aw, bw, a1, b1, a2, b2;   // hparams (Run.py:377)
@@ -156,7 +170,7 @@ struct PeriodInfo {
 
 // grid = problems, block = 256
 __global__ void k_drift(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const double* __restrict__ wind,
-                        int periods, PeriodInfo* __restrict__ pinfo, DayMeta* __restrict__ meta) {
+                        int periods, PeriodInfo* __restrict__ pinfo, DayMeta* __restrict__ meta, double ring_tol) {
     PKB_SHARED(double, red, 256);
     const DayParams dp = dps[blockIdx.x];
     const BvnPar& bp = bvn[dp.bvn_S];
@@ -214,7 +228,11 @@ __global__ void k_drift(const DayParams* __restrict__ dps, const BvnPar* __restr
         d0 = 1.0 - square_prob(bp, cell, h0, pi.mux, pi.muy);
         if (h0 >= 1 && d1 < PKB_CDF_EPS) h = h0 - 1;
         else if (d0 < PKB_CDF_EPS) h = h0;
-        if (fabs(d1 - PKB_CDF_EPS) < 1e-13 || fabs(d0 - PKB_CDF_EPS) < 1e-13) flags |= PKB_ST_BORDERLINE;
+        if (fabs(d1 - PKB_CDF_EPS) < ring_tol || fabs(d0 - PKB_CDF_EPS) < ring_tol) {
+            // too close to call on the one-rectangle form: the reference's own running sum decides
+            flags |= PKB_ST_BORDERLINE;
+            h = ring_halfwidth_ref_order(bp, cell, pi.mux, pi.muy, PKB_CDF_EPS, h0 + 1);
+        }
         pi.h = h;
         pi.pad_ = 0;
         pinfo[(size_t)blockIdx.x * periods + t] = pi;
@@ -370,7 +388,7 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
             const int col = pi.col_c + (ix - h);
             if (row >= 0 && row < dom && col >= 0 && col < dom) {
                 inside += v;
-                atomicAdd(&accp[(size_t)(row - shift) * W + (col - shift)], hp * v);   // (:539)
+                acc_add_fixed(&accp[(size_t)(row - shift) * W + (col - shift)], hp * v);   // (:539)
             }
         }
         __syncthreads();
@@ -405,6 +423,9 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
         for (int t = dp.start_indx; t < P; ++t) loss += loss_t[(size_t)prob * periods + t];   // same order as the loop (:546,558)
         sh[0] = loss;
     }
+    // fixed-point accumulator (acc_add_fixed) -> doubles, in place
+    for (int i = tid; i < nel; i += T) a[i] = acc_fixed_to_double(a[i]);
+    __syncthreads();
     double s = 0.0, mn = 0.0;
     for (int i = tid; i < nel; i += T) { const double v = a[i]; s += v; mn = fmin(mn, v); }
     const double pmfsum = block_sum(s, red);
@@ -470,7 +491,7 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
 // out: [cap] doubles, receives the (2h+1)^2 array in the reference orientation;
 // hout[0] = h, or -1 if (2h+1)^2 > cap or h >= 4096.
 __global__ void k_mvn_cdf(const BvnPar* __restrict__ bvn, double cell, double mux, double muy, double* __restrict__ out, int cap,
-                          int* __restrict__ hout) {
+                          int* __restrict__ hout, double ring_tol) {
     PKB_SHARED(int, okv, 256);
     PKB_SHARED(int, found, 1);
     const BvnPar& p = bvn[0];
@@ -485,6 +506,18 @@ __global__ void k_mvn_cdf(const BvnPar* __restrict__ bvn, double cell, double mu
                 if (okv[t]) { found[0] = base + t; break; }
         __syncthreads();
         if (found[0] >= 0) break;
+    }
+    if (found[0] >= 0) {
+        // within ring_tol of cdf_eps the reference's running sum decides (see k_drift)
+        const int hf = found[0];
+        __syncthreads();
+        if (tid == 0) {
+            const double d0 = 1.0 - square_prob(p, cell, hf, mux, muy);
+            const double d1 = hf >= 1 ? 1.0 - square_prob(p, cell, hf - 1, mux, muy) : 1.0;
+            if (fabs(d0 - PKB_CDF_EPS) < ring_tol || fabs(d1 - PKB_CDF_EPS) < ring_tol)
+                found[0] = ring_halfwidth_ref_order(p, cell, mux, muy, PKB_CDF_EPS, hf + 1);
+        }
+        __syncthreads();
     }
     const int h = found[0];
     const int nc = 2 * h + 1;

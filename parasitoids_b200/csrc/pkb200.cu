@@ -103,6 +103,8 @@ struct pkb_ctx {
     int use_windows;        // fused solve: support-window steps (option "windows", default on)
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
+    double ring_tol;        // ring-growth decisions closer than this to cdf_eps are re-taken in the reference's summation order (option "ring_tol")
+    int use_spectral;       // fused solve: spectral-resident steps while nothing of consequence lies outside the domain (option "spectral")
     int emit_ctas;          // fused solve: side-stream emission as this many persistent 64-thread CTAs (option "emit_ctas"; 0, the
                             // default: one 256-thread CTA per row -- the small persistent CTAs measured slower)
     int rows_desc;          // k_rows_inv takes its jobs in descending order (short fold jobs last; option "rows_desc", default 1)
@@ -333,6 +335,8 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->batch_group = 32;
     ctx->use_step_torus = 1;
     ctx->use_trunc_torus = 1;
+    ctx->use_spectral = 1;
+    ctx->ring_tol = 1e-12;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
     CU(cudaEventCreateWithFlags(&ctx->ev_lane, cudaEventDisableTiming));
@@ -436,6 +440,15 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "trunc_torus")) {
         ctx->use_trunc_torus = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "ring_tol")) {
+        if (!(value >= 0)) return fail(PKB_EINVAL, "ring_tol must be >= 0");
+        ctx->ring_tol = value;
+        return 0;
+    }
+    if (!strcmp(key, "spectral")) {
+        ctx->use_spectral = value != 0;
         return 0;
     }
     if (!strcmp(key, "step_torus")) {
@@ -867,7 +880,7 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
     if ((size_t)4 * periods * sizeof(double) > (size_t)ctx->max_smem) return fail(PKB_ELIMIT, "too many periods per day (%d)", periods);
     LAUNCH(ctx, k_hprob, nprob, 256, 4 * (size_t)periods * sizeof(double), ks->ddp.p, wind_dev, periods, ks->hprob.p, ks->dmeta.p,
            (double*)nullptr, (double*)nullptr);
-    LAUNCH(ctx, k_drift, nprob, 256, 0, ks->ddp.p, ks->bvn.p, wind_dev, periods, ks->pinfo.p, ks->dmeta.p);
+    LAUNCH(ctx, k_drift, nprob, 256, 0, ks->ddp.p, ks->bvn.p, wind_dev, periods, ks->pinfo.p, ks->dmeta.p, ctx->ring_tol);
 
     // size of the accumulation window: needs the drift extents (one small D2H)
     ks->hmeta.resize(nprob);
@@ -1034,7 +1047,7 @@ extern "C" int pkb_mvn_cdf(pkb_ctx* ctx, double cell_length, const double mu[2],
     CU(cudaMemcpyAsync(dpar.p, cov, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dcell.p, &cell_length, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, k_bvn_setup, 1, 32, 0, bp.p, dpar.p, dcell.p, 1);
-    LAUNCH(ctx, k_mvn_cdf, 1, 256, 0, bp.p, cell_length, mu[0], mu[1], dout.p, cap, dh.p);
+    LAUNCH(ctx, k_mvn_cdf, 1, 256, 0, bp.p, cell_length, mu[0], mu[1], dout.p, cap, dh.p, ctx->ring_tol);
     int h = -1;
     CU(cudaMemcpyAsync(&h, dh.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     TRY(sync_check(ctx, "pkb_mvn_cdf"));
@@ -1064,6 +1077,9 @@ struct pkb_chain {
     DBuf<cplx> Yt, Wt, Krt;
     DBuf<cplx> Krt_t;       // kernel row spectra on the truncated-source torus (TruncGeom), when a caller brings none
     DBuf<cplx> cscr;        // k_cols: per-CTA parking space for the filter column spectrum
+    DBuf<cplx> Shat;        // spectral-resident state (ChainCtrl::spec): Nc slices of hstride complex, allocated on first use
+    size_t hstride;
+    bool fixed_torus;       // every whole-torus step runs on the chain's own torus (spectral-resident steps need one torus)
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
     size_t cscr_per_cta;
     int grid_rows, grid_cols;
@@ -1077,6 +1093,7 @@ struct pkb_chain {
     DBuf<cplx> kcache_t[PKB_MAX_COHORTS]; // the same on each filter's truncated-source torus (trunc_torus)
     int kcache_m[PKB_MAX_COHORTS];
     double negval;          // threshold the row statistics were taken with
+    double flag_thresh;     // boundary-flag threshold of the last finalize (1e-8, or negval on the cuda_lib.get_cursol path)
     bool stats_valid;
 };
 
@@ -1131,6 +1148,9 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ch->cur = 0;
     ch->negval = 1e-8;
     ch->stats_valid = false;
+    ch->flag_thresh = 1e-8;
+    ch->hstride = 0;
+    ch->fixed_torus = false;
     for (int i = 0; i < PKB_MAX_COHORTS; ++i) ch->kcache_m[i] = -1;
     guard.c = nullptr;
     *out = ch;
@@ -1175,7 +1195,7 @@ static int step_torus(pkb_chain* ch, int m, ChainDims* d, FftPlan* plan) {
     pkb_ctx* ctx = ch->ctx;
     *d = ch->d;
     *plan = ch->plan;
-    if (!ctx->use_step_torus) return 0;
+    if (!ctx->use_step_torus || ch->fixed_torus) return 0;
     const int Nd = pkb_smooth_len(std::max(2, ch->d.P + 2 * m));
     if (Nd >= ch->d.N) return 0;
     FftPlan p;
@@ -1221,7 +1241,7 @@ static ChainDims trunc_dims(const ChainDims& d, const TruncGeom& tg) {
 
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
-                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true) {
+                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true, bool spec_try = false) {
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
@@ -1230,7 +1250,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         const size_t smem = ((size_t)(8 + 2 * m) * (32 + 2 * m) + (size_t)(2 * m + 1) * (2 * m + 1)) * sizeof(double);
         LAUNCH(ctx, k_stencil, dim3((d.P + 31) / 32, (d.P + 7) / 8), dim3(32, 8), smem, src, K, Wk, m, d, src_ctrl, dst);
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
-        LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc);
+        LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, 1e-8);
         return 0;
     }
     // geometry of this step: the chain's torus, or a smaller one around the state's support window
@@ -1262,11 +1282,22 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     if ((size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads > ch->cscr_per_cta)
         return fail(PKB_ELIMIT, "column scratch too small for torus side %d", d.N);
     const int njobs = win ? (d.wn + 2 * m + 1) / 2 : std::max(rows_inv_jobs(d.P, m), tg.N ? rows_inv_jobs_trunc(d.P, d.D, m) : 0);
+    // spectral-resident steps: main chain, the chain's own torus (ChainCtrl::spec; the kernels decide on the device)
+    cplx* shat = nullptr;
+    if (spec_try && !win && slot == 0 && d.N == ch->d.N) {
+        const size_t hs = (size_t)plan.cols_kb * plan_radix(plan, plan.nstage - 1) * plan.cols_threads;
+        if (!ch->Shat.p || ch->hstride != hs) {
+            ch->hstride = hs;
+            TRY(ch->Shat.alloc(ctx, hs * d.Nc));
+        }
+        shat = ch->Shat.p;
+    }
+    ChainCtrl* src_ctrl_w = const_cast<ChainCtrl*>(src_ctrl);      // (k_cols leaves its `stored` message there)
     if (win) {
         if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
-        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1, tg, plan_t);
+        LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1, tg, plan_t, 0);
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
-                  m, d, src_ctrl, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt);
+                  m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
                   ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
         return 0;
@@ -1281,18 +1312,18 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     if (tg.N && !krt_t_ready)
         LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan_t.grid_rows), plan_t.threads, fft_smem_bytes(plan_t), K, Wk, m, trunc_dims(d, tg), krt_t, plan_t);
     if (!tg.N) krt_t = krt;
-    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m, tg, plan_t);
-    LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl,
-           ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t);
+    LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m, tg, plan_t, shat ? 1 : 0);
+    LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl_w,
+           ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
            ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
     return 0;
 }
 
 // flag / sums of a state whose row statistics are in ch->rstat -> ctrl[0], meta[0] (re-thresholding)
-static void finalize_state(pkb_chain* ch) {
+static void finalize_state(pkb_chain* ch, double flag_thresh) {
     pkb_ctx* ctx = ch->ctx;
-    LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, ch->d, ch->ctrl.p, ch->meta.p, 0);
+    LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, ch->d, ch->ctrl.p, ch->meta.p, 0, flag_thresh);
 }
 
 extern "C" int pkb_chain_set_state(pkb_chain* ch, const double* A) {
@@ -1349,10 +1380,10 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
 }
 
 static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr,
-                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr) {
+                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr, bool spec_try = false) {
     const int nxt = ch->cur ^ 1;
     TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win,
-                  fuse_next, pre_m, true, krt_t));
+                  fuse_next, pre_m, true, krt_t, true, spec_try));
     ch->cur = nxt;
     return 0;
 }
@@ -1364,6 +1395,7 @@ extern "C" int pkb_chain_conv(pkb_chain* ch, const double* B, int k) {
     TRY(upload_filter(ch, B, k, &m));
     TRY(chain_conv_main(ch, ch->kup.p, 2 * m + 1, m, 0));
     ch->stats_valid = true;
+    ch->flag_thresh = 1e-8;
     return sync_check(ch->ctx, "pkb_chain_conv");
 }
 
@@ -1372,6 +1404,7 @@ extern "C" int pkb_chain_conv_kernel(pkb_chain* ch, pkb_kset* ks, int i) {
     CU(cudaSetDevice(ch->ctx->device));
     TRY(chain_conv_main(ch, ks->acc.p + (size_t)ks->W * ks->W * i, ks->W, ks->hmeta[i].rad, 0));
     ch->stats_valid = true;
+    ch->flag_thresh = 1e-8;
     return sync_check(ch->ctx, "pkb_chain_conv_kernel");
 }
 
@@ -1382,15 +1415,19 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
     const ChainDims& d = ch->d;
     CU(cudaSetDevice(ctx->device));
     double* S = ch->S[ch->cur].p;
-    if (!ch->stats_valid || negval != ch->negval) {
+    // cuda_lib.get_cursol (mode 1) keeps v > negval and raises the flag when anything outside the domain survives that
+    // threshold (cuda_lib.py:117-130); the CPU path's ifft2 (modes 0, 2) compares with 1e-8 (CalcSol.py:36-37)
+    const double thresh = mode == 1 ? negval : 1e-8;
+    if (!ch->stats_valid || negval != ch->negval || thresh != ch->flag_thresh) {
         ch->negval = negval;
+        ch->flag_thresh = thresh;
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)S, d, ch->rstat.p, negval);
-        finalize_state(ch);
+        finalize_state(ch, thresh);
         ch->stats_valid = true;
     }
     if (out) {
         if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p);
-        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, 0, ch->dout.p, (int*)nullptr);
+        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, mode == 1 ? 1 : 0, ch->dout.p, (int*)nullptr);
         CU(cudaMemcpyAsync(out, ch->dout.p, (size_t)d.D * d.D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (apply_trunc) {
@@ -1669,6 +1706,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         ~CGuard() { delete c; }
     } cguard{ch};
     ch->negval = negval;
+    // spectral-resident steps on the main chain (probability model, or a one-day release: no cohorts to back-solve)
+    const bool spec_try = ctx->use_spectral && (a->prob_model || a->r_dur == 1);
+    ch->fixed_torus = spec_try;
     const ChainDims d = ch->d;
     res->P = d.P;
     res->N = d.N;
@@ -1904,7 +1944,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
             const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * n);
@@ -1986,7 +2026,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (!wp) TRY(day_spectra(n, &kday, &kday_t));
             else TRY(window_spectra(n, &kday));
             const bool fuse = rd == 1 && !wp && !wmode && n + 1 < nd && fusable(n);
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready, krt_t, ready_t));
@@ -2107,6 +2147,8 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         lane->use_fusion = ctx->use_fusion;
         lane->use_step_torus = ctx->use_step_torus;
         lane->use_trunc_torus = ctx->use_trunc_torus;
+        lane->use_spectral = ctx->use_spectral;
+        lane->ring_tol = ctx->ring_tol;
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
     }

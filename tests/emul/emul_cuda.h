@@ -94,6 +94,10 @@ static inline double atomicAdd(double* addr, double val) {
     return o;
 }
 static inline int atomicAdd(int* addr, int val) { return __atomic_fetch_add(addr, val, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long* addr, unsigned long long val) {
+    return __atomic_fetch_add(addr, val, __ATOMIC_RELAXED);
+}
+static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicOr(int* addr, int val) { return __atomic_fetch_or(addr, val, __ATOMIC_RELAXED); }
 static inline int atomicMax(int* addr, int val) {

@@ -439,6 +439,7 @@ def test_step_torus_matches_chain_torus(pkb):
     args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
     ctx = pkb._lib.ctx()
     ctx.set_option('windows', 0)
+    ctx.set_option('spectral', 0)                       # (spectral-resident steps keep to the chain's torus)
     try:
         for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=2, r_number=1000.0)):
             out = {}
@@ -463,6 +464,61 @@ def test_step_torus_matches_chain_torus(pkb):
     finally:
         ctx.set_option('step_torus', 1)
         ctx.set_option('windows', 1)
+        ctx.set_option('spectral', 1)
+
+
+def test_spectral_steps_match_exact_steps(pkb):
+    """Option spectral: while the content outside the domain is below 1e-14 the chain keeps the product spectrum
+    k_cols forms anyway and starts the next step from it (the reference's own chain state is spectral,
+    CalcSol.py:66,189-201) instead of re-transforming the folded real state.  The device decides per step; the
+    bound on the difference is 1e-12 (chain.cuh).  Calm wind: the mass stays inside, spectral steps must happen
+    and agree with the exact steps and the oracle.  Breeze towards the edge: the flags trip, the chain must fall
+    back to exact steps and give the same flags and solutions."""
+    rng = np.random.default_rng(5)
+    nd, periods, rad_res, rad_dist = 10, 96, 140, 7000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        x = np.cumsum(rng.normal(0, 0.05, nd * periods)).reshape(nd, periods)
+        w[:, :, c] = 0.15 * np.sin(np.linspace(0, 6, nd * periods)).reshape(nd, periods) + x * 0.1
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    drift = w.copy()
+    drift[:, :, 0] = np.abs(drift[:, :, 0]) * 2 + 0.8
+    drift[:, :, 2] = np.hypot(drift[:, :, 0], drift[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    seen_spec = seen_flag = 0
+    try:
+        for windows in (0, 1):
+            ctx.set_option('windows', windows)
+            for wind in (w, drift):
+                for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=1, r_number=1000.0)):
+                    out = {}
+                    for sp in (1, 0):
+                        ctx.set_option('spectral', sp)
+                        with warnings.catch_warnings():
+                            warnings.simplefilter('ignore')
+                            res = pkb.Run.solve(wind, nd, *args, want_coo=False, want_dense=True, keep_pre=True, **kw)
+                        out[sp] = ([res.dense(d) for d in range(nd)], res.flags(), res.spectral_steps(), [res.pre(d) for d in range(nd)])
+                        res.close()
+                    assert out[0][2] == []
+                    assert out[1][1] == out[0][1]
+                    # a spectral step never follows a flagged state
+                    assert not any(out[1][1][d - 1] for d in out[1][2])
+                    seen_spec += len(out[1][2])
+                    seen_flag += sum(1 for f in out[1][1] if f)
+                    scale = kw.get('r_number', 1.0)
+                    for d in range(nd):
+                        assert np.abs(out[1][3][d] - out[0][3][d]).max() <= 1e-13 * scale, 'pre-threshold day %d' % d
+                        H.assert_thresholded_parity(out[1][0][d] / scale, out[0][0][d] / scale, what='day %d' % d, max_abs=1e-13)
+                    if kw['prob_model']:
+                        ref = _oracle_solve(wind, nd, args, rad_res)
+                        for d in range(nd):
+                            H.assert_thresholded_parity(out[1][0][d], ref[d].toarray(), what='oracle day %d' % d)
+    finally:
+        ctx.set_option('spectral', 1)
+        ctx.set_option('windows', 1)
+    assert seen_spec >= 8, 'no spectral-resident steps in the calm case'
+    assert seen_flag > 0, 'no flagged step in the drift case'
 
 
 def test_trunc_torus_matches_full_torus(pkb):

@@ -123,6 +123,48 @@ def test_prob_mass_small(pkb, tmp_path):
         assert np.array_equal(wind[d], snapshot[d])
 
 
+def test_prob_mass_is_bit_reproducible(pkb, tmp_path):
+    """Per-period contributions are accumulated in 64-bit fixed point with integer atomics (phase1.cuh,
+    acc_add_fixed), so the kernels -- and with them every keep/drop decision at the 1e-8 threshold and an MCMC
+    trace -- are bit-identical from run to run, whatever order the period CTAs retire in."""
+    z, wind, days, args = _small(pkb, tmp_path)
+    pm_args = [(d, wind) + args for d in days]
+    runs = []
+    for _ in range(3):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            runs.append(pkb.PM.prob_mass_batch(pm_args))
+    for a, b in zip(runs[0], runs[1]):
+        assert np.array_equal(a.toarray(), b.toarray())
+    for a, b in zip(runs[0], runs[2]):
+        assert np.array_equal(a.toarray(), b.toarray())
+
+
+def test_ring_decision_in_reference_order(pkb, tmp_path):
+    """Option ring_tol: where the support-ring test 1 - sum < 0.001 (ParasitoidModel.py:345-348) lands within
+    ring_tol of the threshold it is re-taken with the reference's own running sum (centre, corners, sides in call
+    order).  ring_tol = 1 forces that path for every period and every get_mvn_cdf_values call: same supports,
+    same kernels."""
+    z, wind, days, args = _small(pkb, tmp_path)
+    ctx = pkb._lib.ctx()
+    out = {}
+    try:
+        for tol in (1e-12, 1.0):
+            ctx.set_option('ring_tol', tol)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                pm = pkb.PM.prob_mass_batch([(d, wind) + args for d in days[:4]])
+            cells = [pkb.PM.get_mvn_cdf_values(25.0, np.array(mu), pkb.PM.Dmat(*dp))
+                     for mu, dp in (((3.0, -7.0), H.DPARAMS), ((0.0, 0.0), H.DLPARAMS), ((-12.4, 12.4), (60.0, 90.0, -0.5)))]
+            out[tol] = (pm, cells)
+    finally:
+        ctx.set_option('ring_tol', 1e-12)
+    for a, b in zip(out[1e-12][0], out[1.0][0]):
+        assert a.shape == b.shape and np.array_equal(a.toarray(), b.toarray())
+    for a, b in zip(out[1e-12][1], out[1.0][1]):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
 def test_prob_mass_edges(pkb, tmp_path):
     z, wind, days, args = _small(pkb, tmp_path)
     rd, rr = args[-2], args[-1]
