@@ -18,10 +18,20 @@ plus the 59-step convolution chain.
             region -- what a caller of Run.main sees.
 `roofline`  the dominant chain kernel against the measured HBM copy bandwidth;
 `roofline_chain` all chain kernels of one simulated day against B_day(P, D).
-`cpu_baseline` / `--impl reference`: the CPU path (oracle/, the numpy
-            restatement of the reference -- the reference itself is Python
-            that cannot travel to the GPU box) on a bounded sample, phase 1
-            fanned out over a multiprocessing pool like Run.py:422-425.
+`roofline_phase1` kernel construction (k_period) against the measured fp64 DFMA
+            and exp rates; executed flops from the committed ncu capture.
+`cpu_baseline` the CPU path (oracle/, the numpy restatement of the reference)
+            on a bounded sample, phase 1 fanned out over a multiprocessing
+            pool like Run.py:422-425.
+`--impl reference` the UNMODIFIED reference (ParasitoidModel.prob_mass with the
+            3-line mvnun shim, CalcSol.get_solutions) from baseline/_ref on a
+            bounded sample (kind "reference"); the oracle port if that copy is
+            absent (kind "port").
+`extra`     the other BASELINE.json configurations at every N: c5 (512 prior
+            draws x the Kalbar population solve through batch.solve_batch,
+            strong scaling), weak_batch (one C4 proposal per rank through the
+            same solve_batch path, weak scaling); at N = 1 also c1/c2/c3
+            (Kalbar / Carnarvon at 801^2) with the CPU port beside them.
 
 N > 1: independent parameter proposals of the same solve, one per rank (the
 batched-likelihood partitioning of SURVEY.md section 8e); the only collective
@@ -59,19 +69,27 @@ WORKLOADS = {
 BATCH = 512
 
 
-def kalbar_wind():
-    """Kalbar wind series (data/kalbarwind.txt as committed in tests/golden/wind.npz) through get_wind_data."""
+SITES = {'kalbar': ('kalbar', '00:00'), 'carnarvon': ('carnarvonearl', '00:30')}       # Run.py:108-138
+
+
+def _wind_reader(cpu):
+    """get_wind_data: the package's (interpolation on the device) or, for the CPU arms, the oracle's restatement."""
+    if cpu:
+        from oracle import pm_oracle as PO
+        return PO.get_wind_data
     from parasitoids_b200 import ParasitoidModel as PM
-    from parasitoids_b200 import Run
-    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'wind.npz'))
-    with tempfile.TemporaryDirectory() as tmp:
-        prefix = os.path.join(tmp, 'kalbar')
-        with open(prefix + 'wind.txt', 'w') as fobj:
-            for d, block in zip(z['kalbar_days'], z['kalbar_raw']):
-                for wx, wy, _ in block:
-                    fobj.write('%d\t%.17g\t%.17g\n' % (d, wx, wy))
-        wind_data, days = PM.get_wind_data(prefix, 30, '00:00')
-    return Run.stack_wind(wind_data, days), wind_data, days, 10000.0, 400
+    return PM.get_wind_data
+
+
+def stack_wind(wind_data, days):
+    return np.stack([np.asarray(wind_data[d], dtype=float) for d in days])
+
+
+def site_wind(site, cpu=False):
+    """data/<site>wind.txt (the reference's wind records, shipped under data/) through get_wind_data."""
+    name, start = SITES[site]
+    wind_data, days = _wind_reader(cpu)(os.path.join(ROOT, 'data', name), 30, start)
+    return stack_wind(wind_data, days), wind_data, days, 10000.0, 400
 
 
 def prior_proposals(B, seed=7):
@@ -112,13 +130,11 @@ def synthetic_wind(ndays, per_day, seed=20261018):
     return w.reshape(ndays, per_day, 2)
 
 
-def load_workload(name):
-    """Write the synthetic series as a wind file and read it back through the
-    package's own get_wind_data (the reference's input path)."""
-    from parasitoids_b200 import ParasitoidModel as PM
-    from parasitoids_b200 import Run
+def load_workload(name, cpu=False):
+    """Write the synthetic series as a wind file and read it back through
+    get_wind_data (the reference's input path)."""
     if name == 'kalbar_batch512':
-        return kalbar_wind()
+        return site_wind('kalbar', cpu)
     ndays, per_day, interp, rad_dist, rad_res = WORKLOADS[name]
     raw = synthetic_wind(ndays, per_day)
     with tempfile.TemporaryDirectory() as tmp:
@@ -127,51 +143,139 @@ def load_workload(name):
             for d in range(ndays):
                 for wx, wy in raw[d]:
                     fobj.write('%d\t%.15g\t%.15g\n' % (d + 1, wx, wy))
-        wind_data, days = PM.get_wind_data(prefix, interp, '00:00')
-    return Run.stack_wind(wind_data, days), wind_data, days, rad_dist, rad_res
+        wind_data, days = _wind_reader(cpu)(prefix, interp, '00:00')
+    return stack_wind(wind_data, days), wind_data, days, rad_dist, rad_res
 
 
 # ---------------------------------------------------------------------------
-# CPU path (oracle) on a bounded sample
+# CPU arms on a bounded sample: the oracle port, or the unmodified reference
 # ---------------------------------------------------------------------------
 def _oracle_day(args):
     import warnings
     from oracle import pm_oracle as PO
-    day, wind_data, rad_dist, rad_res = args
+    day, wind_data, rad_dist, rad_res, start_time = args
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        return PO.prob_mass(day, wind_data, HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res)
+        return PO.prob_mass(day, wind_data, HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res, start_time)
 
 
-def cpu_sample(wind_data, days, rad_dist, rad_res, n_kernel_days, n_chain_steps):
-    """Time the CPU path on `n_kernel_days` kernels (multiprocessing pool, one
-    task per day as Run.py:422-425) and `n_chain_steps` chain steps
-    (single-threaded pocketfft, as scipy.fftpack is).  Returns a dict."""
+def _reference_day(args):
+    """The reference's own prob_mass (per-cell mvnun loop, ParasitoidModel.py:384-613) from baseline/_ref."""
+    import warnings
+    from oracle import ref_loader
+    pm, _, _ = ref_loader.load()
+    day, wind_data, rad_dist, rad_res, start_time = args
+    with warnings.catch_warnings(), ref_loader.quiet():
+        warnings.simplefilter('ignore')
+        return pm.prob_mass(day, wind_data, HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res, start_time)
+
+
+def _warm(kind):
+    """Import the modules a worker needs before the clock starts (scipy.stats alone takes a second or two)."""
+    from oracle import pm_oracle, cs_oracle      # noqa: F401
+    if kind == 'reference':
+        from oracle import ref_loader
+        ref_loader.load()
+    time.sleep(0.2)                              # keep this worker busy so that every worker of the pool gets one
+    return 0
+
+
+def _pool(n):
     import multiprocessing as mp
+    # forkserver: the parent may already hold a CUDA context (get_wind_data interpolates on the device)
+    return mp.get_context('forkserver').Pool(n)
+
+
+def _trim(wind_data, days, n):
+    return {d: wind_data[d] for d in days[:n + 1]}
+
+
+def cpu_sample(wind_data, days, rad_dist, rad_res, n_kernel_days, n_chain_steps, kind='port'):
+    """Time the CPU path on a bounded sample.  Phase 1: one task per day through a multiprocessing pool as
+    Run.py:422-425 does.  kind 'port': `n_kernel_days` whole days of the oracle's prob_mass.  kind 'reference': the
+    reference's prob_mass (54 s per day and core) on the last 1/20 of `cores` days (start_time = 0.95: 72 of the
+    1440 take-off periods), scaled by 20.  Phase 2: `n_chain_steps` chain steps, single-threaded as scipy.fftpack is
+    (the reference's get_solutions incl. its Python r_small_vals loop, or the oracle's).  Returns a dict."""
     from scipy import sparse
-    from oracle import cs_oracle as CO
     cores = os.cpu_count() or 1
-    pool_size = min(cores, n_kernel_days)
-    sub = {d: wind_data[d] for d in days[:n_kernel_days + 1]}
-    t0 = time.perf_counter()
-    with mp.get_context('fork').Pool(pool_size) as pool:
-        pmfs = pool.map(_oracle_day, [(d, sub, rad_dist, rad_res) for d in days[:n_kernel_days]])
-    t_k = time.perf_counter() - t0
+    if kind == 'reference':
+        from oracle import ref_loader
+        _, cs, _ = ref_loader.load()
+        frac, n_kernel_days = 0.05, max(n_kernel_days, min(cores, len(days) - 1))
+        pool_size = min(cores, n_kernel_days)
+        sub = _trim(wind_data, days, n_kernel_days)
+        with _pool(pool_size) as pool:
+            pool.map(_warm, ['reference'] * pool_size, chunksize=1)
+            t0 = time.perf_counter()
+            pool.map(_reference_day, [(d, sub, rad_dist, rad_res, 1.0 - frac) for d in days[:n_kernel_days]], chunksize=1)
+            t_k = (time.perf_counter() - t0) / frac
+        # chain inputs: whole-day kernels from the port (the reference would need ~1 min per day for them)
+        with _pool(min(cores, n_chain_steps + 1)) as pool:
+            pmfs = pool.map(_oracle_day, [(d, sub, rad_dist, rad_res, None) for d in days[:n_chain_steps + 1]])
+        get_solutions = cs.get_solutions
+    else:
+        from oracle import cs_oracle as CO
+        pool_size = min(cores, n_kernel_days)
+        sub = _trim(wind_data, days, n_kernel_days)
+        with _pool(pool_size) as pool:
+            pool.map(_warm, ['port'] * pool_size, chunksize=1)
+            t0 = time.perf_counter()
+            pmfs = pool.map(_oracle_day, [(d, sub, rad_dist, rad_res, None) for d in days[:n_kernel_days]], chunksize=1)
+            t_k = time.perf_counter() - t0
+        get_solutions = CO.get_solutions
     D = 2 * rad_res + 1
-    ms = [max(p.shape[0] for p in pmfs)] * 2
+    ms = np.array([max(p.shape[0] for p in pmfs)] * 2)
     off = rad_res - pmfs[0].shape[0] // 2
     sol = [sparse.coo_matrix((pmfs[0].data, (pmfs[0].row + off, pmfs[0].col + off)), shape=(D, D))]
     nst = min(n_chain_steps, len(pmfs) - 1)
     t0 = time.perf_counter()
-    CO.get_solutions(sol, pmfs, days, nst + 1, D, ms)
+    if kind == 'reference':
+        from oracle import ref_loader
+        with ref_loader.quiet():
+            get_solutions(sol, pmfs, days, nst + 1, D, ms)
+    else:
+        get_solutions(sol, pmfs, days, nst + 1, D, ms)
     t_c = time.perf_counter() - t0
     # a full pool keeps `cores` days in flight: per-day wall = one task's time / concurrency
-    per_day_kernel = t_k / n_kernel_days if pool_size >= n_kernel_days else t_k / n_kernel_days
     per_day_kernel_full_pool = (t_k * pool_size / n_kernel_days) / cores
     per_step_chain = t_c / max(nst, 1)
     return dict(kernel_s_per_day=per_day_kernel_full_pool, kernel_sample_wall_s=t_k, chain_s_per_day=per_step_chain,
-                pool=pool_size, cores=cores, kernel_days=n_kernel_days, chain_steps=nst,
+                pool=pool_size, cores=cores, kernel_days=n_kernel_days, chain_steps=nst, kind=kind,
                 days_per_s=1.0 / (per_day_kernel_full_pool + per_step_chain))
+
+
+def cpu_sample_text(c):
+    if c['kind'] == 'reference':
+        return ('reference prob_mass (unmodified, mvnun shim) on the last 1/20 of %d days through a pool of %d, scaled by 20, + %d chain '
+                'steps of the reference get_solutions single-threaded; per-day costs extrapolated to a pool of all %d cores'
+                % (c['kernel_days'], c['pool'], c['chain_steps'], c['cores']))
+    return ('%d kernel days through a pool of %d (oracle prob_mass) + %d chain steps single-threaded (oracle '
+            'get_solutions), per-day costs extrapolated to a pool of all %d cores' % (c['kernel_days'], c['pool'], c['chain_steps'], c['cores']))
+
+
+def cpu_full_site(site, model):
+    """The oracle port on one of the 801^2 configurations, whole run (C1/C2/C3): phase 1 through a pool of all cores,
+    chain single-threaded.  model: 'prob' or 'pop'.  Returns (seconds, days)."""
+    from oracle import cs_oracle as CO
+    from scipy import sparse
+    wind, wind_data, days, rad_dist, rad_res = site_wind(site, cpu=True)
+    r_dur, r_number, r_start = (1, 130000.0, None) if site == 'kalbar' else (5, 40000.0, 0.354)
+    t0 = time.perf_counter()
+    with _pool(min(os.cpu_count() or 1, len(days))) as pool:
+        pmfs = pool.map(_oracle_day, [(d, {k: wind_data[k] for k in (d, d + 1) if k in wind_data}, rad_dist, rad_res,
+                                        r_start if (model == 'pop' and i == 0) else None) for i, d in enumerate(days)])
+    D = 2 * rad_res + 1
+    ms = [max(p.shape[0] for p in pmfs)] * 2
+
+    def rec(p):
+        off = rad_res - p.shape[0] // 2
+        return sparse.coo_matrix((p.data, (p.row + off, p.col + off)), shape=(D, D))
+    if model == 'prob':
+        sol = [rec(pmfs[0])]
+        CO.get_solutions(sol, pmfs, days, len(days), D, ms)
+    else:
+        CO.get_populations([rec(p).tocsr() for p in pmfs[:r_dur]], pmfs, days, len(days), D, ms, r_dur, r_number, lambda day: 1.0 / r_dur)
+    return time.perf_counter() - t0, len(days)
 
 
 # ---------------------------------------------------------------------------
@@ -260,26 +364,151 @@ def traffic_from_profiles(kernel):
         return None
 
 
+def phase1_roofline(prof_period, ndays, periods, steps):
+    """FP64 roofline of kernel construction (k_period): executed fp64 flops per launch from the committed ncu
+    capture (profiles/ncu_phase1.json: smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on of one C4 launch,
+    60 days x 1440 periods) against the DFMA rate measured by tools/microbench.cu on this pool
+    (profiles/r1_microbench.jsonl), and the exp() rate against the measured fp64 exp rate."""
+    cnt, ms = prof_period
+    if not cnt:
+        return None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_phase1.json')) as fobj:
+            k = json.load(fobj)['k_period']
+        flops = 2.0 * k['dfma'] + k['dmul'] + k['dadd']
+        src = k.get('source')
+    except Exception:
+        return None
+    peak_tf, peak_exp = 36.43, 905.0
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_microbench.jsonl')) as fobj:
+            for ln in fobj:
+                rec = json.loads(ln)
+                if rec.get('bench') == 'dfma':
+                    peak_tf = rec['tflops']
+                if rec.get('bench') == 'exp_f64':
+                    peak_exp = rec['gexp_per_s']
+    except Exception:
+        pass
+    t = ms / cnt / 1000.0
+    # exp() calls of the column recurrence (phase1.cuh): per period a (2h+2)^2 corner lattice, h = 23 at the default
+    # covariance: 48 columns x 4 segments of 12 corners x 6 Gauss-Legendre nodes x 2 exp
+    exps = float(ndays) * periods * 48 * 4 * 6 * 2
+    ach = flops / t / 1e12
+    return {'kernel': 'k_period', 'bound': 'fp64', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+            'executed_fp64_flops_per_launch': flops, 'avg_launch_ms': ms / cnt, 'launches': cnt,
+            'exp_rate_gexp_per_s': exps / t / 1e9, 'exp_peak_gexp_per_s': peak_exp, 'exp_frac': exps / t / 1e9 / peak_exp,
+            'peak_source': 'measured DFMA / exp microbenchmark (profiles/r1_microbench.jsonl)', 'flops_source': src}
+
+
+def run_extras(args, ctx, torch, dist, rank, world, local, main_model, main_wind_dev, main_wind_shape, main_ndays, rad_dist, rad_res, cpu_sites):
+    """The other BASELINE.json configurations, measured in the same run (see the module docstring)."""
+    from parasitoids_b200 import Run, batch
+    extra = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def timed(fn, steps, warmup=1):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        tt = torch.tensor([(time.perf_counter() - t0) * 1000.0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]) / steps
+
+    cells = np.random.default_rng(7).integers(0, 2 * rad_res + 1, (1024, 2)).astype(np.int32)
+    # ---- weak_batch: one C4 proposal per rank through solve_batch (the path every N > 1 point of a scaling run uses)
+    H = main_model[0]
+    props = np.tile(np.array([H[1], H[2], H[3], H[4], H[5], H[6], *main_model[1], *main_model[2], H[0], main_model[4], main_model[3]]), (world, 1))
+    props[:, 6] *= 1 + 0.01 * np.arange(world)
+    props[:, 7] *= 1 - 0.005 * np.arange(world)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ms = timed(lambda: batch.solve_batch(None, props, cells, main_ndays, rad_dist, rad_res, prob_model=True, device=local,
+                                             wind_device_ptr=main_wind_dev.data_ptr(), wind_shape=main_wind_shape), max(2, min(args.steps, 3)))
+    extra['weak_batch'] = {'workload': args.workload, 'value': world * main_ndays / (ms / 1000.0), 'unit': 'days/s', 'ms_per_step': ms,
+                           'scaling': 'weak', 'api': 'batch.solve_batch, one proposal per rank, wind resident on the device, 1024 sample cells'}
+    # ---- c5: 512 prior draws x the Kalbar population solve, sharded over the ranks (strong scaling)
+    wind, wind_data, days, rd, rr = site_wind('kalbar')
+    wdev = torch.from_numpy(wind).cuda(local)
+    wpin = torch.from_numpy(wind).pin_memory()
+    proposals = prior_proposals(BATCH)
+    kcells = np.random.default_rng(7).integers(0, 2 * rr + 1, (1024, 2)).astype(np.int32)
+    kw = dict(prob_model=False, r_dur=1, r_number=130000.0, device=local)
+    l0 = ctx.launch_count()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ms_dev = timed(lambda: batch.solve_batch(None, proposals, kcells, len(days), rd, rr, wind_device_ptr=wdev.data_ptr(),
+                                                 wind_shape=wind.shape, **kw), 2)
+        launches = (ctx.launch_count() - l0) // 3
+        ms_e2e = timed(lambda: batch.solve_batch(wpin.numpy(), proposals, kcells, len(days), rd, rr, **kw), 2, warmup=0)
+    nd5 = BATCH * len(days)
+    per_rank = -(-BATCH // world)
+    extra['c5'] = {'workload': 'kalbar_batch512', 'value': nd5 / (ms_dev / 1000.0), 'unit': 'days/s', 'ms_per_step': ms_dev, 'scaling': 'strong',
+                   'proposals': BATCH, 'days': len(days), 'gpu_launches_per_step_rank0': int(launches),
+                   'e2e': {'value': nd5 / (ms_e2e / 1000.0), 'unit': 'days/s', 'ms_per_step': ms_e2e,
+                           'h2d_bytes_per_step': int(wind.nbytes + proposals[:per_rank].nbytes + kcells.nbytes),
+                           'd2h_bytes_per_step': int(BATCH * len(days) * 1024 * 8)},
+                   'api': 'batch.solve_batch: proposals sharded over the ranks, one all_gather of the sampled cells'}
+    del wdev
+    # ---- c1 / c2 / c3: the 801^2 configurations through Run.solve, COO triplets of every day to the host (N = 1 only)
+    if world == 1:
+        for name, site, model in (('c1', 'kalbar', 'prob'), ('c2', 'kalbar', 'pop'), ('c3_prob', 'carnarvon', 'prob'), ('c3_pop', 'carnarvon', 'pop')):
+            wind, wind_data, days, rd, rr = site_wind(site)
+            r_dur, r_number, r_start = (1, 130000.0, None) if site == 'kalbar' else (5, 40000.0, 0.354)
+            skw = dict(prob_model=True) if model == 'prob' else dict(prob_model=False, r_dur=r_dur, r_number=r_number,
+                                                                     r_dist=[1.0 / r_dur] * r_dur, r_start=r_start)
+            wp = torch.from_numpy(wind).pin_memory().numpy()
+            m = (HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rd, rr)
+
+            def one():
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    res = Run.solve(wp, len(days), *m, want_coo=True, device=local, **skw)
+                    res.coo_arrays()
+                    res.close()
+            ms = timed(one, 5, warmup=2)
+            rec = {'workload': '%s %s model, 801x801, %d days (Run.py presets)' % (site, 'probability' if model == 'prob' else 'population', len(days)),
+                   'e2e': {'value': len(days) / (ms / 1000.0), 'unit': 'days/s', 'ms_per_step': ms,
+                           'api': 'Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}}
+            if name in cpu_sites:
+                rec['cpu_baseline'] = cpu_sites[name]
+            extra[name] = rec
+    return extra
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     if rank != 0:
         return
-    wind, wind_data, days, rad_dist, rad_res = load_workload(args.workload)
+    wind, wind_data, days, rad_dist, rad_res = load_workload(args.workload, cpu=True)
+    from oracle import ref_loader
+    kind = 'reference' if ref_loader.available() else 'port'
     small = rad_res < 1000
-    nk, nc = (8, 4) if small else (4, 2)
+    total = args.warmup + args.steps
+    nk, nc = (8, 4) if small else (4, 3 if total <= 3 else 2)
     vals, last = [], None
-    for i in range(args.warmup + args.steps):
-        last = cpu_sample(wind_data, days, rad_dist, rad_res, nk, nc)
+    for i in range(total):
+        last = cpu_sample(wind_data, days, rad_dist, rad_res, nk, nc, kind)
         if i >= args.warmup:
             vals.append(last['days_per_s'])
     v = float(np.mean(vals))
-    sample = ('%d kernel days through a pool of %d (oracle prob_mass) + %d chain steps single-threaded (oracle '
-              'get_solutions), per-day costs extrapolated to a pool of all %d cores' % (nk, last['pool'], last['chain_steps'], last['cores']))
     line = {'impl': 'reference', 'metric': 'simulated days/sec (fp64)', 'value': v, 'unit': 'days/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * WORKLOADS[args.workload][0] / v,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'note': 'CPU path: numpy/scipy restatement of the reference (oracle/), host cores only'},
-            'cpu_baseline': {'value': v, 'unit': 'days/s', 'cores': last['cores'], 'kind': 'port', 'sample': sample,
+            'config': {'workload': args.workload,
+                       'note': ('CPU path: the unmodified reference modules (baseline/_ref, scipy.stats.mvn.mvnun shimmed onto SciPy\'s Genz BVU)'
+                                if kind == 'reference' else 'CPU path: numpy/scipy restatement of the reference (oracle/)') + ', host cores only'},
+            'cpu_baseline': {'value': v, 'unit': 'days/s', 'cores': last['cores'], 'kind': kind, 'sample': cpu_sample_text(last),
                              'kernel_s_per_day': last['kernel_s_per_day'], 'chain_s_per_day': last['chain_s_per_day']},
             'e2e': {'value': v, 'unit': 'days/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -293,6 +522,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='synthetic_4097x4097_60d', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the extra configurations (c1-c3, c5, weak_batch)')
     ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
                     help='library option (pkb_set_option), e.g. fuse_rows=0; recorded in config')
     args = ap.parse_args()
@@ -311,19 +541,21 @@ def main():
         return
 
     ndays = WORKLOADS[args.workload][0]
-    wind, wind_data, days, rad_dist, rad_res = load_workload(args.workload)
 
-    # CPU baseline first (fork-based pool before any CUDA context exists)
-    cpu = None
+    # CPU baseline first (rank 0 of a one-GPU run only): the oracle port on a bounded sample of the same workload
+    cpu, cpu_sites = None, {}
     if world == 1 and not args.no_cpu_baseline:
-        small = rad_res < 1000
-        nk, nc = (8, 4) if small else (4, 2)
-        c = cpu_sample(wind_data, days, rad_dist, rad_res, nk, nc)
-        cpu = {'value': c['days_per_s'], 'unit': 'days/s', 'cores': c['cores'], 'kind': 'port',
-               'sample': '%d kernel days through a pool of %d (oracle prob_mass) + %d chain steps single-threaded (oracle '
-                         'get_solutions), per-day costs extrapolated to a pool of all %d cores'
-                         % (c['kernel_days'], c['pool'], c['chain_steps'], c['cores']),
+        _, wd_cpu, days_cpu, rd_cpu, rr_cpu = load_workload(args.workload, cpu=True)
+        nk, nc = (8, 4) if rr_cpu < 1000 else (4, 3)
+        c = cpu_sample(wd_cpu, days_cpu, rd_cpu, rr_cpu, nk, nc)
+        cpu = {'value': c['days_per_s'], 'unit': 'days/s', 'cores': c['cores'], 'kind': 'port', 'sample': cpu_sample_text(c),
                'kernel_s_per_day': c['kernel_s_per_day'], 'chain_s_per_day': c['chain_s_per_day']}
+        if args.workload == 'synthetic_4097x4097_60d' and not args.no_extras:
+            for name, site, model in (('c1', 'kalbar', 'prob'), ('c2', 'kalbar', 'pop'), ('c3_prob', 'carnarvon', 'prob'), ('c3_pop', 'carnarvon', 'pop')):
+                sec, nd_site = cpu_full_site(site, model)
+                cpu_sites[name] = {'value': nd_site / sec, 'unit': 'days/s', 'seconds': sec, 'cores': c['cores'], 'kind': 'port',
+                                   'sample': 'whole run: oracle prob_mass through a pool of all cores, oracle chain single-threaded'}
+        del wd_cpu
 
     import torch
     import torch.distributed as dist
@@ -350,6 +582,7 @@ def main():
     for kv in args.opt:
         key, val = kv.split('=')
         ctx.set_option(key, float(val))
+    wind, wind_data, days, rad_dist, rad_res = load_workload(args.workload)
 
     # N > 1: a likelihood batch of one parameter proposal per rank (proposal 0 = the defaults),
     # sharded by parasitoids_b200.batch.solve_batch; the only collective is its all_gather
@@ -411,6 +644,7 @@ def main():
                       wind_shape=wind.shape, device=local)
     info = (r.P, r.N, r.dom_len, r.flags(), r.radii())
     window_steps = r.window_steps()
+    spectral_steps = len(r.spectral_steps())
     r.close()
     for _ in range(args.warmup):
         close(step_device())
@@ -512,23 +746,31 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e_ms = float(te[0])
     e2e = {'value': units * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
-           'h2d_bytes_per_step': int(wind.nbytes) * (len(proposals) if (world > 1 or batch_mode) else 1), 'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
+           # batch modes: every rank uploads the wind once per call plus its share of the proposals and the cells
+           'h2d_bytes_per_step': int(wind.nbytes + (proposals[:-(-len(proposals) // world)].nbytes + cells.nbytes if (world > 1 or batch_mode) else 0)),
+           'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
            'ms_per_step': e_ms / args.steps, 'timer': 'host wall clock between device synchronisations',
            'api': ('parasitoids_b200.batch.solve_batch: wind from pinned host memory on every rank, sampled cells of all proposals '
                    'all-gathered and copied to host') if (world > 1 or batch_mode) else
                   'parasitoids_b200.Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}
 
+    extra = None
+    if not args.no_extras and not batch_mode and args.workload == 'synthetic_4097x4097_60d':
+        extra = run_extras(args, ctx, torch, dist, rank, world, local, model, wind_dev, wind.shape, ndays, rad_dist, rad_res, cpu_sites)
     if rank == 0:
         line = {'metric': 'simulated days/sec (fp64)', 'value': value, 'unit': 'days/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if batch_mode else 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': P, 'fft_len': N,
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
-                           'support_window_steps': window_steps,
+                           'support_window_steps': window_steps, 'spectral_resident_steps': spectral_steps,
                            'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if (world > 1 or batch_mode) else 'single solve',
                            'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
-                'roofline': roofline, 'roofline_chain': roofline_chain}
+                'roofline': roofline, 'roofline_chain': roofline_chain,
+                'roofline_phase1': None if batch_mode else phase1_roofline(prof['k_period'], ndays, int(wind.shape[1]), args.steps)}
+        if extra:
+            line['extra'] = extra
         if args.opt:
             line['config']['options'] = list(args.opt)
         if cpu is not None:

@@ -55,6 +55,14 @@ typedef struct pkb_day_args {
     int rad_res;
     int wind_day;        /* row of the wind array that holds this day */
     int single;          /* 1: wind row is a single (wx, wy, wr) triple (test form, :426-428) */
+    /* kind 1: not a prob_mass day but the local day-0 spread kernel the Bayes drivers prepend when the wind record
+     * starts a day late (Bayes_Run.py:245-270, Bayes_MAP.py:247-277): sprd_factor * get_mvn_cdf_values(dparams)
+     * shifted by the integer part of sprd_drift, plus (1 - sprd_factor) * get_mvn_cdf_values(dlparams), centre
+     * topped up to unit mass; not thresholded.  Only dparams, dlparams, rad_dist and rad_res are read besides. */
+    int kind;
+    int pad_;
+    double sprd_factor;
+    double sprd_drift[2];   /* mean drift in metres (the reference uses (-25, 15)) */
 } pkb_day_args;
 
 typedef struct pkb_day_meta {
@@ -86,6 +94,7 @@ int pkb_sync(pkb_ctx* ctx);
  * "trunc_torus" (0/1: steps from a truncated (flagged) state on a torus >= dom_len + 2m, default 1),
  * "spectral" (0/1: spectral-resident chain steps while the content outside the domain is below 1e-14, default 1;
  *             the one option whose results differ by more than rounding: by at most 1e-12, see chain.cuh),
+ * "spectral_min_reach" (arm them only if the exact support stays inside the domain for this many steps, default 4),
  * "ring_tol" (support-ring decisions of get_mvn_cdf_values closer than this to cdf_eps are re-taken with the reference's
  *             own running sum, ParasitoidModel.py:345-373; default 1e-12, 1.0 forces that path everywhere),
  * "batch_lanes" (1..8: proposals of pkb_solve_batch in flight at once, default 4),
@@ -109,6 +118,11 @@ int pkb_profile_reset(pkb_ctx* ctx);
 int pkb_profile_get(pkb_ctx* ctx, const char* kernel, long long* count, double* total_ms);
 
 /* ---- phase 1: ParasitoidModel.py ------------------------------------------ */
+/* The interpolation of get_wind_data(site_name, interp_num, start_time)  (ParasitoidModel.py:162-227).
+ * raw: [nd][npts][3] (wx, wy, wr) of consecutive days as read from the wind file; out: [nd][npts*interp_num][3].
+ * half_hour_start: 0 for start_time '00:00', 1 for '00:30'. */
+int pkb_wind_interp(pkb_ctx* ctx, const double* raw, int nd, int npts, int interp_num, int half_hour_start, double* out);
+
 /* h_flight_prob(day_wind, lam, aw, bw, a1, b1, a2, b2)  (ParasitoidModel.py:282-309)
  * wind: [periods][3] (or [3] when single != 0); out: [periods] (or [1]) */
 int pkb_hprob(pkb_ctx* ctx, const double* wind, int periods, int single, const double hparams[7], double* out,
@@ -202,6 +216,12 @@ typedef struct pkb_solve_args {
     int want_dense_host;     /* copy dense solutions to host */
     int want_coo;            /* build COO (row-major) on device and copy to host */
     int keep_dense_device;   /* keep [ndays][D][D] on device (bench / gather) */
+    int sprd;                /* 1: prepend the day-0 spread kernel (pkb_day_args kind 1) built from day.dparams / day.dlparams,
+                              * run the chain over ndays + 1 days and drop the first (Bayes_Run.py:245-296) */
+    double sprd_factor;
+    double sprd_drift[2];
+    const double* sprd_factors; /* pkb_solve_batch only: one sprd_factor per proposal (it is a sampled variable of its own,
+                                 * Bayes_Run.py:202); NULL: sprd_factor for all */
     int keep_pre_device;     /* parity export: also keep every day's UN-thresholded domain grid (the `A[:D,:D]` of
                               * CalcSol.py:189-190 / the cohort sum of :322 before r_small_vals) for pkb_result_pre */
 } pkb_solve_args;
@@ -216,6 +236,32 @@ int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
  * (proposal, day) kernel.  Kernel construction is batched over groups of proposals. */
 int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells /*[K][2]*/, int K,
                     double* out, int* status);
+/* ---- likelihood projection: Bayes_funcs.py:20-180 on the device --------------------------------------------
+ * popdensity_to_emergence / popdensity_grid read the model only at a few cells and fold it with the incubation
+ * distribution; both are an ordered linear map of the model at K sample cells, described by the caller (the
+ * Python side builds it from a LocInfo exactly as the reference's loops run, parasitoids_b200/Bayes_funcs.py):
+ *   S[day][set]   = numpy-sum of the model over the sample cells set_cells[set_ptr[set] .. set_ptr[set+1])
+ *   G[group]      = ((0 + S[term_day][term_set] * term_w) + ...) over the terms grp_ptr[group] .. grp_ptr[group+1)
+ *   out[row]      = numpy-sum of G over the groups row_ptr[row] .. row_ptr[row+1)
+ * ("numpy-sum": numpy's pairwise summation order, restated in csrc/project.cuh.)  All arrays are host arrays. */
+typedef struct pkb_projection {
+    int nsets;
+    const int* set_ptr;     /* [nsets + 1] */
+    const int* set_cells;   /* indices into the K sample cells */
+    int nrows;
+    const int* row_ptr;     /* [nrows + 1] -> groups */
+    int ngroups;
+    const int* grp_ptr;     /* [ngroups + 1] -> terms */
+    const int* term_day;    /* model day (0 = first output day) */
+    const int* term_set;
+    const double* term_w;
+} pkb_projection;
+/* out[nprop][nrows] from host samples[nprop][ndays][K] (what pkb_solve_batch returns) */
+int pkb_project(pkb_ctx* ctx, const pkb_projection* proj, const double* samples, int nprop, int ndays, int K, double* out);
+/* pkb_solve_batch with the projection applied on the device: out[nprop][proj->nrows]; only the projected values
+ * cross PCIe (Bayes_Run.py:298-306: popdensity_to_emergence + popdensity_grid straight after get_populations) */
+int pkb_solve_batch_projected(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells /*[K][2]*/,
+                              int K, const pkb_projection* proj, double* out, int* status);
 int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape);
 /* number of chain steps that ran on a support-window torus smaller than N (exact: the state is
  * identically zero outside the window while the spread has not reached the domain edge) */
@@ -233,6 +279,8 @@ int pkb_result_coo(pkb_result* r, const long long** day_offsets /*[ndays+1]*/, c
                    const double** vals);
 /* gather values at K (row, col) cells for every day: out[ndays][K] */
 int pkb_result_sample(pkb_result* r, const int* cells /*[K][2]*/, int K, double* out);
+/* projection of one solve's dense device-resident days (keep_dense_device / want_dense_host): out[proj->nrows] */
+int pkb_result_project(pkb_result* r, const int* cells /*[K][2]*/, int K, const pkb_projection* proj, double* out);
 /* device pointer of the dense solutions [ndays][D][D] (keep_dense_device) */
 int pkb_result_device_ptr(pkb_result* r, void** dptr);
 int pkb_result_destroy(pkb_result* r);

@@ -366,12 +366,103 @@ def _make_full(which):
     _save(which + '_full', **out)
 
 
+SPRD_CASES = [
+    # (domain_info, Dparams, Dlparams, sprd_factor)
+    ((10000.0, 400), DPARAMS, DLPARAMS, 0.1),            # Bayes_Run defaults (res 25 m)
+    ((10000.0, 200), DPARAMS, DLPARAMS, 0.35),           # Bayes_MAP domain (res 50 m)
+    ((10000.0, 400), (90.0, 60.0, -0.6), (20.0, 31.0, 0.4), 0.8),
+    ((8000.0, 500), (30.0, 40.0, 0.95), (9.0, 9.0, 0.0), 0.0),
+    ((2000.0, 40), DPARAMS, DLPARAMS, 1.0),
+]
+
+
+def _reference_sprd_source():
+    """The body of the `if sprd_factor is not None:` block of Bayes_Run.pop_model (Bayes_Run.py:246-269), read from
+    the reference tree at generation time and executed as it stands (Bayes_Run itself cannot be imported: pymc)."""
+    import textwrap
+    with open(os.path.join(ref_loader.REF_ROOT, 'Bayes_Run.py')) as fobj:
+        lines = fobj.read().split('\n')
+    start = next(i for i, ln in enumerate(lines) if ln.strip() == 'if sprd_factor is not None:') + 1
+    end = next(i for i in range(start, len(lines)) if lines[i].strip().startswith('pmf_list = [sparse.coo_matrix(sprd)]'))
+    return textwrap.dedent('\n'.join(lines[start:end]))
+
+
+def make_sprd():
+    pm, _, _ = ref_loader.load()
+    src = _reference_sprd_source()
+    out = {'ncases': np.array(len(SPRD_CASES))}
+    for i, (dom, dp, dl, f) in enumerate(SPRD_CASES):
+        class _P(object):
+            domain_info = dom
+        ns = {'np': np, 'PM': pm, 'params': _P(), 'params_ary': list(range(6)) + list(dp) + list(dl), 'sprd_factor': f}
+        exec(src, ns)
+        out['c%d_sprd' % i] = ns['sprd']
+        out['c%d_args' % i] = np.array([dom[0], dom[1], *dp, *dl, f])
+    _save('sprd', **out)
+
+
+class _Days(object):
+    """Stand-in for a pandas Timedelta: Bayes_funcs only reads `.days`."""
+    def __init__(self, d):
+        self.days = int(d)
+
+
+def bayes_locinfo(rng, dom_len, ndays):
+    """A synthetic LocInfo with the attributes Bayes_funcs.py:20-173 reads (Data_Import.LocInfo builds the real one
+    from the field spreadsheets): two collections with emergence grids and observation dates, three sentinel
+    fields, a release-field grid observed on two days."""
+    import pandas as pd
+
+    class Loc(object):
+        pass
+    loc = Loc()
+    mid = dom_len // 2
+    span = max(3, dom_len // 10)
+    loc.collection_datesPR = [_Days(min(ndays - 1, 6)), _Days(ndays)]
+    loc.emerg_grids = [[(int(mid + rng.integers(-span, span)), int(mid + rng.integers(-span, span))) for _ in range(n)] for n in (7, 11)]
+    loc.release_DataFrames = []
+    loc.sent_DataFrames = []
+    for cd, obs in zip(loc.collection_datesPR, ((0, 3, 4, 9), (2, 5, 20, 24))):
+        dates = [pd.Timedelta(days=cd.days + o) for o in obs for _ in range(2)]
+        loc.release_DataFrames.append(pd.DataFrame({'datePR': dates}))
+        loc.sent_DataFrames.append(pd.DataFrame({'datePR': dates[::2] + dates[-1:]}))
+    loc.sent_ids = ['A', 'B', 'C']
+    loc.field_cells = {}
+    for k, fid in enumerate(loc.sent_ids):
+        r0, c0 = mid + (k - 1) * span, mid - span + 2 * k
+        rr, cc = np.meshgrid(np.arange(r0, r0 + 4 + k), np.arange(c0, c0 + 5))
+        loc.field_cells[fid] = np.stack([rr.ravel(), cc.ravel()], axis=1)
+    loc.grid_cells = np.array([(int(mid + rng.integers(-span, span)), int(mid + rng.integers(-span, span))) for _ in range(9)])
+    loc.grid_obs_datesPR = [_Days(2), _Days(min(ndays, 5))]
+    return loc
+
+
+def make_bayes_funcs():
+    """Bayes_funcs.popdensity_to_emergence / popdensity_grid (the reference module imports as it stands) on the
+    small Kalbar population solution of chain_small and on a random dense model of 30 days."""
+    ref_loader.load()
+    bf = __import__('Bayes_funcs')
+    out = {}
+    rng = np.random.default_rng(42)
+    for tag, D, nd in (('a', 81, 8), ('b', 61, 30)):
+        model = [sparse.csr_matrix(np.where(rng.random((D, D)) < 0.3, rng.random((D, D)) * 50, 0.0)) for _ in range(nd)]
+        loc = bayes_locinfo(np.random.default_rng(7), D, nd)
+        rel, sen = bf.popdensity_to_emergence(model, loc)
+        grid = bf.popdensity_grid(model, loc)
+        out[tag + '_model'] = np.stack([m.toarray() for m in model])
+        for i, (r, s_) in enumerate(zip(rel, sen)):
+            out['%s_rel%d' % (tag, i)] = r
+            out['%s_sen%d' % (tag, i)] = s_
+        out[tag + '_grid'] = grid
+    _save('bayes_funcs', **out)
+
+
 def main(argv):
     if not ref_loader.available():
         sys.exit('reference tree not found at ' + ref_loader.REF_ROOT)
     what = argv or ['bvn', 'hprob', 'pm_small', 'chain_small']
     table = {'wind': make_wind, 'bvn': make_bvn, 'hprob': make_hprob, 'pm_small': make_pm_small,
-             'chain_small': make_chain_small, 'pm_full': make_pm_full,
+             'chain_small': make_chain_small, 'pm_full': make_pm_full, 'sprd': make_sprd, 'bayes_funcs': make_bayes_funcs,
              'kalbar_full': lambda: _make_full('kalbar'),
              'carnarvon_full': lambda: _make_full('carnarvon')}
     for w in what:

@@ -250,6 +250,91 @@ def get_mvn_cdf_values(cell_length, mu, S, H0=None):
     return np.ascontiguousarray(sub.T[::-1, :])          # rows: y descending
 
 
+def sprd_kernel(res, Dparams, Dlparams, sprd_factor, mean_drift=(-25., 15.)):
+    """Bayes_Run.py:245-270 / Bayes_MAP.py:247-277 -- the local day-0 spread kernel the Bayes drivers prepend when
+    the wind record starts a day late: the in-flow blob carried by the mean drift (integer cells + remainder, Python
+    floor division / modulo), mixed with the out-of-flow blob, centre topped up to unit mass.  Dense (mlen, mlen)."""
+    xi = int(mean_drift[0] // res)
+    xr = mean_drift[0] % res
+    yi = int(mean_drift[1] // res)
+    yr = mean_drift[1] % res
+    longsprd = get_mvn_cdf_values(res, np.array([xr, yr]), Dmat(*Dparams))
+    shrtsprd = get_mvn_cdf_values(res, np.array([0., 0.]), Dmat(*Dlparams))
+    mlen = int(max(longsprd.shape[0], shrtsprd.shape[0]) + max(abs(xi), abs(yi)) * 2)
+    sprd = np.zeros((mlen, mlen))
+    lo, hi = mlen // 2 - longsprd.shape[0] // 2, mlen // 2 + longsprd.shape[0] // 2 + 1
+    sprd[lo - yi:hi - yi, lo + xi:hi + xi] = longsprd * sprd_factor
+    lo, hi = mlen // 2 - shrtsprd.shape[0] // 2, mlen // 2 + shrtsprd.shape[0] // 2 + 1
+    sprd[lo:hi, lo:hi] += shrtsprd * (1 - sprd_factor)
+    sprd[mlen // 2, mlen // 2] += max(0, 1 - sprd.sum())
+    return sprd
+
+
+# --------------------------------------------------------------------------
+# Wind input (ParasitoidModel.py:64-227): the path's input producer
+# --------------------------------------------------------------------------
+def read_wind_file(site_name):
+    """ParasitoidModel.py:64-132 -- raw wind series {day: ndarray(times, 3)} of (windx, windy, windr) and the sorted
+    day list; components below 1e-4 are zeroed."""
+    rows = {}
+    with open(site_name + 'wind.txt') as fobj:
+        for line in fobj:
+            cols = line.split()
+            if not cols:
+                continue
+            wx, wy = float(cols[1]), float(cols[2])
+            if abs(wx) < 10e-5:
+                wx = 0
+            if abs(wy) < 10e-5:
+                wy = 0
+            wr = np.sqrt(wx ** 2 + wy ** 2)
+            if abs(wr) < 10e-5:
+                wr = 0
+            rows.setdefault(int(cols[0]), []).append((wx, wy, wr))
+    wind = {day: np.array(v, dtype=float) for day, v in rows.items()}
+    return wind, sorted(wind)
+
+
+def get_wind_data(site_name, interp_num, start_time):
+    """Linearly interpolated wind, ``interp_num`` points per raw interval
+    (ParasitoidModel.py:136-227).  '00:00': the day's last interval interpolates towards the
+    next day's first sample (the final day repeats its last sample); '00:30':
+    the day's first interval interpolates from the previous day's last sample
+    (the first day repeats its first sample)."""
+    raw, days = read_wind_file(site_name)
+    if start_time not in ('00:00', '00:30'):
+        raise ValueError("start_time must be either '00:00' or '00:30'")
+    npts = raw[days[0]].shape[0]
+    w1 = np.linspace(0, 1, interp_num + 1)[:-1][:, None]       # weight of the later sample
+    w0 = 1 - w1
+
+    def blend(a, b):
+        return w0 * a + w1 * b
+
+    wind = {}
+    for n, day in enumerate(days):
+        r = raw[day]
+        out = np.zeros((npts * interp_num, 3))
+        first = 0 if start_time == '00:00' else 1
+        for k in range(npts - 1):
+            out[(k + first) * interp_num:(k + first + 1) * interp_num] = blend(r[k], r[k + 1])
+        if start_time == '00:00':
+            if n + 1 < len(days):
+                out[(npts - 1) * interp_num:] = blend(r[-1], raw[day + 1][0])
+                out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
+            else:
+                out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
+                out[(npts - 1) * interp_num:] = r[-1]
+        else:
+            if n == 0:
+                out[:interp_num] = r[0]
+            else:
+                out[:interp_num] = blend(raw[day - 1][-1], r[0])
+            out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
+        wind[day] = out
+    return wind, days
+
+
 # --------------------------------------------------------------------------
 # Threshold / renormalise (CalcSol.py:112-136), needed by prob_mass
 # --------------------------------------------------------------------------

@@ -20,7 +20,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('PARASITOIDS_REFERENCE', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the copy that __graft_entry__.build() leaves under
+# baseline/_ref/ (git-ignored, travels with the snapshot) -- used there ONLY by bench.py's reference arm
+_SHIPPED = os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')
+REF_ROOT = os.environ.get('PARASITOIDS_REFERENCE') or ('/root/reference' if os.path.isfile('/root/reference/ParasitoidModel.py') else _SHIPPED)
 
 
 def available():

@@ -69,39 +69,20 @@ def get_wind_data(site_name, interp_num, start_time):
     (:136-227).  '00:00': the day's last interval interpolates towards the
     next day's first sample (the final day repeats its last sample); '00:30':
     the day's first interval interpolates from the previous day's last sample
-    (the first day repeats its first sample)."""
+    (the first day repeats its first sample).  The file is parsed on the host;
+    the interpolation runs on the device (k_wind_interp) with numpy's own
+    weights and operation order, so the arrays equal the reference's bit for bit."""
     raw, days = read_wind_file(site_name)
     if start_time not in ('00:00', '00:30'):
         raise ValueError("start_time must be either '00:00' or '00:30'")
+    if days != list(range(days[0], days[0] + len(days))):
+        raise KeyError('wind days must be consecutive integers (:178,:214)')
     npts = raw[days[0]].shape[0]
-    w1 = np.linspace(0, 1, interp_num + 1)[:-1][:, None]       # weight of the later sample
-    w0 = 1 - w1
-
-    def blend(a, b):
-        return w0 * a + w1 * b
-
-    wind = {}
-    for n, day in enumerate(days):
-        r = raw[day]
-        out = np.zeros((npts * interp_num, 3))
-        first = 0 if start_time == '00:00' else 1
-        for k in range(npts - 1):
-            out[(k + first) * interp_num:(k + first + 1) * interp_num] = blend(r[k], r[k + 1])
-        if start_time == '00:00':
-            if n + 1 < len(days):
-                out[(npts - 1) * interp_num:] = blend(r[-1], raw[day + 1][0])
-                out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
-            else:
-                out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
-                out[(npts - 1) * interp_num:] = r[-1]
-        else:
-            if n == 0:
-                out[:interp_num] = r[0]
-            else:
-                out[:interp_num] = blend(raw[day - 1][-1], r[0])
-            out[:, 2] = np.sqrt(out[:, 0] ** 2 + out[:, 1] ** 2)
-        wind[day] = out
-    return wind, days
+    stacked = _lib.as_f64(np.stack([raw[d] for d in days]))
+    out = np.empty((len(days), npts * int(interp_num), 3))
+    _lib.check(_lib.lib().pkb_wind_interp(_lib.ctx().h, _lib.dptr(stacked), len(days), npts, int(interp_num),
+                                          0 if start_time == '00:00' else 1, _lib.dptr(out)))
+    return {day: out[n] for n, day in enumerate(days)}, days
 
 
 # ---------------------------------------------------------------------------
@@ -266,6 +247,29 @@ def build_kernels(wind, args, keep_pre=False):
     _lib.check(_lib.lib().pkb_kernels_build(_lib.ctx().h, _lib.dptr(wind), wind.shape[0], wind.shape[1], arr,
                                             len(args), 1 if keep_pre else 0, C.byref(h)))
     return KernelSet(h, len(args))
+
+
+def sprd_kernel(res, Dparams, Dlparams, sprd_factor, mean_drift=(-25., 15.)):
+    """The local day-0 spread kernel the Bayes drivers build inline when the wind record starts a day late
+    (Bayes_Run.py:245-270, Bayes_MAP.py:247-277), as a dense (mlen, mlen) array: ``sprd_factor`` times the in-flow
+    blob ``get_mvn_cdf_values(res, drift remainder, Dmat(*Dparams))`` shifted by the whole cells of ``mean_drift``,
+    plus ``1 - sprd_factor`` times the out-of-flow blob, centre topped up to unit mass.  ``Run.solve(...,
+    sprd_factor=...)`` builds and uses it on the device; this function hands it back for inspection."""
+    a = _abi.DayArgs()
+    a.dparams[:] = [float(v) for v in Dparams]
+    a.dlparams[:] = [float(v) for v in Dlparams]
+    a.rad_res = 4096                      # only the cell size matters: rad_dist / rad_res = res
+    a.rad_dist = float(res) * a.rad_res
+    a.start_time = -1.0
+    a.n_periods = 1
+    a.kind = 1
+    a.sprd_factor = float(sprd_factor)
+    a.sprd_drift[:] = [float(mean_drift[0]), float(mean_drift[1])]
+    ks = build_kernels(np.zeros((1, 1, 3)), [a])
+    try:
+        return ks.dense(0)
+    finally:
+        ks.close()
 
 
 def _stack_wind(day, wind_data):

@@ -287,7 +287,8 @@ class SolveResult(object):
 
 
 def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur, r_number,
-                r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre=False):
+                r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre=False,
+                sprd_factor=None, sprd_drift=(-25., 15.)):
     """Fill a ``pkb_solve_args``; returns it with the arrays it points into (keep them alive)."""
     a = _abi.SolveArgs()
     if wind_device_ptr is not None:
@@ -313,17 +314,27 @@ def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_di
     a.want_coo = 1 if want_coo else 0
     a.keep_dense_device = 1 if keep_device else 0
     a.keep_pre_device = 1 if keep_pre else 0
+    if sprd_factor is not None:          # leading local-spread day (Bayes_Run.py:245-270, Bayes_MAP.py:247-277)
+        a.sprd = 1
+        a.sprd_factor = float(sprd_factor)
+        a.sprd_drift[0], a.sprd_drift[1] = float(sprd_drift[0]), float(sprd_drift[1])
     return a, (keep, w)
 
 
 def solve(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model=True,
           r_dur=1, r_number=1.0, r_dist=None, r_start=None, want_coo=True, want_dense=False, keep_device=False,
-          wind_device_ptr=None, wind_shape=None, device=None, keep_pre=False):
+          wind_device_ptr=None, wind_shape=None, device=None, keep_pre=False, sprd_factor=None, sprd_drift=(-25., 15.)):
     """Fused forward solve.  ``wind``: ndarray (nd_wind, periods, 3) of
     consecutive days (or None with ``wind_device_ptr``/``wind_shape`` for a
-    wind array already resident on the device).  Returns a ``SolveResult``."""
+    wind array already resident on the device).  Returns a ``SolveResult``.
+
+    ``sprd_factor`` (not None): the Bayes drivers' extra first day -- the release spreads locally for one day before
+    the wind record starts (Bayes_Run.py:245-270, Bayes_MAP.py:247-277): a kernel mixed from two
+    ``get_mvn_cdf_values`` blobs is prepended, the chain runs over ndays + 1 days and the first solution is dropped
+    (Bayes_Run.py:288-296)."""
     a, keep = _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur,
-                          r_number, r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre)
+                          r_number, r_dist, r_start, want_coo, want_dense, keep_device, wind_device_ptr, wind_shape, keep_pre,
+                          sprd_factor, sprd_drift)
     h = C.c_void_p()
     _lib.check(_lib.lib().pkb_solve(_lib.ctx(device).h, C.byref(a), C.byref(h)))
     del keep

@@ -26,7 +26,8 @@ ST_BORDERLINE = 128
 class DayArgs(C.Structure):
     _fields_ = [('hparams', C.c_double * 7), ('dparams', C.c_double * 3), ('dlparams', C.c_double * 3),
                 ('mu_r', C.c_double), ('rad_dist', C.c_double), ('start_time', C.c_double),
-                ('n_periods', C.c_int), ('rad_res', C.c_int), ('wind_day', C.c_int), ('single', C.c_int)]
+                ('n_periods', C.c_int), ('rad_res', C.c_int), ('wind_day', C.c_int), ('single', C.c_int),
+                ('kind', C.c_int), ('pad_', C.c_int), ('sprd_factor', C.c_double), ('sprd_drift', C.c_double * 2)]
 
 
 class DayMeta(C.Structure):
@@ -45,7 +46,13 @@ class SolveArgs(C.Structure):
                 ('ndays', C.c_int), ('day', DayArgs), ('prob_model', C.c_int), ('r_dur', C.c_int),
                 ('r_number', C.c_double), ('r_dist', c_double_p), ('r_start', C.c_double), ('negval', C.c_double),
                 ('want_dense_host', C.c_int), ('want_coo', C.c_int), ('keep_dense_device', C.c_int),
+                ('sprd', C.c_int), ('sprd_factor', C.c_double), ('sprd_drift', C.c_double * 2), ('sprd_factors', c_double_p),
                 ('keep_pre_device', C.c_int)]
+
+
+class Projection(C.Structure):
+    _fields_ = [('nsets', C.c_int), ('set_ptr', c_int_p), ('set_cells', c_int_p), ('nrows', C.c_int), ('row_ptr', c_int_p),
+                ('ngroups', C.c_int), ('grp_ptr', c_int_p), ('term_day', c_int_p), ('term_set', c_int_p), ('term_w', c_double_p)]
 
 
 _H = C.c_void_p        # opaque handles
@@ -65,6 +72,7 @@ _SIGS = {
     'pkb_profile_enable': (C.c_int, [_H, C.c_int]),
     'pkb_profile_reset': (C.c_int, [_H]),
     'pkb_profile_get': (C.c_int, [_H, C.c_char_p, c_ll_p, c_double_p]),
+    'pkb_wind_interp': (C.c_int, [_H, c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
     'pkb_hprob': (C.c_int, [_H, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     'pkb_mvn_cdf': (C.c_int, [_H, C.c_double, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p]),
     'pkb_kernels_build': (C.c_int, [_H, c_double_p, C.c_int, C.c_int, C.POINTER(DayArgs), C.c_int, C.c_int, _HP]),
@@ -90,6 +98,10 @@ _SIGS = {
     'pkb_smooth_len': (C.c_int, [C.c_int]),
     'pkb_solve': (C.c_int, [_H, C.POINTER(SolveArgs), _HP]),
     'pkb_solve_batch': (C.c_int, [_H, C.POINTER(SolveArgs), c_double_p, C.c_int, c_int_p, C.c_int, c_double_p, c_int_p]),
+    'pkb_project': (C.c_int, [_H, C.POINTER(Projection), c_double_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    'pkb_solve_batch_projected': (C.c_int, [_H, C.POINTER(SolveArgs), c_double_p, C.c_int, c_int_p, C.c_int, C.POINTER(Projection),
+                                            c_double_p, c_int_p]),
+    'pkb_result_project': (C.c_int, [_H, c_int_p, C.c_int, C.POINTER(Projection), c_double_p]),
     'pkb_result_info': (C.c_int, [_H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'pkb_result_window_steps': (C.c_int, [_H, c_int_p]),
     'pkb_result_day_meta': (C.c_int, [_H, C.c_int, C.POINTER(DayMeta), C.POINTER(StepMeta)]),

@@ -50,7 +50,7 @@ def _dist():
 
 
 def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number, r_dist, r_start, device,
-                 wind_device_ptr, wind_shape, ids):
+                 wind_device_ptr, wind_shape, ids, sprd_factors=None, sprd_drift=(-25., 15.), projection=None):
     """This rank's proposals through ONE library call (``pkb_solve_batch``: kernel construction
     batched over groups of proposals, chains back to back on the device-resident kernels)."""
     import ctypes as C
@@ -58,13 +58,24 @@ def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur
     from . import ParasitoidModel as PM
     hp, dp, dl, mu_r, n_periods = unpack_proposal(props[0])
     a, keep = Run._solve_args(wind, ndays, hp, dp, dl, mu_r, n_periods, rad_dist, rad_res, prob_model, r_dur, r_number,
-                              r_dist, r_start, False, False, True, wind_device_ptr, wind_shape)
+                              r_dist, r_start, False, False, True, wind_device_ptr, wind_shape,
+                              sprd_factor=None if sprd_factors is None else float(sprd_factors[0]), sprd_drift=sprd_drift)
+    if sprd_factors is not None:
+        sf = np.ascontiguousarray(sprd_factors, dtype=np.float64)
+        a.sprd_factors = _lib.dptr(sf)
+        keep = (keep, sf)
     props = np.ascontiguousarray(props, dtype=np.float64)
     n = props.shape[0]
-    out = np.empty((n, ndays, cells.shape[0]))
     status = np.zeros((n, ndays), dtype=np.int32)
-    _lib.check(_lib.lib().pkb_solve_batch(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells), cells.shape[0],
-                                          _lib.dptr(out), _lib.iptr(status)))
+    if projection is None:
+        out = np.empty((n, ndays, cells.shape[0]))
+        _lib.check(_lib.lib().pkb_solve_batch(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells), cells.shape[0],
+                                              _lib.dptr(out), _lib.iptr(status)))
+    else:
+        # the likelihood projection of every proposal on the device (Bayes_Run.py:298-306): only its rows come back
+        out = np.empty((n, projection.nrows))
+        _lib.check(_lib.lib().pkb_solve_batch_projected(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells),
+                                                        cells.shape[0], C.byref(projection.c), _lib.dptr(out), _lib.iptr(status)))
     del keep
     # the reference's assertion / warning sites, per (proposal, day) kernel (ParasitoidModel.py:529-599)
     for i in range(n):
@@ -76,29 +87,42 @@ def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur
 
 
 def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=False, r_dur=1, r_number=1.0,
-                r_dist=None, r_start=None, device=None, group=None, wind_device_ptr=None, wind_shape=None):
+                r_dist=None, r_start=None, device=None, group=None, wind_device_ptr=None, wind_shape=None,
+                sprd_factor=None, sprd_drift=(-25., 15.), projection=None):
     """Solve every proposal and return the model at ``cells`` for all of them.
 
     wind:       (nd_wind, periods, 3) consecutive days (``Run.stack_wind``), shared by all proposals
     proposals:  (B, 15) array in ``PROPOSAL_FIELDS`` order
     cells:      (K, 2) int (row, col) sample cells of the domain
+    sprd_factor: None, a scalar or (B,) -- the leading local-spread day of Bayes_Run.py:245-296 (its own sampled
+                variable there), see ``Run.solve``
+    projection: a ``Bayes_funcs.Projection`` (then ``cells`` is ignored, its own sample cells are used): every
+                proposal's solution is folded into the values ``popdensity_to_emergence`` / ``popdensity_grid`` return,
+                on the device; the result is (B, projection.nrows), ``projection.split(row)`` gives the arrays
     returns     (B, ndays, K) float64, identical on every rank
 
     With an initialised ``torch.distributed`` process group the proposals are
     sharded over the ranks (``shard``) and the results all-gathered; without
     one this is a plain loop on one GPU."""
     proposals = np.asarray(proposals, dtype=float).reshape(-1, len(PROPOSAL_FIELDS))
+    if projection is not None:
+        if projection.ndays != ndays:
+            raise ValueError('the projection was built for {} model days, the solve has {}'.format(projection.ndays, ndays))
+        cells = projection.cells
     cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
     B, K = proposals.shape[0], cells.shape[0]
+    tail = (ndays, K) if projection is None else (projection.nrows,)
     dist = _dist()
     world = dist.get_world_size(group) if dist else 1
     rank = dist.get_rank(group) if dist else 0
     mine = shard(B, world, rank)
     per = -(-B // world)                      # padded shard length
-    local = np.zeros((per, ndays, K))
+    local = np.zeros((per,) + tail)
+    sf = None if sprd_factor is None else np.broadcast_to(np.asarray(sprd_factor, dtype=float), (B,))
     if mine:
         local[:len(mine)] = _solve_shard(wind, proposals[mine], cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number,
-                                         r_dist, r_start, device, wind_device_ptr, wind_shape, mine)
+                                         r_dist, r_start, device, wind_device_ptr, wind_shape, mine,
+                                         None if sf is None else sf[mine], sprd_drift, projection)
     if world == 1:
         return local[:B]
     import torch
@@ -109,7 +133,7 @@ def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=Fal
     out = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)       # concatenated along dim 0 (gloo and nccl both accept this form)
     out = out.cpu().numpy().reshape((world, per) + tuple(t.shape[1:]))
-    full = np.empty((B, ndays, K))
+    full = np.empty((B,) + tail)
     for r in range(world):
         idx = shard(B, world, r)
         full[idx] = out[r, :len(idx)]

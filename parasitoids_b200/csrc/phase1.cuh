@@ -30,25 +30,33 @@ namespace pkb {
 #define PKB_LATTICE_CAP 5120      // doubles of shared memory for the corner lattice tile
 #define PKB_BVN_SEG 12            // lattice corners a thread marches along one column (k_period)
 
-// Per-period contributions are accumulated as 64-bit FIXED-POINT numbers (units of 2^-60) with integer atomics:
-// integer addition is associative, so the day's window is bit-identical from run to run whatever order the
-// period CTAs finish in (fp64 atomics gave sums that differed in the last bits, and with them the occasional
-// keep/drop decision at the 1e-8 threshold).  A contribution h[t] * cdf is <= 1 and is rounded to 2^-60 = 8.7e-19;
-// over the 1440 periods of a day that stays below 1e-15 absolute in the worst case, the same order as the rounding of
-// the reference's own `pmf += hprob * cdf` (ParasitoidModel.py:539) on cells of the size that matter.
-#define PKB_ACC_SCALE 1152921504606846976.0        // 2^60
-__device__ __forceinline__ void acc_add_fixed(double* cell, double v) {
-    const long long q = __double2ll_rn(v * PKB_ACC_SCALE);
-    atomicAdd(reinterpret_cast<unsigned long long*>(cell), (unsigned long long)q);
+// Per-period contributions are accumulated EXACTLY and order-independently: every contribution x = h[t] * cdf (a
+// double in [0, 1]) is split without error into hi = the multiple of 2^-50 nearest to x and the remainder
+// lo = x - hi (|lo| <= 2^-51, exact in fp64), and the two parts are added to two 64-bit integer planes -- hi in
+// units of 2^-50, lo in units of 2^-100 -- with integer atomics.  Integer addition is associative, so the day's
+// window is bit-identical from run to run whatever order the period CTAs retire in (fp64 atomics gave sums that
+// differed in the last bits, and with them the occasional keep/drop decision at the 1e-8 threshold), and nothing
+// above 2^-100 = 8e-31 is ever lost: the sum is the correctly rounded one to within an ulp, closer to the exact
+// value than the reference's own sequential `pmf += hprob * cdf` (ParasitoidModel.py:539).  Ranges: a cell's
+// contributions sum to <= 1 (hi plane <= 2^50), and |lo| 2^100 <= 2^49 per period leaves room for 2^13 periods.
+#define PKB_ACC_HI 1125899906842624.0                  // 2^50
+#define PKB_ACC_LO 1267650600228229401496703205376.0   // 2^100
+__device__ __forceinline__ void acc_add_exact(double* cell_hi, double* cell_lo, double v) {
+    const double h = rint(v * PKB_ACC_HI);             // |v| <= 1: exact product, integer-valued double
+    const double r = v - h * (1.0 / PKB_ACC_HI);       // exact (h / 2^50 is v rounded to a coarser grid)
+    atomicAdd(reinterpret_cast<unsigned long long*>(cell_hi), (unsigned long long)(long long)h);
+    const long long q = __double2ll_rn(r * PKB_ACC_LO);
+    if (q) atomicAdd(reinterpret_cast<unsigned long long*>(cell_lo), (unsigned long long)q);
 }
-__device__ __forceinline__ double acc_fixed_to_double(double bits) {
-    return (double)__double_as_longlong(bits) * (1.0 / PKB_ACC_SCALE);
+__device__ __forceinline__ double acc_exact_to_double(double bits_hi, double bits_lo) {
+    return (double)__double_as_longlong(bits_hi) * (1.0 / PKB_ACC_HI) + (double)__double_as_longlong(bits_lo) * (1.0 / PKB_ACC_LO);
 }
 
 struct DayParams {      // one per (proposal, day) problem
     double lam, aw, bw, a1, b1, a2, b2;   // hparams (Run.py:377)
     double mu_r;
     double cell;                          // rad_dist / rad_res
+    double sprd_factor, sdx, sdy;         // kind == 1: mixing weight and mean drift (metres) of the day-0 spread kernel
     int n_periods;
     int rad_res;
     int start_indx;                       // floor(start_time * periods), 0 if None
@@ -56,7 +64,8 @@ struct DayParams {      // one per (proposal, day) problem
     int has_next;                         // wind_day + 1 exists in the wind data
     int single;                           // 1-D wind row test form (:426-428)
     int bvn_S, bvn_Sl;                    // indices into the BvnPar array
-    int pad_;
+    int kind;                             // 0: a day's dispersal kernel (prob_mass); 1: the local day-0 spread kernel of
+                                          // Bayes_Run.py:245-270 / Bayes_MAP.py:247-277 (no wind, no threshold)
 };
 
 struct DayMeta {        // results of one (proposal, day) problem
@@ -99,6 +108,45 @@ __global__ void k_bvn_setup(BvnPar* pars, const double* __restrict__ dpar /*[n][
 }
 
 // ---------------------------------------------------------------------------
+// get_wind_data's interpolation (ParasitoidModel.py:162-227): every raw interval becomes interp_num periods,
+// linearly blended with numpy's linspace weights w1 = i * (1 / interp_num), value = (1 - w1) * a + w1 * b, and
+// windr = sqrt(wx^2 + wy^2) recomputed.  mode 0 ('00:00'): the day's last interval runs towards the next day's
+// first sample; on the final day it repeats the last raw sample, raw windr included (:196-204).  mode 1
+// ('00:30'): the day's first interval comes from the previous day's last sample; on the first day it repeats the
+// first raw sample (:206-223).  raw: [nd][npts][3], out: [nd][npts * interp_num][3].  grid = (ceil(periods/256), nd)
+__global__ void k_wind_interp(const double* __restrict__ raw, int nd, int npts, int interp_num, int mode, double* __restrict__ out) {
+    const int day = blockIdx.y;
+    const int periods = npts * interp_num;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= periods) return;
+    const int k = t / interp_num, i = t - k * interp_num;       // output interval, position inside it
+    const double step = 1.0 / (double)interp_num;
+    const double w1 = (double)i * step, w0 = 1.0 - w1;
+    const double* r = raw + (size_t)day * npts * 3;
+    const double* a;
+    const double* b;
+    bool copy_a = false;          // the interval repeats sample a
+    bool raw_r = false;           // ... including its raw windr
+    if (mode == 0) {
+        a = r + 3 * k;
+        if (k + 1 < npts) b = a + 3;
+        else if (day + 1 < nd) b = r + (size_t)npts * 3;
+        else { b = a; copy_a = true; raw_r = true; }
+    } else {
+        if (k > 0) { a = r + 3 * (k - 1); b = r + 3 * k; }
+        else if (day > 0) { a = r - 3; b = r; }
+        else { a = r; b = r; copy_a = true; }
+    }
+    double x, y;
+    if (copy_a) { x = a[0]; y = a[1]; }
+    else { x = w0 * a[0] + w1 * b[0]; y = w0 * a[1] + w1 * b[1]; }
+    double* o = out + ((size_t)day * periods + t) * 3;
+    o[0] = x;
+    o[1] = y;
+    o[2] = raw_r ? a[2] : sqrt(x * x + y * y);
+}
+
+// ---------------------------------------------------------------------------
 // h_flight_prob: grid = problems, block = 256, dyn smem = 4*periods doubles
 // f_out / g_out (optional, one problem only): f_time_prob and g_wind_prob (:231-267)
 __global__ void k_hprob(const DayParams* __restrict__ dps, const double* __restrict__ wind, int periods,
@@ -111,6 +159,7 @@ __global__ void k_hprob(const DayParams* __restrict__ dps, const double* __restr
     double* c1 = g + periods;
     double* c2 = c1 + periods;
     const DayParams dp = dps[blockIdx.x];
+    if (dp.kind) return;                          // (the spread kernel has no flight probability; hprob stays zero)
     const int n = dp.single ? 1 : periods;
     const double* w = wind + (size_t)dp.wind_day * periods * 3;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -174,6 +223,40 @@ __global__ void k_drift(const DayParams* __restrict__ dps, const BvnPar* __restr
     PKB_SHARED(double, red, 256);
     const DayParams dp = dps[blockIdx.x];
     const BvnPar& bp = bvn[dp.bvn_S];
+    if (dp.kind) {
+        // Day-0 spread kernel: integer / remainder split of the mean drift with Python's floor division and modulo
+        // (Bayes_Run.py:247-251), support of the drifted blob (get_mvn_cdf_values with mu = remainder, :252-253), and
+        // mlen//2 = max(h_long, h_short) + max(|xdrift_int|, |ydrift_int|) (:258-259) as the window extent.
+        if (threadIdx.x == 0) {
+            const double cell = dp.cell;
+            const double fx = floor(dp.sdx / cell), fy = floor(dp.sdy / cell);
+            PeriodInfo pi;
+            pi.mux = dp.sdx - fx * cell;                  // x % res  (sign of the divisor, like Python)
+            pi.muy = dp.sdy - fy * cell;
+            pi.col_c = (int)fx;                           // xdrift_int
+            pi.row_c = (int)fy;                           // ydrift_int
+            const int h0 = bp.h0;
+            int h = h0;
+            while (h > 0 && 1.0 - square_prob(bp, cell, h - 1, pi.mux, pi.muy) < PKB_CDF_EPS) --h;
+            while (!(1.0 - square_prob(bp, cell, h, pi.mux, pi.muy) < PKB_CDF_EPS) && h < 4096) ++h;
+            const double d0 = 1.0 - square_prob(bp, cell, h, pi.mux, pi.muy);
+            const double d1 = h >= 1 ? 1.0 - square_prob(bp, cell, h - 1, pi.mux, pi.muy) : 1.0;
+            int flags = 0;
+            if (fabs(d0 - PKB_CDF_EPS) < ring_tol || fabs(d1 - PKB_CDF_EPS) < ring_tol) {
+                flags = PKB_ST_BORDERLINE;
+                h = ring_halfwidth_ref_order(bp, cell, pi.mux, pi.muy, PKB_CDF_EPS, h + 1);
+            }
+            pi.h = h;
+            pi.pad_ = 0;
+            pinfo[(size_t)blockIdx.x * periods] = pi;
+            const int hl = bvn[dp.bvn_Sl].h0;
+            int ai = pi.col_c < 0 ? -pi.col_c : pi.col_c, aj = pi.row_c < 0 ? -pi.row_c : pi.row_c;
+            meta[blockIdx.x].ext = (h > hl ? h : hl) + (ai > aj ? ai : aj);
+            meta[blockIdx.x].hl = hl;
+            if (flags) atomicOr(&meta[blockIdx.x].status, flags);
+        }
+        return;
+    }
     const int P = dp.single ? 1 : periods;
     const double* w = wind + (size_t)dp.wind_day * periods * 3;
     const double* wn = w + (size_t)periods * 3;
@@ -262,8 +345,8 @@ __device__ __forceinline__ int py_slice_len(int start, int stop, int n) {
 // grid = (periods, problems), block = 64 / 128 / 256 by lattice size (pkb200.cu), dyn smem = (6*nmax + tile_cap) doubles, tile_cap = min(PKB_LATTICE_CAP, nmax^2)
 // acc: per problem (2*racc+1)^2 window centred on the release cell
 __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
-                         const double* __restrict__ hprob, int periods, int nmax, int tile_cap, double* __restrict__ acc, int racc,
-                         double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
+                         const double* __restrict__ hprob, int periods, int nmax, int tile_cap, double* __restrict__ acc,
+                         double* __restrict__ acc_lo, int racc, double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(double, red, 256);
     PKB_SHARED(double, cstep, 20);
@@ -271,7 +354,7 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
     const int t = blockIdx.x;
     const DayParams dp = dps[prob];
     const int P = dp.single ? 1 : periods;
-    if (t < dp.start_indx || t >= P) return;
+    if (dp.kind || t < dp.start_indx || t >= P) return;
     const BvnPar& bp = bvn[dp.bvn_S];
     const PeriodInfo pi = pinfo[(size_t)prob * periods + t];
     const double hp = hprob[(size_t)prob * periods + t];
@@ -328,6 +411,7 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
     const int shift = dp.rad_res - racc;                 // acc window origin in domain coords
     const int W = 2 * racc + 1;
     double* accp = acc + (size_t)prob * W * W;
+    double* accl = acc_lo + (size_t)prob * W * W;
     double inside = 0.0;
     for (int y0 = 0; y0 < nc; y0 += rows_per_tile) {
         const int ny = (nc - y0 < rows_per_tile) ? (nc - y0) : rows_per_tile;   // cell rows in this tile
@@ -388,7 +472,8 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
             const int col = pi.col_c + (ix - h);
             if (row >= 0 && row < dom && col >= 0 && col < dom) {
                 inside += v;
-                acc_add_fixed(&accp[(size_t)(row - shift) * W + (col - shift)], hp * v);   // (:539)
+                const size_t ci = (size_t)(row - shift) * W + (col - shift);
+                acc_add_exact(&accp[ci], &accl[ci], hp * v);   // (:539)
             }
         }
         __syncthreads();
@@ -405,8 +490,8 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
 // grid = problems, block = 1024.  Works in place on the accumulation window.
 // pre (optional): receives the pre-threshold window (parity export).
 __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, int periods, double* __restrict__ acc,
-                               int racc, const double* __restrict__ loss_t, DayMeta* __restrict__ meta, double negval,
-                               double* __restrict__ pre) {
+                               const double* __restrict__ acc_lo, int racc, const double* __restrict__ loss_t, DayMeta* __restrict__ meta,
+                               double negval, double* __restrict__ pre, const PeriodInfo* __restrict__ pinfo) {
     PKB_SHARED(double, red, 1024);
     PKB_SHARED(double, sh, 4);
     const int prob = blockIdx.x;
@@ -417,17 +502,69 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     double* a = acc + (size_t)prob * nel;
     const int tid = threadIdx.x, T = blockDim.x;
     int status = 0;
+    // The window is sized for the widest problem of the batch (racc); this problem's periods and its local blob only
+    // reach max(ext, hl) cells from the release cell (k_drift), the rest of its window is still the zeros of the
+    // initial memset.  All passes below walk that sub-window: element q -> (row, col) of the W x W window.
+    const int hl = bvn[dp.bvn_Sl].h0;
+    int rsub = meta[prob].ext > hl ? meta[prob].ext : hl;
+    if (rsub > racc) rsub = racc;
+    const int ns = 2 * rsub + 1, off = racc - rsub, nsub = ns * ns;
+    auto at = [&](int q) -> int {
+        const int rr = q / ns;
+        return (rr + off) * W + (q - rr * ns + off);
+    };
+    if (dp.kind) {
+        // Day-0 spread kernel (Bayes_Run.py:252-270): sprd = f * longsprd shifted by the integer drift, += (1 - f) *
+        // shrtsprd at the centre, centre += max(0, 1 - sum).  No threshold, no renormalisation; its shape is mlen.
+        const PeriodInfo pi = pinfo[(size_t)prob * periods];
+        const BvnPar& bs = bvn[dp.bvn_S];
+        const BvnPar& bl = bvn[dp.bvn_Sl];
+        const double cell = dp.cell, r = cell / 2, f = dp.sprd_factor;
+        const int h = pi.h, nc = 2 * h + 1;
+        for (int q = tid; q < nc * nc; q += T) {
+            const int iy = q / nc, ix = q - iy * nc;      // cell (x = ix - h, y = iy - h) of the drifted blob
+            const double xl = (ix - h) * cell - r, yl = (iy - h) * cell - r;
+            const double v = mvn_rect(bs, xl, xl + cell, yl, yl + cell, pi.mux, pi.muy);
+            const int row = racc - ((iy - h) + pi.row_c), col = racc + ((ix - h) + pi.col_c);
+            if (row >= 0 && row < W && col >= 0 && col < W) a[(size_t)row * W + col] = v * f;
+        }
+        __syncthreads();
+        const int ncl = 2 * hl + 1;
+        for (int q = tid; q < ncl * ncl; q += T) {
+            const int iy = q / ncl, ix = q - iy * ncl;
+            const double xl = (ix - hl) * cell - r, yl = (iy - hl) * cell - r;
+            const double v = mvn_rect(bl, xl, xl + cell, yl, yl + cell, 0.0, 0.0);
+            a[(size_t)(racc - (iy - hl)) * W + racc + (ix - hl)] += v * (1.0 - f);
+        }
+        __syncthreads();
+        double s = 0.0, kc = 0.0;
+        for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; kc += v != 0.0 ? 1.0 : 0.0; }
+        const double tot = block_sum(s, red);
+        const double cnt = block_sum(kc, red);
+        if (pre) {
+            for (int i = tid; i < nel; i += T) pre[(size_t)prob * nel + i] = a[i];
+        }
+        if (tid == 0) {
+            const double fix = 1.0 - tot > 0.0 ? 1.0 - tot : 0.0;
+            a[(size_t)racc * W + racc] += fix;
+            DayMeta& m = meta[prob];
+            m.loss = 0.0; m.pmfsum = tot; m.total = tot + fix; m.kept_sum = tot + fix; m.add = fix;
+            m.rad = rsub; m.nnz = (int)cnt;
+        }
+        return;
+    }
 
     if (tid == 0) {
         double loss = 0.0;
         for (int t = dp.start_indx; t < P; ++t) loss += loss_t[(size_t)prob * periods + t];   // same order as the loop (:546,558)
         sh[0] = loss;
     }
-    // fixed-point accumulator (acc_add_fixed) -> doubles, in place
-    for (int i = tid; i < nel; i += T) a[i] = acc_fixed_to_double(a[i]);
+    // exact two-plane accumulator (acc_add_exact) -> doubles, in place
+    const double* al = acc_lo + (size_t)prob * nel;
+    for (int q = tid; q < nsub; q += T) { const int i = at(q); a[i] = acc_exact_to_double(a[i], al[i]); }
     __syncthreads();
     double s = 0.0, mn = 0.0;
-    for (int i = tid; i < nel; i += T) { const double v = a[i]; s += v; mn = fmin(mn, v); }
+    for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
     const double pmfsum = block_sum(s, red);
     const double pmin = block_min(mn, red);
     const double loss = sh[0];
@@ -438,7 +575,6 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     if (total < 0.99999) {
         // wasps that did not fly diffuse locally around the release cell (:581-585)
         const BvnPar& bl = bvn[dp.bvn_Sl];
-        const int hl = bl.h0;
         const int ncl = 2 * hl + 1;
         const double cell = dp.cell, r = cell / 2;
         const double wgt = 1.0 - total;
@@ -451,7 +587,7 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
         }
         __syncthreads();
         s = 0.0; mn = 0.0;
-        for (int i = tid; i < nel; i += T) { const double v = a[i]; s += v; mn = fmin(mn, v); }
+        for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
         const double sum2 = block_sum(s, red);
         const double min2 = block_min(mn, red);
         if (!(min2 >= -1e-8)) status |= PKB_ST_PMF_NEG2;
@@ -459,7 +595,8 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     }
     // r_small_vals(coo(pmf), prob_model=True) (:605, CalcSol.py:112-136)
     double ks = 0.0, kc = 0.0, kr = 0.0;
-    for (int i = tid; i < nel; i += T) {
+    for (int q = tid; q < nsub; q += T) {
+        const int i = at(q);
         const double v = a[i];
         if (v != 0.0 && !(v < negval)) {
             ks += v; kc += 1.0;
@@ -473,9 +610,14 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     const double kcnt = block_sum(kc, red);
     const double krad = block_max(kr, red);
     const double add = (1.0 - ksum) / kcnt;
-    for (int i = tid; i < nel; i += T) {
+    if (pre) {      // parity export: the whole window, zeros outside the sub-window
+        for (int i = tid; i < nel; i += T) pre[(size_t)prob * nel + i] = 0.0;
+        __syncthreads();
+        for (int q = tid; q < nsub; q += T) { const int i = at(q); pre[(size_t)prob * nel + i] = a[i]; }
+    }
+    for (int q = tid; q < nsub; q += T) {
+        const int i = at(q);
         const double v = a[i];
-        if (pre) pre[(size_t)prob * nel + i] = v;
         a[i] = (v != 0.0 && !(v < negval)) ? v + add : 0.0;
     }
     if (tid == 0) {

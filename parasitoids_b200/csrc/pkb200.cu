@@ -13,6 +13,7 @@
 #include "../../include/pkb200.h"
 #include "phase1.cuh"
 #include "chain.cuh"
+#include "project.cuh"
 
 #include <algorithm>
 #include <array>
@@ -104,6 +105,7 @@ struct pkb_ctx {
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
     double ring_tol;        // ring-growth decisions closer than this to cdf_eps are re-taken in the reference's summation order (option "ring_tol")
+    int spec_min_reach;     // ... armed only if the exact support stays inside the domain for this many steps (option "spectral_min_reach")
     int use_spectral;       // fused solve: spectral-resident steps while nothing of consequence lies outside the domain (option "spectral")
     int emit_ctas;          // fused solve: side-stream emission as this many persistent 64-thread CTAs (option "emit_ctas"; 0, the
                             // default: one 256-thread CTA per row -- the small persistent CTAs measured slower)
@@ -336,6 +338,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_step_torus = 1;
     ctx->use_trunc_torus = 1;
     ctx->use_spectral = 1;
+    ctx->spec_min_reach = 4;
     ctx->ring_tol = 1e-12;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
@@ -445,6 +448,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "ring_tol")) {
         if (!(value >= 0)) return fail(PKB_EINVAL, "ring_tol must be >= 0");
         ctx->ring_tol = value;
+        return 0;
+    }
+    if (!strcmp(key, "spectral_min_reach")) {
+        ctx->spec_min_reach = (int)value;
         return 0;
     }
     if (!strcmp(key, "spectral")) {
@@ -795,7 +802,7 @@ struct pkb_kset {
     pkb_ctx* ctx;
     int nprob, periods, racc, W, rad_res;
     bool keep_pre;
-    DBuf<double> acc, pre, hprob, loss_t;
+    DBuf<double> acc, acc_lo, pre, hprob, loss_t;      // acc_lo: low plane of the exact accumulator (phase1.cuh, acc_add_exact)
     DBuf<PeriodInfo> pinfo;
     DBuf<DayMeta> dmeta;
     DBuf<DayParams> ddp;
@@ -834,8 +841,10 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
         const pkb_day_args& a = args[i];
         if (a.rad_res != ks->rad_res) return fail(PKB_EINVAL, "pkb_kernels_build: all problems must share rad_res");
         if (a.rad_res < 1 || !(a.rad_dist > 0)) return fail(PKB_EINVAL, "pkb_kernels_build: bad domain (rad_dist %g, rad_res %d)", a.rad_dist, a.rad_res);
-        if (a.n_periods < 1) return fail(PKB_EINVAL, "pkb_kernels_build: n_periods must be >= 1");
-        if (a.wind_day < 0 || a.wind_day >= nd_wind) return fail(PKB_EINVAL, "pkb_kernels_build: wind_day %d out of range", a.wind_day);
+        if (a.kind != 0 && a.kind != 1) return fail(PKB_EINVAL, "pkb_kernels_build: kind must be 0 (day) or 1 (spread kernel)");
+        if (!a.kind && a.n_periods < 1) return fail(PKB_EINVAL, "pkb_kernels_build: n_periods must be >= 1");
+        if (!a.kind && (a.wind_day < 0 || a.wind_day >= nd_wind)) return fail(PKB_EINVAL, "pkb_kernels_build: wind_day %d out of range", a.wind_day);
+        if (a.kind && !(a.sprd_factor >= 0 && a.sprd_factor <= 1)) return fail(PKB_EINVAL, "pkb_kernels_build: sprd_factor must be in [0, 1]");
         TRY(check_dparams(a.dparams, "Dparams"));
         TRY(check_dparams(a.dlparams, "Dlparams"));
         DayParams& d = hdp[i];
@@ -856,7 +865,11 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
         d.has_next = (a.wind_day + 1 < nd_wind) ? 1 : 0;
         d.bvn_S = 2 * i;
         d.bvn_Sl = 2 * i + 1;
-        d.pad_ = 0;
+        d.kind = a.kind;
+        d.sprd_factor = a.sprd_factor;
+        d.sdx = a.sprd_drift[0];
+        d.sdy = a.sprd_drift[1];
+        if (a.kind) { d.n_periods = 1; d.wind_day = 0; d.has_next = 0; d.single = 0; d.start_indx = 0; }
         for (int k = 0; k < 3; ++k) { dpar[6 * i + k] = a.dparams[k]; dpar[6 * i + 3 + k] = a.dlparams[k]; }
         cells[2 * i] = cells[2 * i + 1] = d.cell;
     }
@@ -901,7 +914,9 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
     ks->W = 2 * racc + 1;
     const size_t nel = (size_t)ks->W * ks->W;
     TRY(ks->acc.alloc(ctx, nel * nprob));
+    TRY(ks->acc_lo.alloc(ctx, nel * nprob));
     CU(cudaMemsetAsync(ks->acc.p, 0, sizeof(double) * nel * nprob, ctx->stream));
+    CU(cudaMemsetAsync(ks->acc_lo.p, 0, sizeof(double) * nel * nprob, ctx->stream));
     if (keep_pre) TRY(ks->pre.alloc(ctx, nel * nprob));
 
     // lattice tile: the whole (nmax x nmax) corner lattice when it fits, so that small supports leave room for more CTAs per SM
@@ -911,10 +926,10 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
     // small supports get small CTAs and more of them per SM (C4, 48 x 48 lattice: 256 threads 1.83 ms, 64 threads 1.23 ms)
     const int lattice_items = nmax * ((nmax + PKB_BVN_SEG - 1) / PKB_BVN_SEG);
     const int period_threads = lattice_items <= 256 ? 64 : (lattice_items <= 1024 ? 128 : 256);
-    LAUNCH(ctx, k_period, dim3(periods, nprob), period_threads, smem, ks->ddp.p, ks->bvn.p, ks->pinfo.p, ks->hprob.p, periods, nmax, tile_cap, ks->acc.p, racc,
-           ks->loss_t.p, ks->dmeta.p);
-    LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ks->ddp.p, ks->bvn.p, periods, ks->acc.p, racc, ks->loss_t.p, ks->dmeta.p, 1e-8,
-           keep_pre ? ks->pre.p : (double*)nullptr);
+    LAUNCH(ctx, k_period, dim3(periods, nprob), period_threads, smem, ks->ddp.p, ks->bvn.p, ks->pinfo.p, ks->hprob.p, periods, nmax, tile_cap, ks->acc.p, ks->acc_lo.p,
+           racc, ks->loss_t.p, ks->dmeta.p);
+    LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ks->ddp.p, ks->bvn.p, periods, ks->acc.p, (const double*)ks->acc_lo.p, racc, ks->loss_t.p, ks->dmeta.p, 1e-8,
+           keep_pre ? ks->pre.p : (double*)nullptr, (const PeriodInfo*)ks->pinfo.p);
     CU(cudaMemcpyAsync(ks->hmeta.data(), ks->dmeta.p, sizeof(DayMeta) * nprob, cudaMemcpyDeviceToHost, ctx->stream));
     TRY(sync_check(ctx, "phase 1"));
     guard.k = nullptr;
@@ -996,6 +1011,21 @@ extern "C" int pkb_kset_destroy(pkb_kset* ks) {
     cudaStreamSynchronize(ks->ctx->stream);
     delete ks;
     return 0;
+}
+
+extern "C" int pkb_wind_interp(pkb_ctx* ctx, const double* raw, int nd, int npts, int interp_num, int half_hour_start, double* out) {
+    if (!ctx || !raw || !out) return fail(PKB_EINVAL, "pkb_wind_interp: NULL argument");
+    if (nd < 1 || npts < 1 || interp_num < 1) return fail(PKB_EINVAL, "pkb_wind_interp: bad sizes");
+    CU(cudaSetDevice(ctx->device));
+    DBuf<double> din, dout;
+    const size_t nin = (size_t)nd * npts * 3, nout = nin * interp_num;
+    TRY(din.alloc(ctx, nin));
+    TRY(dout.alloc(ctx, nout));
+    CU(cudaMemcpyAsync(din.p, raw, nin * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int periods = npts * interp_num;
+    LAUNCH(ctx, k_wind_interp, dim3((periods + 255) / 256, nd), 256, 0, (const double*)din.p, nd, npts, interp_num, half_hour_start ? 1 : 0, dout.p);
+    CU(cudaMemcpyAsync(out, dout.p, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_wind_interp");
 }
 
 // h_flight_prob alone: a one-problem hprob launch
@@ -1645,21 +1675,37 @@ static int coo_collect(pkb_ctx* ctx, pkb_result* r) {
 
 static int check_solve_args(const pkb_solve_args* a) {
     if (a->ndays < 1 || a->ndays > a->nd_wind) return fail(PKB_EINVAL, "pkb_solve: ndays %d must be in [1, %d]", a->ndays, a->nd_wind);
+    if (a->sprd && !(a->sprd_factor >= 0 && a->sprd_factor <= 1)) return fail(PKB_EINVAL, "pkb_solve: sprd_factor must be in [0, 1]");
     if (!a->prob_model) {
-        if (a->r_dur < 1 || a->r_dur > a->ndays) return fail(PKB_EINVAL, "pkb_solve: r_dur %d must be in [1, ndays]", a->r_dur);
+        if (a->r_dur < 1 || a->r_dur > a->ndays + (a->sprd ? 1 : 0)) return fail(PKB_EINVAL, "pkb_solve: r_dur %d must be in [1, ndays]", a->r_dur);
         if (a->r_dur > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "pkb_solve: r_dur is limited to %d days", PKB_MAX_COHORTS);
         if (!a->r_dist) return fail(PKB_EINVAL, "pkb_solve: r_dist is NULL");
     }
     return 0;
 }
 
-// per-day prob_mass arguments of one solve (Run.py:412-425)
+// per-day prob_mass arguments of one solve (Run.py:412-425); with a->sprd the day-0 spread kernel of
+// Bayes_Run.py:245-270 comes first: ndays + 1 problems
+static int solve_nkernels(const pkb_solve_args* a) { return a->ndays + (a->sprd ? 1 : 0); }
 static void solve_day_args(const pkb_solve_args* a, pkb_day_args* dargs) {
+    const int lead = a->sprd ? 1 : 0;
+    if (lead) {
+        dargs[0] = a->day;
+        dargs[0].kind = 1;
+        dargs[0].wind_day = 0;
+        dargs[0].single = 0;
+        dargs[0].start_time = -1.0;
+        dargs[0].sprd_factor = a->sprd_factor;
+        dargs[0].sprd_drift[0] = a->sprd_drift[0];
+        dargs[0].sprd_drift[1] = a->sprd_drift[1];
+    }
     for (int i = 0; i < a->ndays; ++i) {
-        dargs[i] = a->day;
-        dargs[i].wind_day = i;
-        dargs[i].single = 0;
-        dargs[i].start_time = (!a->prob_model && i == 0 && a->r_start >= 0) ? a->r_start : -1.0;   // Run.py:418-421
+        pkb_day_args& d = dargs[lead + i];
+        d = a->day;
+        d.kind = 0;
+        d.wind_day = i;
+        d.single = 0;
+        d.start_time = (!a->prob_model && i == 0 && a->r_start >= 0) ? a->r_start : -1.0;   // Run.py:418-421
     }
 }
 
@@ -1673,7 +1719,10 @@ struct SampleSink {
     double* out;            // device [nd][K]
 };
 static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int k0, pkb_result** out, const SampleSink* sink = nullptr) {
-    const int nd = a->ndays;
+    // chain days: with a->sprd the spread kernel is day 0 of the chain and its output is dropped (Bayes_Run.py:288-296);
+    // output day o is chain day o + lead
+    const int lead = a->sprd ? 1 : 0;
+    const int nd = a->ndays + lead, nout = a->ndays;
     if (sink && a->want_coo) return fail(PKB_EINVAL, "sample-cell emission excludes COO output");
     const int sgrid = sink ? (sink->K + 255) / 256 : 0;
     const double negval = a->negval > 0 ? a->negval : 1e-8;
@@ -1689,13 +1738,13 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         ~RGuard() { delete r; }
     } rguard{res};
     res->ctx = ctx;
-    res->ndays = nd;
+    res->ndays = nout;
     res->D = D;
     res->max_shape = 2 * mmax + 1;
     res->have_coo = false;
     res->window_steps = 0;
-    res->kmeta.assign(ks->hmeta.begin() + k0, ks->hmeta.begin() + k0 + nd);
-    res->smeta.assign(nd, StepMeta());
+    res->kmeta.assign(ks->hmeta.begin() + k0 + lead, ks->hmeta.begin() + k0 + nd);
+    res->smeta.assign(nout, StepMeta());
     for (auto& sm : res->smeta) memset(&sm, 0, sizeof sm);
 
     // ---- phase 2 -----------------------------------------------------------
@@ -1707,27 +1756,42 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     } cguard{ch};
     ch->negval = negval;
     // spectral-resident steps on the main chain (probability model, or a one-day release: no cohorts to back-solve)
-    const bool spec_try = ctx->use_spectral && (a->prob_model || a->r_dur == 1);
+    // Spectral-resident steps on the main chain (probability model, or a one-day release: no cohorts to back-solve).
+    // They need ONE torus for every whole-torus step, which gives up the per-step torus, so they are only armed for
+    // solves that look like the in-domain regime: the exact support (first kernel, grown by every later radius) stays
+    // inside the domain for at least PKB_SPEC_MIN_REACH steps.  (A performance heuristic only: the device-side
+    // criterion of chain.cuh decides whether any step actually goes spectral.)
+    int reach = 0;
+    {
+        int lo = D / 2 - ks->hmeta[k0].rad, hi = D / 2 + ks->hmeta[k0].rad;
+        for (int n = (a->prob_model ? 1 : a->r_dur); n < nd; ++n, ++reach) {
+            lo -= ks->hmeta[k0 + n].rad;
+            hi += ks->hmeta[k0 + n].rad;
+            if (lo < 0 || hi >= D) break;
+        }
+    }
+    const bool spec_try = ctx->use_spectral && (a->prob_model || a->r_dur == 1) && reach >= ctx->spec_min_reach;
     ch->fixed_torus = spec_try;
     const ChainDims d = ch->d;
     res->P = d.P;
     res->N = d.N;
     const size_t nD = (size_t)D * D, nW = (size_t)ks->W * ks->W;
-    if (!sink) TRY(res->dense.alloc(ctx, nD * nd));
-    if (!sink && a->keep_pre_device) TRY(res->pre.alloc(ctx, nD * nd));      // parity export (pkb_result_pre)
-    res->counted.assign(nd, 0);
+    if (!sink) TRY(res->dense.alloc(ctx, nD * nout));
+    if (!sink && a->keep_pre_device) TRY(res->pre.alloc(ctx, nD * nout));      // parity export (pkb_result_pre)
+    res->counted.assign(nout, 0);
     if (a->want_coo) {
-        TRY(res->rownnz.alloc(ctx, (size_t)nd * D));
-        TRY(res->rowoff.alloc(ctx, (size_t)nd * D));
-        TRY(res->daytot.alloc(ctx, 2 * (size_t)nd));
-        TRY(res->tot_host.alloc(ctx, 2 * (size_t)nd));
-        while ((int)ctx->day_events.size() < nd) {
+        TRY(res->rownnz.alloc(ctx, (size_t)nout * D));
+        TRY(res->rowoff.alloc(ctx, (size_t)nout * D));
+        TRY(res->daytot.alloc(ctx, 2 * (size_t)nout));
+        TRY(res->tot_host.alloc(ctx, 2 * (size_t)nout));
+        while ((int)ctx->day_events.size() < nout) {
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->day_events.push_back(e);
         }
     }
-    auto emitted = [&](int day, cudaStream_t strm) -> int { return a->want_coo ? coo_day_ready(ctx, res, day, strm) : 0; };
+    // (day: chain day; nothing is emitted for the dropped leading day)
+    auto emitted = [&](int day, cudaStream_t strm) -> int { return a->want_coo && day >= lead ? coo_day_ready(ctx, res, day - lead, strm) : 0; };
     DBuf<StepMeta> dsm, dcm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
@@ -1930,10 +1994,12 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     if (a->prob_model) {
         // modelsol[0] = first kernel re-centred on the domain (Run.py:454-458)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
-        if (sink) LAUNCH(ctx, k_copy_domain_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, sink->cells, sink->K, sink->out);
-        else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
-        if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p);
-        TRY(emitted(0, ctx->stream));
+        if (!lead) {
+            if (sink) LAUNCH(ctx, k_copy_domain_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, sink->cells, sink->K, sink->out);
+            else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
+            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p);
+            TRY(emitted(0, ctx->stream));
+        }
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
             const int* wp = step_window(n);
             cplx* krt = nullptr;
@@ -1947,18 +2013,18 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * n);
+            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * (n - lead));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
             if (sink)
                 LAUNCH_ON(ctx, ctx->aux, k_emit_dense_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval,
-                          1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * n);
+                          1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * (n - lead));
             else
                 LAUNCH_ON(ctx, ctx->aux, k_emit_dense, ctx->emit_ctas > 0 ? std::min(D, ctx->emit_ctas) : D, ctx->emit_ctas > 0 ? 64 : PKB_EMIT_T, 0,
                           (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
-                          res->dense.p + nD * n, a->want_coo ? res->rownnz.p + (size_t)D * n : (int*)nullptr);
-            if (a->want_coo) res->counted[n] = 1;
+                          res->dense.p + nD * (n - lead), a->want_coo ? res->rownnz.p + (size_t)D * (n - lead) : (int*)nullptr);
+            if (a->want_coo) res->counted[n - lead] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
             TRY(emitted(n, ctx->aux));
         }
@@ -1992,7 +2058,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         // day 0 (CalcSol.py:236-237)
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         ca.n = 1; ca.S[0] = ch->S[ch->cur].p; ca.w[0] = a->r_dist[0];
-        auto emit_pop = [&](int day, double centre_extra, int add_centre, int first_day) -> int {
+        auto emit_pop = [&](int cday, double centre_extra, int add_centre, int first_day) -> int {
+            const int day = cday - lead;
+            if (day < 0) return 0;               // the leading spread day is not part of the output
             if (sink)
                 LAUNCH(ctx, k_emit_population_cells, sgrid, 256, 0, ca, d, rn, centre_extra, add_centre, negval, first_day, sink->cells, sink->K,
                        sink->out + (size_t)sink->K * day);
@@ -2056,10 +2124,11 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     // ---- outputs (the chain is enqueued, not finished: compaction and D2H overlap it) ----
     if (a->want_coo) TRY(coo_collect(ctx, res));
     // (pageable destination: this copy blocks the host until the chain has finished, so it comes last)
-    CU(cudaMemcpyAsync(res->smeta.data(), dsm.p, sizeof(StepMeta) * nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(res->smeta.data(), dsm.p + lead, sizeof(StepMeta) * nout, cudaMemcpyDeviceToHost, ctx->stream));
     if (want_cmeta) {
-        res->cmeta.resize((size_t)nd * PKB_MAX_COHORTS);
-        CU(cudaMemcpyAsync(res->cmeta.data(), dcm.p, sizeof(StepMeta) * nd * PKB_MAX_COHORTS, cudaMemcpyDeviceToHost, ctx->stream));
+        res->cmeta.resize((size_t)nout * PKB_MAX_COHORTS);
+        CU(cudaMemcpyAsync(res->cmeta.data(), dcm.p + (size_t)lead * PKB_MAX_COHORTS, sizeof(StepMeta) * nout * PKB_MAX_COHORTS, cudaMemcpyDeviceToHost,
+                           ctx->stream));
     }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     TRY(sync_check(ctx, "pkb_solve outputs"));
@@ -2079,7 +2148,6 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
     *out = nullptr;
     TRY(check_solve_args(a));
     CU(cudaSetDevice(ctx->device));
-    const int nd = a->ndays;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 
     // ---- phase 1 (Run.py:412-425) ------------------------------------------
@@ -2091,15 +2159,78 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
         CU(cudaMemcpyAsync(dwind.p, a->wind, nw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         wind_dev = dwind.p;
     }
-    std::vector<pkb_day_args> dargs(nd);
+    std::vector<pkb_day_args> dargs(solve_nkernels(a));
     solve_day_args(a, dargs.data());
     pkb_kset* ks = nullptr;
-    TRY(kernels_build_dev(ctx, wind_dev, a->nd_wind, a->periods, dargs.data(), nd, 0, &ks));
+    TRY(kernels_build_dev(ctx, wind_dev, a->nd_wind, a->periods, dargs.data(), (int)dargs.size(), 0, &ks));
     struct KGuard {
         pkb_kset* k;
         ~KGuard() { delete k; }
     } kguard{ks};
     return solve_chain(ctx, a, ks, 0, out);
+}
+
+// ---- likelihood projection (Bayes_funcs.py) -----------------------------------------------------------------
+struct DevProjection {
+    DBuf<int> set_ptr, set_cells, row_ptr, grp_ptr, term_day, term_set;
+    DBuf<double> term_w;
+    ProjTables t;
+};
+static int upload_projection(pkb_ctx* ctx, const pkb_projection* p, int ndays, int K, DevProjection* d) {
+    if (!p || !p->set_ptr || !p->row_ptr || !p->grp_ptr) return fail(PKB_EINVAL, "projection: NULL table");
+    if (p->nsets < 0 || p->nrows < 1 || p->ngroups < 0) return fail(PKB_EINVAL, "projection: bad sizes");
+    const int ncell = p->set_ptr[p->nsets], nterm = p->grp_ptr[p->ngroups];
+    if (p->row_ptr[p->nrows] != p->ngroups) return fail(PKB_EINVAL, "projection: row_ptr does not cover the groups");
+    if ((ncell > 0 && !p->set_cells) || (nterm > 0 && (!p->term_day || !p->term_set || !p->term_w))) return fail(PKB_EINVAL, "projection: NULL table");
+    for (int i = 0; i < p->nsets; ++i)
+        if (p->set_ptr[i + 1] < p->set_ptr[i]) return fail(PKB_EINVAL, "projection: set_ptr is not monotone");
+    for (int i = 0; i < ncell; ++i)
+        if (p->set_cells[i] < 0 || p->set_cells[i] >= K) return fail(PKB_EINVAL, "projection: sample-cell index %d out of range", p->set_cells[i]);
+    for (int i = 0; i < p->nrows; ++i)
+        if (p->row_ptr[i + 1] < p->row_ptr[i]) return fail(PKB_EINVAL, "projection: row_ptr is not monotone");
+    for (int i = 0; i < p->ngroups; ++i)
+        if (p->grp_ptr[i + 1] < p->grp_ptr[i]) return fail(PKB_EINVAL, "projection: grp_ptr is not monotone");
+    for (int i = 0; i < nterm; ++i) {
+        if (p->term_day[i] < 0 || p->term_day[i] >= ndays) return fail(PKB_EINVAL, "projection: model day %d out of range [0, %d)", p->term_day[i], ndays);
+        if (p->term_set[i] < 0 || p->term_set[i] >= p->nsets) return fail(PKB_EINVAL, "projection: set index %d out of range", p->term_set[i]);
+    }
+    auto up_i = [&](DBuf<int>& b, const int* src, size_t n) -> int {
+        TRY(b.alloc(ctx, n));
+        if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    };
+    TRY(up_i(d->set_ptr, p->set_ptr, (size_t)p->nsets + 1));
+    TRY(up_i(d->set_cells, p->set_cells, ncell));
+    TRY(up_i(d->row_ptr, p->row_ptr, (size_t)p->nrows + 1));
+    TRY(up_i(d->grp_ptr, p->grp_ptr, (size_t)p->ngroups + 1));
+    TRY(up_i(d->term_day, p->term_day, nterm));
+    TRY(up_i(d->term_set, p->term_set, nterm));
+    TRY(d->term_w.alloc(ctx, nterm));
+    if (nterm) CU(cudaMemcpyAsync(d->term_w.p, p->term_w, (size_t)nterm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));      // the caller's (pageable) tables may go away after this call
+    d->t.set_ptr = d->set_ptr.p; d->t.set_cells = d->set_cells.p; d->t.row_ptr = d->row_ptr.p; d->t.grp_ptr = d->grp_ptr.p;
+    d->t.term_day = d->term_day.p; d->t.term_set = d->term_set.p; d->t.term_w = d->term_w.p; d->t.nrows = p->nrows;
+    return 0;
+}
+static void launch_project(pkb_ctx* ctx, const DevProjection& d, const double* samples, int nd, int K, int nprop, double* out) {
+    const long long n = (long long)nprop * d.t.nrows;
+    LAUNCH(ctx, k_project, (unsigned)((n + 127) / 128), 128, 0, d.t, samples, nd, K, nprop, out);
+}
+
+extern "C" int pkb_project(pkb_ctx* ctx, const pkb_projection* proj, const double* samples, int nprop, int ndays, int K, double* out) {
+    if (!ctx || !proj || !samples || !out) return fail(PKB_EINVAL, "pkb_project: NULL argument");
+    if (nprop < 1 || ndays < 1 || K < 1) return fail(PKB_EINVAL, "pkb_project: bad sizes");
+    CU(cudaSetDevice(ctx->device));
+    DevProjection dp;
+    TRY(upload_projection(ctx, proj, ndays, K, &dp));
+    DBuf<double> ds, dout;
+    const size_t ns = (size_t)nprop * ndays * K, no = (size_t)nprop * proj->nrows;
+    TRY(ds.alloc(ctx, ns));
+    TRY(dout.alloc(ctx, no));
+    CU(cudaMemcpyAsync(ds.p, samples, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_project(ctx, dp, ds.p, ndays, K, nprop, dout.p);
+    CU(cudaMemcpyAsync(out, dout.p, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_project");
 }
 
 // Likelihood batch: `nprop` independent proposals of the same solve (shared wind, domain and release
@@ -2111,8 +2242,8 @@ extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out
 // last wave leaves most SMs idle, and a second chain in flight fills those tails.  Every chain emits
 // only the K sample cells (SampleSink); the host synchronises once per group.
 #define PKB_BATCH_GROUP 32
-extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells, int K,
-                               double* out, int* status) {
+static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells, int K,
+                            const pkb_projection* proj, double* out, int* status) {
     if (!ctx || !base || !base->wind || !proposals || !cells || !out) return fail(PKB_EINVAL, "pkb_solve_batch: NULL argument");
     if (nprop < 0 || K < 1) return fail(PKB_EINVAL, "pkb_solve_batch: bad sizes");
     TRY(check_solve_args(base));
@@ -2132,6 +2263,10 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
     DBuf<int> dcells;
     TRY(dcells.alloc(ctx, 2 * (size_t)K));
     CU(cudaMemcpyAsync(dcells.p, cells, sizeof(int) * 2 * K, cudaMemcpyHostToDevice, ctx->stream));
+    // optional likelihood projection of every proposal's samples, on the device (Bayes_funcs.py)
+    DevProjection dproj;
+    DBuf<double> dprojout;
+    if (proj) TRY(upload_projection(ctx, proj, nd, K, &dproj));
     // lanes: child contexts on the same device, created on first use and kept
     const int nlanes = std::max(1, std::min(ctx->batch_lanes, nprop));
     while ((int)ctx->lanes.size() < nlanes) {
@@ -2148,6 +2283,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         lane->use_step_torus = ctx->use_step_torus;
         lane->use_trunc_torus = ctx->use_trunc_torus;
         lane->use_spectral = ctx->use_spectral;
+        lane->spec_min_reach = ctx->spec_min_reach;
         lane->ring_tol = ctx->ring_tol;
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
@@ -2182,7 +2318,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         return rc;
     };
     // bound the group so that the accumulation windows (worst case the whole domain per problem) stay below ~8 GB
-    int group = (int)std::max<size_t>(1, std::min<size_t>(ctx->batch_group, ((size_t)8 << 30) / (dom * dom * sizeof(double) * nd)));
+    int group = (int)std::max<size_t>(1, std::min<size_t>(ctx->batch_group, ((size_t)8 << 30) / (2 * dom * dom * sizeof(double) * (nd + 1))));
     // Groups are pipelined: the kernels of group g+1 are built on the parent's stream (and its small
     // sizing D2H waited for) while the lanes still run the chains of group g; only then are the lanes
     // drained and group g's samples copied out.  Two kernel sets and two output buffers are alive at a time.
@@ -2190,6 +2326,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
     const size_t out_group = (size_t)std::min(group, std::max(nprop, 1)) * nd * K;
     TRY(dout[0].alloc(ctx, out_group));
     if (nprop > group) TRY(dout[1].alloc(ctx, out_group));
+    if (proj) TRY(dprojout.alloc(ctx, (size_t)std::min(group, std::max(nprop, 1)) * proj->nrows));
     struct Pending {
         pkb_kset* ks = nullptr;
         int p0 = 0, np = 0, buf = 0;
@@ -2202,7 +2339,13 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         int rc = drain();
         if (pend.rc) rc = pend.rc;
         if (!rc) {
-            cudaError_t e = cudaMemcpyAsync(out + (size_t)pend.p0 * nd * K, dout[pend.buf].p, sizeof(double) * pend.np * nd * K,
+            cudaError_t e;
+            if (proj) {
+                launch_project(ctx, dproj, dout[pend.buf].p, nd, K, pend.np, dprojout.p);
+                e = cudaMemcpyAsync(out + (size_t)pend.p0 * proj->nrows, dprojout.p, sizeof(double) * pend.np * proj->nrows, cudaMemcpyDeviceToHost,
+                                    ctx->stream);
+            } else
+                e = cudaMemcpyAsync(out + (size_t)pend.p0 * nd * K, dout[pend.buf].p, sizeof(double) * pend.np * nd * K,
                                             cudaMemcpyDeviceToHost, ctx->stream);
             if (e != cudaSuccess) rc = fail(PKB_ECUDA, "pkb_solve_batch: output copy failed: %s", cudaGetErrorString(e));
             else rc = sync_check(ctx, "pkb_solve_batch outputs");
@@ -2215,7 +2358,8 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
     for (int p0 = 0; p0 < nprop; p0 += group, ++gi) {
         const int np = std::min(group, nprop - p0);
         std::vector<pkb_solve_args> sa(np, *base);
-        std::vector<pkb_day_args> dargs((size_t)np * nd);
+        const int nk = solve_nkernels(base), lead = nk - nd;      // kernels per proposal (leading spread kernel, Bayes_Run.py:245-270)
+        std::vector<pkb_day_args> dargs((size_t)np * nk);
         for (int p = 0; p < np; ++p) {
             const double* q = proposals + 15 * (size_t)(p0 + p);      // g_aw g_bw f_a1 f_b1 f_a2 f_b2 sig_x sig_y corr sig_xl sig_yl corr_l lam n_periods mu_r
             pkb_solve_args& s = sa[p];
@@ -2226,12 +2370,16 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
             for (int j = 0; j < 3; ++j) { s.day.dparams[j] = q[6 + j]; s.day.dlparams[j] = q[9 + j]; }
             s.day.n_periods = (int)llround(q[13]);
             s.day.mu_r = q[14];
+            if (base->sprd && base->sprd_factors) {
+                s.sprd_factor = base->sprd_factors[p0 + p];
+                if (!(s.sprd_factor >= 0 && s.sprd_factor <= 1)) return fail(PKB_EINVAL, "pkb_solve_batch: sprd_factor of proposal %d outside [0, 1]", p0 + p);
+            }
             s.want_coo = 0; s.want_dense_host = 0; s.keep_dense_device = 0;
-            solve_day_args(&s, dargs.data() + (size_t)p * nd);
+            solve_day_args(&s, dargs.data() + (size_t)p * nk);
         }
         cudaEventRecord(ctx->ev[0], ctx->stream);
         pkb_kset* ks = nullptr;
-        const int rcb = kernels_build_dev(ctx, wind_dev, base->nd_wind, base->periods, dargs.data(), np * nd, 0, &ks);
+        const int rcb = kernels_build_dev(ctx, wind_dev, base->nd_wind, base->periods, dargs.data(), np * nk, 0, &ks);
         if (rcb) {
             const std::string msg = g_err;      // (finish() may overwrite the message)
             finish();
@@ -2239,7 +2387,8 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
             return rcb;
         }
         if (status)
-            for (int i = 0; i < np * nd; ++i) status[(size_t)p0 * nd + i] = ks->hmeta[i].status;
+            for (int p = 0; p < np; ++p)
+                for (int i = 0; i < nd; ++i) status[(size_t)(p0 + p) * nd + i] = ks->hmeta[(size_t)p * nk + lead + i].status;
         cudaEventRecord(ctx->ev[1], ctx->stream);
         const int rcf = finish();              // the previous group (its chains overlapped the kernel construction above)
         if (rcf) { delete ks; return rcf; }
@@ -2249,7 +2398,7 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         pend.ks = ks; pend.p0 = p0; pend.np = np; pend.buf = gi & 1; pend.live = true;
         for (int p = 0; p < np && !pend.rc; ++p) {
             SampleSink sink = {dcells.p, K, dout[pend.buf].p + (size_t)p * nd * K};
-            pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nd, nullptr, &sink);
+            pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nk, nullptr, &sink);
         }
         if (pend.rc) {
             const std::string msg = g_err;
@@ -2260,6 +2409,17 @@ extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const d
         }
     }
     return finish();
+}
+
+extern "C" int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells, int K,
+                               double* out, int* status) {
+    return solve_batch_impl(ctx, base, proposals, nprop, cells, K, nullptr, out, status);
+}
+
+extern "C" int pkb_solve_batch_projected(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells,
+                                         int K, const pkb_projection* proj, double* out, int* status) {
+    if (!proj) return fail(PKB_EINVAL, "pkb_solve_batch_projected: NULL projection");
+    return solve_batch_impl(ctx, base, proposals, nprop, cells, K, proj, out, status);
 }
 
 extern "C" int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape) {
@@ -2338,6 +2498,27 @@ extern "C" int pkb_result_sample(pkb_result* r, const int* cells, int K, double*
     LAUNCH(ctx, k_sample, r->ndays, 256, 0, (const double*)r->dense.p, r->D, (const int*)dc.p, K, dv.p);
     CU(cudaMemcpyAsync(out, dv.p, sizeof(double) * K * r->ndays, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx, "pkb_result_sample");
+}
+
+extern "C" int pkb_result_project(pkb_result* r, const int* cells, int K, const pkb_projection* proj, double* out) {
+    if (!r || !cells || !proj || !out || K < 1) return fail(PKB_EINVAL, "pkb_result_project: bad argument");
+    if (!r->dense.p) return fail(PKB_ESTATE, "pkb_result_project: dense solutions were not kept");
+    pkb_ctx* ctx = r->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2 * K; ++k)
+        if (cells[k] < 0 || cells[k] >= r->D) return fail(PKB_EINVAL, "pkb_result_project: cell index %d outside the domain", cells[k]);
+    DevProjection dp;
+    TRY(upload_projection(ctx, proj, r->ndays, K, &dp));
+    DBuf<int> dc;
+    DBuf<double> dv, dout;
+    TRY(dc.alloc(ctx, 2 * (size_t)K));
+    TRY(dv.alloc(ctx, (size_t)K * r->ndays));
+    TRY(dout.alloc(ctx, proj->nrows));
+    CU(cudaMemcpyAsync(dc.p, cells, sizeof(int) * 2 * K, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_sample, r->ndays, 256, 0, (const double*)r->dense.p, r->D, (const int*)dc.p, K, dv.p);
+    launch_project(ctx, dp, dv.p, r->ndays, K, 1, dout.p);
+    CU(cudaMemcpyAsync(out, dout.p, sizeof(double) * proj->nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx, "pkb_result_project");
 }
 
 extern "C" int pkb_result_device_ptr(pkb_result* r, void** dptr) {

@@ -56,10 +56,20 @@ def test_hprob_golden():
     assert np.abs(PO.h_flight_prob(z['carn1_wind'], 1., 1.8, 6, 7., 2., 19., 2.) - z['carn1_h']).max() < 1e-18
 
 
+def test_wind_interpolation_golden(tmp_path):
+    """get_wind_data restated (ParasitoidModel.py:136-227) against the reference's interpolated series."""
+    z = H.load('wind')
+    for site, start in H.SITES.items():
+        wind, days = PO.get_wind_data(H.write_wind_file(tmp_path, site), 30, start)
+        assert list(days) == list(z[site + '_days'])
+        assert np.array_equal(wind[days[0]], z[site + '_i30_first'])
+        assert np.array_equal(wind[days[-1]], z[site + '_i30_last'])
+        assert np.array_equal(wind[days[len(days) // 2]], z[site + '_i30_mid'])
+
+
 def _small_wind(tmp_path):
-    from parasitoids_b200 import ParasitoidModel as PM     # host-side reader only
     z = H.load('pm_small')
-    wind, days = PM.get_wind_data(H.write_wind_file(tmp_path, 'kalbar'), int(z['interp']), '00:00')
+    wind, days = PO.get_wind_data(H.write_wind_file(tmp_path, 'kalbar'), int(z['interp']), '00:00')
     return z, wind, days
 
 
