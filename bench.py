@@ -486,6 +486,70 @@ def run_extras(args, ctx, torch, dist, rank, world, local, main_model, main_wind
     return extra
 
 
+def run_single_solve(args, ctx, torch, dist, rank, world, local, wind, ndays, rad_dist, rad_res):
+    """--single-solve: one forward solve over all ranks; value = days of that ONE solve per second (strong scaling)."""
+    from parasitoids_b200 import multi
+    model = (HPARAMS, DPARAMS, DLPARAMS, MU_R, N_PERIODS, rad_dist, rad_res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one():
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return multi.solve_single(wind, ndays, *model, device=local)
+    res = None
+    for _ in range(max(args.warmup, 1)):
+        res = one()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = one()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    clk = clocks.stop(t0, t1)
+    tt = torch.tensor([e0.elapsed_time(e1), (t1 - t0) * 1000.0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, wall_ms = float(tt[0]), float(tt[1])
+    launches = ctx.launch_count() - l0
+    # a checksum every rank can produce from its own rows: the mass of the last day (summed over the ranks)
+    mass = res.rows[-1].sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(mass)
+    if rank == 0:
+        D, per = res.dom_len, int(res.rows.shape[1])
+        Nc = res.N // 2 + 1
+        cg = -(-(-(-Nc // world)) // 4) * 4
+        xchg = 16.0 * cg * per * (world - 1)            # bytes one GPU sends per day (its columns x the other ranks' rows)
+        line = {'metric': 'simulated days/sec (fp64)', 'value': ndays * args.steps / (t_ms / 1000.0), 'unit': 'days/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': res.P, 'fft_len': res.N,
+                           'parallelism': ('ONE solve over %d GPU(s): phase-1 days round-robin + one all-gather of the kernels; chain state '
+                                           'sharded by spectral column, one all-to-all and one 4-double all-gather per day' % world),
+                           'sharded': bool(res.sharded), 'rows_per_rank': per,
+                           'l2': 'per-rank working set per day exceeds the 126 MB L2 up to 4 GPUs; no explicit flush'},
+                'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'gpu_launches': int(launches),
+                'timer': 'CUDA events on the stream every kernel and collective of the solve is enqueued on, max over ranks; wind uploaded from host memory inside the timed region',
+                'nvlink': {'alltoall_bytes_sent_per_gpu_per_day': xchg, 'bytes_per_solve_per_gpu': xchg * (ndays - 1),
+                           'time_at_770_GBps_ms_per_solve': xchg * (ndays - 1) / 770e9 * 1e3},
+                'last_day_mass': float(mass[0]), 'max_outside_domain': float(res.meta[:, 3].max()),
+                'e2e': {'value': ndays * args.steps / (wall_ms / 1000.0), 'unit': 'days/s', 'h2d_bytes_per_step': int(wind.nbytes),
+                        'd2h_bytes_per_step': int(res.meta.nbytes), 'note': 'solutions stay sharded on the GPUs (each rank holds its rows of every day)'}}
+        print(json.dumps(line))
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     if rank != 0:
@@ -523,6 +587,9 @@ def main():
     ap.add_argument('--workload', default='synthetic_4097x4097_60d', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the extra configurations (c1-c3, c5, weak_batch)')
+    ap.add_argument('--single-solve', action='store_true',
+                    help='ONE solve of the workload sharded over all ranks (parasitoids_b200.multi: phase-1 days round-robin, '
+                         'slab-decomposed spectral chain with one all-to-all per day) -- strong scaling of BASELINE config 4')
     ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
                     help='library option (pkb_set_option), e.g. fuse_rows=0; recorded in config')
     args = ap.parse_args()
@@ -583,6 +650,11 @@ def main():
         key, val = kv.split('=')
         ctx.set_option(key, float(val))
     wind, wind_data, days, rad_dist, rad_res = load_workload(args.workload)
+    if args.single_solve:
+        run_single_solve(args, ctx, torch, dist, rank, world, local, wind, ndays, rad_dist, rad_res)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # N > 1: a likelihood batch of one parameter proposal per rank (proposal 0 = the defaults),
     # sharded by parasitoids_b200.batch.solve_batch; the only collective is its all_gather

@@ -78,6 +78,8 @@ typedef struct pkb_step_meta {
     long long kcnt;
     int flag;     /* boundary flag, CalcSol.py:36-40 */
     int spec;     /* this step started from the stored spectrum of the state (option "spectral") */
+    int wr0, wr1; /* spectral-resident step restricted to the rows [wr0, wr1) that can hold anything above 1e-15
+                   * (option "spectral_rows"); wr1 <= wr0: all rows */
 } pkb_step_meta;
 
 const char* pkb_last_error(void);
@@ -92,8 +94,9 @@ int pkb_sync(pkb_ctx* ctx);
  * "fuse_rows" (0/1: inverse row pass also runs the next step's forward row pass, default 1),
  * "step_torus" (0/1: whole-torus steps on the smallest 7-smooth torus >= P + 2m of that day's kernel, default 1),
  * "trunc_torus" (0/1: steps from a truncated (flagged) state on a torus >= dom_len + 2m, default 1),
- * "spectral" (0/1: spectral-resident chain steps while the content outside the domain is below 1e-14, default 1;
- *             the one option whose results differ by more than rounding: by at most 1e-12, see chain.cuh),
+ * "spectral" (0/1: spectral-resident chain steps while the content outside the domain is below 1e-13, default 1;
+ *             the one option whose results differ by more than rounding: by at most 1e-11, see chain.cuh),
+ * "spectral_rows" (0/1: such a step inverse-transforms only the rows that can hold a cell above 1e-15, default 1),
  * "spectral_min_reach" (arm them only if the exact support stays inside the domain for this many steps, default 4),
  * "ring_tol" (support-ring decisions of get_mvn_cdf_values closer than this to cdf_eps are re-taken with the reference's
  *             own running sum, ParasitoidModel.py:345-373; default 1e-12, 1.0 forces that path everywhere),
@@ -262,6 +265,38 @@ int pkb_project(pkb_ctx* ctx, const pkb_projection* proj, const double* samples,
  * cross PCIe (Bayes_Run.py:298-306: popdensity_to_emergence + popdensity_grid straight after get_populations) */
 int pkb_solve_batch_projected(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells /*[K][2]*/,
                               int K, const pkb_projection* proj, double* out, int* status);
+/* ---- one solve over the G GPUs of a box (one process per GPU) ----------------------
+ * Phase 1: every rank builds the kernels of its share of the days (the fan-out of Run.py:422-425), exports them into
+ * a caller-owned device buffer, the caller all-gathers those (NCCL) and hands the complete set back as a kernel set.
+ * Phase 2: the slab-decomposed spectral-resident chain of csrc/dist.cuh; the caller drives one day at a time and
+ * runs the two collectives between the passes on the same stream:
+ *     pkb_dist_step_cols(day)  ->  all_to_all(send -> recv)  ->  pkb_dist_step_rows()
+ *                              ->  all_gather(stats -> allstats)  ->  pkb_dist_step_emit(day)
+ * parasitoids_b200/multi.py does exactly that with torch.distributed. */
+typedef struct pkb_dist pkb_dist;
+/* launch everything of this context on `stream` (a cudaStream_t owned by the caller, e.g. torch's current stream);
+ * NULL restores the context's own stream */
+int pkb_set_stream(pkb_ctx* ctx, void* stream);
+/* centred (Wdst x Wdst) window of kernel i, zero padded, into caller-owned DEVICE memory */
+int pkb_kset_export_device(pkb_kset* ks, int i, void* dst_dev, int Wdst);
+/* kernel set from n (W x W) windows in DEVICE memory (copied), with their crop radii */
+int pkb_kset_from_device(pkb_ctx* ctx, const void* windows_dev, int n, int W, const int* rads, int rad_res, pkb_kset** out);
+/* geometry for `world` ranks: complex elements of the send (= recv) buffer, rows per rank, torus */
+int pkb_dist_plan(pkb_ctx* ctx, int dom_len, int mmax, int world, long long* xchg_elems, int* rows_per_rank, int* P, int* N);
+/* send / recv: xchg_elems complex each; stats: 4 doubles; allstats: 4 * world doubles; out: [ndays][rows_per_rank][dom_len]
+ * doubles (this rank's rows of every day's thresholded + renormalised solution; rows beyond the domain are zero).
+ * All caller-owned DEVICE memory.  Day 0 (the recentred first kernel, Run.py:454-458) is written at once. */
+int pkb_dist_create(pkb_ctx* ctx, pkb_kset* ks, int ndays, int rank, int world, void* send, void* recv, void* stats, void* allstats,
+                    void* out, pkb_dist** handle);
+int pkb_dist_step_cols(pkb_dist* h, int day);
+int pkb_dist_step_rows(pkb_dist* h);
+int pkb_dist_step_emit(pkb_dist* h, int day);
+/* after the last day (synchronises): meta[ndays][4] = (kept sum, kept count, max outside the domain, max |.| outside)
+ * per day; ok = 0 if the criterion for skipping the fold mod P failed on some day (then the results must be
+ * discarded and the solve repeated with pkb_solve) */
+int pkb_dist_finish(pkb_dist* h, double* meta, int* ok);
+int pkb_dist_destroy(pkb_dist* h);
+
 int pkb_result_info(pkb_result* r, int* ndays, int* dom_len, int* P, int* N, int* max_shape);
 /* number of chain steps that ran on a support-window torus smaller than N (exact: the state is
  * identically zero outside the window while the spread has not reached the domain edge) */

@@ -230,6 +230,14 @@ class SolveResult(object):
         """Days whose chain step started from the stored spectrum of the state (option ``spectral``)."""
         return [d for d in range(self.ndays) if self.day_meta(d)[1].spec]
 
+    def row_windows(self):
+        """(first row, one past the last row) a spectral-resident step computed on each day, None where all rows."""
+        out = []
+        for d in range(self.ndays):
+            sm = self.day_meta(d)[1]
+            out.append((sm.wr0, sm.wr1) if sm.wr1 > sm.wr0 else None)
+        return out
+
     def radii(self):
         return [self.day_meta(d)[0].rad for d in range(self.ndays)]
 

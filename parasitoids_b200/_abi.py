@@ -38,7 +38,8 @@ class DayMeta(C.Structure):
 
 class StepMeta(C.Structure):
     _fields_ = [('padmax', C.c_double), ('ksum', C.c_double), ('add', C.c_double), ('padabs', C.c_double),
-                ('kcnt', C.c_longlong), ('flag', C.c_int), ('spec', C.c_int)]
+                ('kcnt', C.c_longlong), ('flag', C.c_int), ('spec', C.c_int),
+                ('wr0', C.c_int), ('wr1', C.c_int)]
 
 
 class SolveArgs(C.Structure):
@@ -102,6 +103,16 @@ _SIGS = {
     'pkb_solve_batch_projected': (C.c_int, [_H, C.POINTER(SolveArgs), c_double_p, C.c_int, c_int_p, C.c_int, C.POINTER(Projection),
                                             c_double_p, c_int_p]),
     'pkb_result_project': (C.c_int, [_H, c_int_p, C.c_int, C.POINTER(Projection), c_double_p]),
+    'pkb_set_stream': (C.c_int, [_H, C.c_void_p]),
+    'pkb_kset_export_device': (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int]),
+    'pkb_kset_from_device': (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, c_int_p, C.c_int, _HP]),
+    'pkb_dist_plan': (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ll_p, c_int_p, c_int_p, c_int_p]),
+    'pkb_dist_create': (C.c_int, [_H, _H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _HP]),
+    'pkb_dist_step_cols': (C.c_int, [_H, C.c_int]),
+    'pkb_dist_step_rows': (C.c_int, [_H]),
+    'pkb_dist_step_emit': (C.c_int, [_H, C.c_int]),
+    'pkb_dist_finish': (C.c_int, [_H, c_double_p, c_int_p]),
+    'pkb_dist_destroy': (C.c_int, [_H]),
     'pkb_result_info': (C.c_int, [_H, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'pkb_result_window_steps': (C.c_int, [_H, c_int_p]),
     'pkb_result_day_meta': (C.c_int, [_H, C.c_int, C.POINTER(DayMeta), C.POINTER(StepMeta)]),

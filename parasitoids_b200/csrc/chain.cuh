@@ -110,6 +110,8 @@ struct ChainCtrl {
     int hint;    // the content of this state outside the domain is negligible (<= PKB_SPEC_EPS): worth storing Shat next step
     double eps_sum;   // bound on the deviation from the exact fold mod P accumulated since the state went spectral
     double eps_max;   // largest outside-domain content seen since then
+    int er0, er1;     // rows [er0, er1) hold every cell of this state with |value| >= PKB_SPEC_TAU (er1 <= er0: unknown)
+    int pad_[2];
 };
 
 // Spectral-resident state.  The reference keeps its chain state in Fourier space and only inverse-transforms
@@ -122,8 +124,29 @@ struct ChainCtrl {
 // step starts from it: no forward row pass, no forward column transform of the state.  The real state is
 // still produced (folded, with flag and sums) every day, so the chain drops back to exact steps the moment
 // the criterion fails -- decided on the device in the last CTA of k_rows_inv, no host round trip.
-#define PKB_SPEC_EPS 1e-14
-#define PKB_SPEC_BUDGET 1e-12
+// (What lies outside the domain in the in-domain regime is rounding noise of the transforms, ~2e-14 of the state's
+// peak on a 4704^2 torus: 1e-14 right after the release, when the peak is ~0.4, 1e-19 a few weeks later.)
+#define PKB_SPEC_EPS 1e-13
+#define PKB_SPEC_BUDGET 1e-11
+// Row window of a spectral-resident step.  The real state of such a step is only produced for output, and most of
+// it is (numerically) empty: if every cell of yesterday's state outside the rows [er0, er1) is below PKB_SPEC_TAU in
+// magnitude, every cell of today's outside [er0 - m, er1 + m) is too (a convolution with a non-negative kernel of
+// unit mass and radius m is a weighted average).  Those rows are neither inverse-transformed nor read by the
+// emission; the thresholded output there is zero either way (TAU << 1e-8), and as long as the window stays inside
+// the domain rows the content outside the domain is below max(TAU, what the window rows show in their pad columns),
+// which is what enters the criterion above.  er0 / er1 are re-measured on every step from the rows that were computed.
+#define PKB_SPEC_TAU 1e-15
+__device__ __forceinline__ bool spec_row_window(int allow, int spec, int er0, int er1, double eps_sum, double eps_max, int m, int D, int& w0,
+                                                int& w1) {
+    if (!allow || !spec || er1 <= er0) return false;
+    w0 = er0 - m;
+    w1 = er1 + m;
+    if (w0 < 0 || w1 > D) return false;
+    if (eps_sum + 2.0 * fmax(eps_max, PKB_SPEC_TAU) > PKB_SPEC_BUDGET) return false;
+    w0 &= ~1;
+    w1 = (w1 + 1) & ~1;
+    return true;
+}
 
 // Geometry of a step whose SOURCE state is truncated (ChainCtrl::trunc: zero outside [0,D)^2).  Its linear
 // convolution with a radius-m kernel spans D + 2m cells only, so such a step can run on a torus
@@ -139,6 +162,7 @@ struct StepMeta {   // one per emitted solution
     long long kcnt;
     int flag;
     int spec;    // this step started from the stored spectrum (spectral-resident step)
+    int wr0, wr1;   // rows [wr0, wr1) of the state were computed, the others are below PKB_SPEC_TAU (wr1 <= wr0: all rows)
 };
 
 // ---------------------------------------------------------------------------
@@ -386,14 +410,20 @@ __device__ __forceinline__ void cols_final(cplx* x, cplx* __restrict__ scr, cplx
 // Shat (optional): spectral-resident state, gridDim-independent slices of hstride complex per column.
 __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __restrict__ Krt, int m, ChainDims d,
                                    ChainCtrl* ctrl, cplx* __restrict__ Wt, cplx* __restrict__ scr, FftPlan plan,
-                                   TruncGeom tg, FftPlan plan_t, const cplx* __restrict__ Krt_t, cplx* __restrict__ Shat, size_t hstride) {
+                                   TruncGeom tg, FftPlan plan_t, const cplx* __restrict__ Krt_t, cplx* __restrict__ Shat, size_t hstride,
+                                   int rowwin_ok) {
     const int c_trunc = ctrl->trunc, c_spec = ctrl->spec, c_hint = ctrl->hint;
+    const int c_er0 = ctrl->er0, c_er1 = ctrl->er1;
+    const double c_esum = ctrl->eps_sum, c_emax = ctrl->eps_max;
     const bool tr = tg.N && c_trunc;          // truncated source on its smaller torus (TruncGeom)
     // start from the stored spectrum / keep the product spectrum for the next step (uniform over the grid; `stored`
     // tells this step's k_rows_inv, which decides whether the next step may start from it)
     const bool use_spec = Shat != nullptr && c_spec && !tr && !d.win;
     const bool store = Shat != nullptr && !tr && !d.win && (use_spec || c_hint);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->stored = store ? 1 : 0;
+    // spectral-resident step: only the rows of the window are needed downstream (spec_row_window)
+    int w0 = 0, w1 = 0;
+    const bool rowwin = use_spec && spec_row_window(rowwin_ok, c_spec, c_er0, c_er1, c_esum, c_emax, m, d.D, w0, w1);
     if (tr) {
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
         plan = plan_t;
@@ -425,7 +455,7 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
         };
         auto ld_state = [&](int i) -> cplx { return i < lim ? ycol[(size_t)i * PKB_CB] : cmake(0.0, 0.0); };
         auto st_out = [&](int i, cplx v) {
-            if (i < hi || i >= N - m) wcol[(size_t)i * PKB_CB] = v;
+            if (rowwin ? (i >= w0 && i < w1) : (i < hi || i >= N - m)) wcol[(size_t)i * PKB_CB] = v;
         };
         for (int phase = 0; phase < 2; ++phase) {
             auto ld = [&](int i) -> cplx { return phase ? ld_state(i) : ld_filter(i); };
@@ -460,8 +490,11 @@ __global__ void PKB_COLS_LB k_cols(const cplx* __restrict__ Yt, const cplx* __re
 struct RowStats {
     double padmax, ksum, padabs;
     int kcnt;
-    int pad_;
+    int has_e;      // some cell of the row (any column of the torus) is >= PKB_SPEC_TAU in magnitude
 };
+// has_e travels through the block reduction inside the kept-count sum: every thread that saw such a cell adds 2^20
+// (a row has far fewer than 2^20 cells, and the sums are exact in fp64)
+#define PKB_HAS_E_UNIT 1048576.0
 
 // Block reduction of 8 per-thread values: entries with (i & 3) == 0 or 3 by max, the
 // others by sum.  Result valid in thread i (i < 8) of warp 0.  red: PKB_RED_DOUBLES doubles
@@ -496,6 +529,7 @@ struct SpecIn {
     int stored;        // k_cols of this step wrote the product spectrum
     int was_spec;      // this step itself started from Shat
     double eps_sum, eps_max;
+    int rowwin, w0, w1;   // only the rows [w0, w1) were computed (spec_row_window)
 };
 
 // Flag / kept sum / kept count / largest outside-domain magnitude of a state from its per-row statistics
@@ -505,30 +539,39 @@ struct SpecIn {
 __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const ChainDims& d, ChainCtrl* ctrl,
                                                     StepMeta* __restrict__ meta, int apply_trunc, double* red, int tid, int T,
                                                     SpecIn si, double flag_thresh) {
-    // st[0] pad max, st[1] kept sum, st[2] kept count, st[3] max |v| outside the domain
-    double st[8] = {-INFINITY, 0.0, 0.0, 0.0, -INFINITY, 0.0, 0.0, 0.0};
-    // contiguous chunks per thread so the summation order over rows is fixed
-    const int chunk = (d.P + T - 1) / T;
+    // st[0] pad max, st[1] kept sum, st[2] kept count, st[3] max |v| outside the domain,
+    // st[4] -(first row with a cell >= PKB_SPEC_TAU), st[7] last such row
+    double st[8] = {-INFINITY, 0.0, 0.0, 0.0, -INFINITY, 0.0, 0.0, -INFINITY};
+    // contiguous chunks per thread so the summation order over rows is fixed; a row-windowed step only has
+    // statistics for its window rows (the others hold nothing above PKB_SPEC_TAU)
+    const int lo = si.rowwin ? si.w0 : 0, hi = si.rowwin ? si.w1 : d.P;
+    const int chunk = (hi - lo + T - 1) / T;
     const volatile RowStats* rv = rstat;
-    for (int r = tid * chunk; r < d.P && r < (tid + 1) * chunk; ++r) {
+    for (int r = lo + tid * chunk; r < hi && r < lo + (tid + 1) * chunk; ++r) {
         const double pm = rv[r].padmax, ks = rv[r].ksum, pa = rv[r].padabs;
         const int kc = rv[r].kcnt;
         st[0] = fmax(st[0], pm);
         st[3] = fmax(st[3], pa);
         if (r < d.D) { st[1] += ks; st[2] += (double)kc; }
+        if (rv[r].has_e) { st[4] = fmax(st[4], -(double)r); st[7] = fmax(st[7], (double)r); }
     }
     __syncthreads();
     const double rr = block_reduce8(st, red, tid, T);
-    if (tid < 4) red[64 + tid] = rr;
+    if (tid < 8) red[64 + tid] = rr;
     __syncthreads();
     if (tid == 0) {
-        const double bp = red[64], bs = red[65], bc = red[66], ba = red[67];
+        const double bp = si.rowwin ? fmax(red[64], -PKB_SPEC_TAU) : red[64], bs = red[65], bc = red[66];
+        const double ba = si.rowwin ? fmax(red[67], PKB_SPEC_TAU) : red[67];
         const int flag = bp > flag_thresh ? 1 : 0;   // CalcSol.py:36-37
         meta->padmax = bp; meta->ksum = bs; meta->kcnt = (long long)bc; meta->padabs = ba;
         meta->add = (1.0 - bs) / bc;                 // CalcSol.py:135
         meta->flag = flag;
         meta->spec = si.was_spec;
+        meta->wr0 = si.rowwin ? si.w0 : 0;
+        meta->wr1 = si.rowwin ? si.w1 : 0;
         ctrl->flag = flag;
+        ctrl->er0 = red[71] >= 0.0 ? (int)(-red[68]) : 0;
+        ctrl->er1 = red[71] >= 0.0 ? (int)red[71] + 1 : 0;
         // a fresh convolution result is a full P x P state; it becomes a
         // truncated one only where the caller applies CalcSol.py:200-201
         ctrl->trunc = apply_trunc ? flag : 0;
@@ -550,7 +593,7 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
 __global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* ctrl, StepMeta* __restrict__ meta,
                                 int apply_trunc, double flag_thresh) {
     PKB_SHARED(double, red, PKB_RED_DOUBLES);
-    SpecIn si = {0, 0, 0.0, 0.0};
+    SpecIn si = {0, 0, 0.0, 0.0, 0, 0, 0};
     step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x, si, flag_thresh);
 }
 
@@ -614,10 +657,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* ctrl, StepMeta* __restrict__ meta, int apply_trunc,
                                        cplx* __restrict__ Yt_next, const ChainCtrl* src_ctrl, TruncGeom tg, FftPlan plan_t,
-                                       int desc_order) {
+                                       int desc_order, int rowwin_ok) {
     const volatile ChainCtrl* sc = src_ctrl;
-    const SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max};
+    SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max, 0, 0, 0};
     const bool tr = tg.N && !d.win && sc->trunc;      // truncated source on its smaller torus (TruncGeom)
+    // row window of a spectral-resident step (the same decision k_cols took from the same control block)
+    si.rowwin = (!tr && !d.win && spec_row_window(rowwin_ok, si.was_spec, sc->er0, sc->er1, si.eps_sum, si.eps_max, m, d.D, si.w0, si.w1)) ? 1 : 0;
     if (tr) {
         d.N = tg.N; d.Nc = tg.Nc; d.ldW = tg.ldW;
         plan = plan_t;
@@ -638,14 +683,14 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     __syncthreads();
     const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
     const int wout = d.wn + 2 * m;                       // window mode: side of the result
-    const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : rows_inv_jobs(P, m));
+    const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : (si.rowwin ? (si.w1 - si.w0) / 2 : rows_inv_jobs(P, m)));
     const double scale = 1.0 / ((double)N * (double)N);
     const cplx zero = cmake(0.0, 0.0);
     const int E = D + m, Lo = P - m;                     // truncated mode: extent of the positive rows / columns, first folded one
     // Whole-torus mode: jobs are taken in DESCENDING order.  The fold jobs (job < 2m) are the short ones --
     // one output row and never a fused forward transform -- so they go last and the partial final round of
     // the persistent grid is made of short jobs instead of the longest ones.
-    const bool descending = desc_order && !d.win && !tr;
+    const bool descending = desc_order && !d.win && !tr && !si.rowwin;
     for (int it = blockIdx.x; it < njobs; it += gridDim.x) {
         const int job = descending ? njobs - 1 - it : it;
         int ra, rb, out_a, out_b;
@@ -664,12 +709,17 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             out_a = d.wr0 + ja;
             if (jb < d.wn + m) { rb = jb < 0 ? jb + N : jb; out_b = d.wr0 + jb; }
             else { rb = -1; out_b = -1; }
+        } else if (si.rowwin) {
+            // window rows in pairs; what would fold onto them from beyond the torus edge is below PKB_SPEC_TAU
+            fold = false;
+            out_a = ra = si.w0 + 2 * job;
+            out_b = rb = out_a + 1;
         } else {
             rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
         }
         {   // next job's Wt rows -> L2 while this one is transformed
             const int nj = job - (int)gridDim.x;        // (descending order)
-            if ((PKB_PREFETCH & 2) && !d.win && !tr && nj >= 0) {
+            if ((PKB_PREFETCH & 2) && !d.win && !tr && !si.rowwin && nj >= 0) {
                 int na, nb, oa, ob;
                 bool nf;
                 rows_inv_decode(nj, m, P, N, na, nb, oa, ob, nf);
@@ -747,6 +797,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         if (d.win) { st[0] = st[4] = 0.0; }                          // the untouched rest of the row is zero
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
         const int Dc = D - col0;                                     // first pad column, relative to col0
+        bool e_a = false, e_b = false;                               // a cell >= PKB_SPEC_TAU in this row (RowStats::has_e)
         for (int c = tid; c < ncols; c += T) {
             cplx z;
             if (tr) {
@@ -758,15 +809,19 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             }
             const double va = (fold ? z.x + z.y : z.x) * scale;
             dst_a[c] = va;
+            e_a |= fabs(va) >= PKB_SPEC_TAU;
             if (pad_a || c >= Dc) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
             else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
             if (out_b >= 0) {
                 const double vb = z.y * scale;
                 dst_b[c] = vb;
+                e_b |= fabs(vb) >= PKB_SPEC_TAU;
                 if (pad_b || c >= Dc) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
                 else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
             }
         }
+        if (e_a) st[2] += PKB_HAS_E_UNIT;
+        if (e_b) st[6] += PKB_HAS_E_UNIT;
         __syncthreads();                               // every thread is done reading x: reuse it as scratch
         const double r = block_reduce8(st, red, tid, T);
         if (tid < 8) red[64 + tid] = r;
@@ -774,7 +829,9 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         if (tid == 0 || (tid == 1 && out_b >= 0)) {
             const double* q = red + 64 + 4 * tid;
             RowStats rs;
-            rs.padmax = q[0]; rs.ksum = q[1]; rs.kcnt = (int)q[2]; rs.padabs = q[3]; rs.pad_ = 0;
+            rs.padmax = q[0]; rs.ksum = q[1]; rs.padabs = q[3];
+            rs.has_e = q[2] >= PKB_HAS_E_UNIT ? 1 : 0;
+            rs.kcnt = (int)(q[2] - floor(q[2] / PKB_HAS_E_UNIT) * PKB_HAS_E_UNIT);
             rstat[tid ? out_b : out_a] = rs;
         }
         __syncthreads();
@@ -828,11 +885,17 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
                              int strict, double* __restrict__ out, int* __restrict__ rownnz) {
     PKB_SHARED(int, cnt, 1);
     const double add = prob_model ? meta->add : 0.0;
+    const int wr0 = meta->wr0, wr1 = meta->wr1;          // row-windowed step: the other rows were not computed (all below PKB_SPEC_TAU)
     // rows blockIdx.x, blockIdx.x + gridDim.x, ...: one CTA per row (grid = D), or a few small persistent
     // CTAs that trickle through the day next to the FFT kernels of the following step (fused solve)
     for (int r = blockIdx.x; r < d.D; r += gridDim.x) {
         const double* src = S + (size_t)r * d.ldS;
         double* dst = out + (size_t)r * d.D;
+        if (wr1 > wr0 && (r < wr0 || r >= wr1)) {
+            for (int c = threadIdx.x; c < d.D; c += blockDim.x) dst[c] = 0.0;
+            if (rownnz && threadIdx.x == 0) rownnz[r] = 0;
+            continue;
+        }
         if (rownnz) {
             __syncthreads();                 // (the previous row's count has been read)
             if (threadIdx.x == 0) cnt[0] = 0;
@@ -878,10 +941,12 @@ __global__ void k_zero_pad(double* __restrict__ S, ChainDims d, const ChainCtrl*
     for (int c = c0 + threadIdx.x; c < d.P; c += blockDim.x) row[c] = 0.0;
 }
 
-// plain copy of the domain block (un-thresholded), grid = D
-__global__ void k_copy_domain(const double* __restrict__ S, ChainDims d, double* __restrict__ out) {
+// plain copy of the domain block (un-thresholded), grid = D.  meta (optional): rows a row-windowed step did not
+// compute (all below PKB_SPEC_TAU) are written as zeros
+__global__ void k_copy_domain(const double* __restrict__ S, ChainDims d, double* __restrict__ out, const StepMeta* __restrict__ meta) {
     const int r = blockIdx.x;
-    for (int c = threadIdx.x; c < d.D; c += blockDim.x) out[(size_t)r * d.D + c] = S[(size_t)r * d.ldS + c];
+    const bool skip = meta && meta->wr1 > meta->wr0 && (r < meta->wr0 || r >= meta->wr1);
+    for (int c = threadIdx.x; c < d.D; c += blockDim.x) out[(size_t)r * d.D + c] = skip ? 0.0 : S[(size_t)r * d.ldS + c];
 }
 
 // Place a dense centred kernel window (Wk x Wk, radius used: m) into a zeroed
@@ -947,7 +1012,9 @@ __global__ void k_emit_dense_cells(const double* __restrict__ S, ChainDims d, co
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     const double add = prob_model ? meta->add : 0.0;
-    const double v = S[(size_t)cells[2 * k] * d.ldS + cells[2 * k + 1]];
+    const int r = cells[2 * k];
+    if (meta->wr1 > meta->wr0 && (r < meta->wr0 || r >= meta->wr1)) { out[k] = 0.0; return; }      // row-windowed step
+    const double v = S[(size_t)r * d.ldS + cells[2 * k + 1]];
     const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
     out[k] = keep ? v + add : 0.0;
 }
@@ -1106,20 +1173,22 @@ __global__ void k_stencil(const double* __restrict__ S, const double* __restrict
 __global__ void k_row_stats(const double* __restrict__ S, ChainDims d, RowStats* __restrict__ rstat, double negval) {
     PKB_SHARED(double, red, 256);
     const int r = blockIdx.x;
-    double pmax = -INFINITY, ks = 0.0, pab = 0.0;
+    double pmax = -INFINITY, ks = 0.0, pab = 0.0, rab = 0.0;
     int kc = 0;
     for (int c = threadIdx.x; c < d.P; c += blockDim.x) {
         const double v = S[(size_t)r * d.ldS + c];
+        rab = fmax(rab, fabs(v));
         if (r >= d.D || c >= d.D) { pmax = fmax(pmax, v); pab = fmax(pab, fabs(v)); }
         else if (!(v < negval)) { ks += v; kc += 1; }
     }
+    const double brab = block_max(rab, red);
     const double bpmax = block_max(pmax, red);
     const double bks = block_sum(ks, red);
     const double bkc = block_sum((double)kc, red);
     const double bab = block_max(pab, red);
     if (threadIdx.x == 0) {
         RowStats rs;
-        rs.padmax = bpmax; rs.ksum = bks; rs.padabs = bab; rs.kcnt = (int)bkc; rs.pad_ = 0;
+        rs.padmax = bpmax; rs.ksum = bks; rs.padabs = bab; rs.kcnt = (int)bkc; rs.has_e = brab >= PKB_SPEC_TAU ? 1 : 0;
         rstat[r] = rs;
     }
 }

@@ -14,6 +14,7 @@
 #include "phase1.cuh"
 #include "chain.cuh"
 #include "project.cuh"
+#include "dist.cuh"
 
 #include <algorithm>
 #include <array>
@@ -77,6 +78,7 @@ struct PlanRec {
 struct pkb_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t own_stream;   // the stream created with the context (ctx->stream unless pkb_set_stream lent another one)
     cudaStream_t aux;       // side stream: output emission overlapped with the next chain step
     cudaStream_t cp;        // copy stream: per-day COO compaction + D2H while the chain is still running
     std::vector<cudaEvent_t> day_events;
@@ -105,6 +107,7 @@ struct pkb_ctx {
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
     double ring_tol;        // ring-growth decisions closer than this to cdf_eps are re-taken in the reference's summation order (option "ring_tol")
+    int use_rowwin;         // ... restricted to the rows that can hold anything (option "spectral_rows", chain.cuh PKB_SPEC_TAU)
     int spec_min_reach;     // ... armed only if the exact support stays inside the domain for this many steps (option "spectral_min_reach")
     int use_spectral;       // fused solve: spectral-resident steps while nothing of consequence lies outside the domain (option "spectral")
     int emit_ctas;          // fused solve: side-stream emission as this many persistent 64-thread CTAs (option "emit_ctas"; 0, the
@@ -339,6 +342,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_trunc_torus = 1;
     ctx->use_spectral = 1;
     ctx->spec_min_reach = 4;
+    ctx->use_rowwin = 1;
     ctx->ring_tol = 1e-12;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
@@ -351,6 +355,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->prof_on = false;
     for (int i = 0; i < 4; ++i) ctx->timing[i] = 0.0;
     CU(cudaStreamCreate(&ctx->stream));
+    ctx->own_stream = ctx->stream;
     {
         // the side streams carry short kernels that must slip in between the persistent FFT kernels
         // of the main stream: highest priority, so their CTAs are placed first whenever SM slots free up
@@ -372,6 +377,8 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     TRY(opt_in_smem(k_kernel_rows_batch));
     TRY(opt_in_smem(k_cols));
     TRY(opt_in_smem(k_rows_inv));
+    TRY(opt_in_smem(k_cols_dist));
+    TRY(opt_in_smem(k_rows_inv_dist));
     TRY(opt_in_smem(k_fft_test));
     TRY(opt_in_smem(k_period));
     TRY(opt_in_smem(k_hprob));
@@ -411,7 +418,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     cudaEventDestroy(ctx->ev_cp);
     cudaStreamDestroy(ctx->cp);
     cudaStreamDestroy(ctx->aux);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return 0;
 }
@@ -448,6 +455,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "ring_tol")) {
         if (!(value >= 0)) return fail(PKB_EINVAL, "ring_tol must be >= 0");
         ctx->ring_tol = value;
+        return 0;
+    }
+    if (!strcmp(key, "spectral_rows")) {
+        ctx->use_rowwin = value != 0;
         return 0;
     }
     if (!strcmp(key, "spectral_min_reach")) {
@@ -1271,7 +1282,8 @@ static ChainDims trunc_dims(const ChainDims& d, const TruncGeom& tg) {
 
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
-                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true, bool spec_try = false) {
+                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true, int spec_try = 0) {
+    // spec_try: 0 exact steps only; 1 spectral-resident steps allowed; 2 ... with row windows (ChainCtrl::er0, probability model)
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
@@ -1323,13 +1335,14 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         shat = ch->Shat.p;
     }
     ChainCtrl* src_ctrl_w = const_cast<ChainCtrl*>(src_ctrl);      // (k_cols leaves its `stored` message there)
+    const int rowwin_ok = (shat && spec_try >= 2 && ctx->use_rowwin) ? 1 : 0;
     if (win) {
         if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
         LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1, tg, plan_t, 0);
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
-                  m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0);
+                  m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0, 0);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
@@ -1344,9 +1357,10 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     if (!tg.N) krt_t = krt;
     LAUNCH(ctx, k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, pre_m, tg, plan_t, shat ? 1 : 0);
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl_w,
-           ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride);
+           ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride, rowwin_ok);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
-           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc);
+           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc,
+           rowwin_ok);
     return 0;
 }
 
@@ -1410,7 +1424,7 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
 }
 
 static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr,
-                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr, bool spec_try = false) {
+                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr, int spec_try = 0) {
     const int nxt = ch->cur ^ 1;
     TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win,
                   fuse_next, pre_m, true, krt_t, true, spec_try));
@@ -1456,7 +1470,7 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
         ch->stats_valid = true;
     }
     if (out) {
-        if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p);
+        if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p, (const StepMeta*)nullptr);
         else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, mode == 1 ? 1 : 0, ch->dout.p, (int*)nullptr);
         CU(cudaMemcpyAsync(out, ch->dout.p, (size_t)d.D * d.D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -1512,7 +1526,7 @@ extern "C" int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters,
         TRY(upload_filter(ch, filters[j], ks[j], &m));
         TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false, 1 + j, 1));
         if (out) {
-            if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p);
+            if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p, (const StepMeta*)nullptr);
             else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p, (int*)nullptr);
             CU(cudaMemcpyAsync(out + nd * j, ch->dout.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
@@ -1563,6 +1577,265 @@ extern "C" int pkb_chain_get_state(pkb_chain* ch, double* out) {
     for (int r = 0; r < d.P; ++r)
         CU(cudaMemcpyAsync(out + (size_t)r * d.P, S + (size_t)r * d.ldS, sizeof(double) * d.P, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx, "pkb_chain_get_state");
+}
+
+// ---------------------------------------------------------------------------
+// one solve over the GPUs of a box (csrc/dist.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int pkb_set_stream(pkb_ctx* ctx, void* stream) {
+    if (!ctx) return fail(PKB_EINVAL, "pkb_set_stream: NULL context");
+    CU(cudaSetDevice(ctx->device));
+    TRY(sync_check(ctx, "pkb_set_stream"));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return 0;
+}
+
+// dst[r][c] = centred (Wd x Wd) window of the (Ws x Ws) source, zero where the source has no cell.  grid = Wd, block = 128
+__global__ void k_copy_window(const double* __restrict__ src, int Ws, double* __restrict__ dst, int Wd) {
+    const int r = blockIdx.x, off = Ws / 2 - Wd / 2;
+    for (int c = threadIdx.x; c < Wd; c += blockDim.x) {
+        const int sr = r + off, sc = c + off;
+        dst[(size_t)r * Wd + c] = (sr >= 0 && sr < Ws && sc >= 0 && sc < Ws) ? src[(size_t)sr * Ws + sc] : 0.0;
+    }
+}
+
+extern "C" int pkb_kset_export_device(pkb_kset* ks, int i, void* dst_dev, int Wdst) {
+    if (!ks || !dst_dev || i < 0 || i >= ks->nprob) return fail(PKB_EINVAL, "pkb_kset_export_device: bad argument");
+    if (Wdst < 2 * ks->hmeta[i].rad + 1 || !(Wdst & 1)) return fail(PKB_EINVAL, "pkb_kset_export_device: window side %d does not hold radius %d", Wdst, ks->hmeta[i].rad);
+    pkb_ctx* ctx = ks->ctx;
+    CU(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_copy_window, Wdst, 128, 0, (const double*)(ks->acc.p + (size_t)ks->W * ks->W * i), ks->W, (double*)dst_dev, Wdst);
+    return check_launches(ctx, "pkb_kset_export_device");
+}
+
+extern "C" int pkb_kset_from_device(pkb_ctx* ctx, const void* windows_dev, int n, int W, const int* rads, int rad_res, pkb_kset** out) {
+    if (!ctx || !windows_dev || !rads || !out) return fail(PKB_EINVAL, "pkb_kset_from_device: NULL argument");
+    if (n < 1 || W < 1 || !(W & 1) || rad_res < 1) return fail(PKB_EINVAL, "pkb_kset_from_device: bad sizes");
+    CU(cudaSetDevice(ctx->device));
+    pkb_kset* ks = new pkb_kset();
+    ks->ctx = ctx;
+    ks->nprob = n;
+    ks->periods = 0;
+    ks->keep_pre = false;
+    ks->rad_res = rad_res;
+    ks->racc = W / 2;
+    ks->W = W;
+    ks->hmeta.resize(n);
+    ks->hdp.resize(n);
+    for (int i = 0; i < n; ++i) {
+        memset(&ks->hmeta[i], 0, sizeof(DayMeta));
+        memset(&ks->hdp[i], 0, sizeof(DayParams));
+        if (rads[i] < 0 || 2 * rads[i] + 1 > W) { delete ks; return fail(PKB_EINVAL, "pkb_kset_from_device: radius %d does not fit the window", rads[i]); }
+        ks->hmeta[i].rad = rads[i];
+    }
+    const size_t nel = (size_t)W * W * n;
+    int rc = ks->acc.alloc(ctx, nel);
+    if (rc) { delete ks; return rc; }
+    cudaError_t e = cudaMemcpyAsync(ks->acc.p, windows_dev, nel * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { delete ks; return fail(PKB_ECUDA, "pkb_kset_from_device: copy failed: %s", cudaGetErrorString(e)); }
+    *out = ks;
+    return 0;
+}
+
+struct pkb_dist {
+    pkb_ctx* ctx;
+    pkb_kset* ks;          // borrowed
+    int nd;
+    ChainDims d;
+    FftPlan plan;
+    DistGeom g;
+    DBuf<double> S0;       // the placed kernel of day 0 (full real state, only for the first forward row pass)
+    DBuf<cplx> Yt, Krt, cscr, Shat;
+    size_t hstride;
+    DBuf<double> Sloc;     // [Jr][ldL]
+    int ldL;
+    DBuf<RowStats> rstat;
+    DBuf<int> done;
+    DBuf<double> meta;     // [nd][4]
+    DBuf<double> worst;
+    DBuf<ChainCtrl> ctrl;
+    cplx *send, *recv;
+    double *stats, *allstats, *out;
+    bool first;            // the next column pass starts from Yt (day 1)
+};
+
+static int dist_geom(pkb_ctx* ctx, int D, int mmax, int world, int rank, ChainDims* d, FftPlan* plan, DistGeom* g) {
+    if (D < 1 || mmax < 0 || world < 1 || rank < 0 || rank >= world) return fail(PKB_EINVAL, "pkb_dist: bad sizes");
+    memset(d, 0, sizeof *d);
+    d->D = D;
+    d->P = D + mmax;
+    d->N = pkb_smooth_len(std::max(2, d->P + 2 * mmax));
+    d->Nc = d->N / 2 + 1;
+    d->ldS = roundup(d->P, 16);
+    d->ldY = roundup(d->P, 2);
+    d->ldW = roundup(d->N, 2);
+    d->ldK = roundup(2 * mmax + 1, 2);
+    TRY(get_plan(ctx, d->N, plan));
+    if (fft_smem_bytes(*plan) > (size_t)ctx->max_smem || plan->grid_rows < 1 || plan->grid_cols < 1)
+        return fail(PKB_ELIMIT, "torus side %d exceeds the shared-memory FFT limit", d->N);
+    memset(g, 0, sizeof *g);
+    g->G = world;
+    g->rank = rank;
+    g->Cg = roundup((d->Nc + world - 1) / world, PKB_CB);
+    g->c0 = std::min(d->Nc, rank * g->Cg);
+    g->c1 = std::min(d->Nc, (rank + 1) * g->Cg);
+    g->mmax = mmax;
+    g->J = d->P + 2 * mmax;
+    g->Jr = roundup((g->J + world - 1) / world, 2);
+    g->j0 = std::min(g->J, rank * g->Jr);
+    g->j1 = std::min(g->J, (rank + 1) * g->Jr);
+    g->jr_magic = g->Jr == 1 ? 0u : 0xFFFFFFFFu / (unsigned)g->Jr + 1u;
+    g->blk = spec_size(g->Cg, g->Jr);
+    if (g->J >= 65536 || d->Nc >= 65536) return fail(PKB_ELIMIT, "pkb_dist: torus too large for the 16-bit index arithmetic");
+    return 0;
+}
+
+extern "C" int pkb_dist_plan(pkb_ctx* ctx, int dom_len, int mmax, int world, long long* xchg_elems, int* rows_per_rank, int* P, int* N) {
+    if (!ctx) return fail(PKB_EINVAL, "pkb_dist_plan: NULL context");
+    CU(cudaSetDevice(ctx->device));
+    ChainDims d;
+    FftPlan plan;
+    DistGeom g;
+    TRY(dist_geom(ctx, dom_len, mmax, world, 0, &d, &plan, &g));
+    if (xchg_elems) *xchg_elems = (long long)g.blk * world;
+    if (rows_per_rank) *rows_per_rank = g.Jr;
+    if (P) *P = d.P;
+    if (N) *N = d.N;
+    return 0;
+}
+
+extern "C" int pkb_dist_create(pkb_ctx* ctx, pkb_kset* ks, int ndays, int rank, int world, void* send, void* recv, void* stats,
+                               void* allstats, void* out, pkb_dist** handle) {
+    if (!ctx || !ks || !send || !recv || !stats || !allstats || !out || !handle) return fail(PKB_EINVAL, "pkb_dist_create: NULL argument");
+    *handle = nullptr;
+    if (ndays < 1 || ndays > ks->nprob) return fail(PKB_EINVAL, "pkb_dist_create: ndays %d exceeds the kernel set", ndays);
+    CU(cudaSetDevice(ctx->device));
+    int mmax = 0;
+    for (int i = 0; i < ndays; ++i) mmax = std::max(mmax, ks->hmeta[i].rad);
+    const int D = 2 * ks->rad_res + 1;
+    pkb_dist* h = new pkb_dist();
+    struct Guard {
+        pkb_dist* p;
+        ~Guard() { delete p; }
+    } guard{h};
+    h->ctx = ctx;
+    h->ks = ks;
+    h->nd = ndays;
+    TRY(dist_geom(ctx, D, mmax, world, rank, &h->d, &h->plan, &h->g));
+    const ChainDims& d = h->d;
+    const FftPlan& plan = h->plan;
+    for (int i = 0; i < ndays; ++i)
+        if (ks->hmeta[i].rad <= ctx->stencil_max_radius || ks->hmeta[i].rad > D / 2)
+            return fail(PKB_ELIMIT, "pkb_dist_create: kernel radius %d is outside the range the distributed chain handles", ks->hmeta[i].rad);
+    h->send = (cplx*)send; h->recv = (cplx*)recv;
+    h->stats = (double*)stats; h->allstats = (double*)allstats; h->out = (double*)out;
+    const int RL = plan_radix(plan, plan.nstage - 1);
+    h->hstride = (size_t)plan.cols_kb * RL * plan.cols_threads;
+    const size_t ns = (size_t)d.P * d.ldS;
+    TRY(h->S0.alloc(ctx, ns));
+    TRY(h->Yt.alloc(ctx, spec_size(d.Nc + 1, d.ldY)));
+    TRY(h->Krt.alloc(ctx, spec_size(d.Nc + 1, d.ldK)));
+    TRY(h->cscr.alloc(ctx, (size_t)ctx->occ_cap * ctx->sm_count * ((size_t)d.N + 21 * 256 + 256)));
+    TRY(h->Shat.alloc(ctx, h->hstride * std::max(1, h->g.c1 - h->g.c0)));
+    h->ldL = roundup(D, 16);
+    TRY(h->Sloc.alloc(ctx, (size_t)h->g.Jr * h->ldL));
+    TRY(h->rstat.alloc(ctx, h->g.Jr));
+    TRY(h->done.alloc(ctx, 1));
+    TRY(h->meta.alloc(ctx, (size_t)ndays * 4));
+    TRY(h->worst.alloc(ctx, 1));
+    TRY(h->ctrl.alloc(ctx, 1));
+    CU(cudaMemsetAsync(h->done.p, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(h->meta.p, 0, sizeof(double) * 4 * ndays, ctx->stream));
+    CU(cudaMemsetAsync(h->worst.p, 0, sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(h->ctrl.p, 0, sizeof(ChainCtrl), ctx->stream));
+    CU(cudaMemsetAsync(h->S0.p, 0, ns * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(h->send, 0, sizeof(cplx) * h->g.blk * world, ctx->stream));      // (padding rows / columns of the blocks stay zero)
+    // day 0: the first kernel recentred on the domain (Run.py:454-458); its row spectra feed the first column pass
+    const size_t nW = (size_t)ks->W * ks->W;
+    LAUNCH(ctx, k_place_kernel, 2 * ks->hmeta[0].rad + 1, 128, 0, (const double*)ks->acc.p, ks->W, ks->hmeta[0].rad, d, h->S0.p);
+    TruncGeom tg;
+    memset(&tg, 0, sizeof tg);
+    const size_t sm1 = fft_smem_bytes(plan);
+    LAUNCH(ctx, k_rows_fwd, std::min((d.P + 1) / 2, plan.grid_rows), plan.threads, sm1, (const double*)h->S0.p, d, (const ChainCtrl*)h->ctrl.p, h->Yt.p,
+           plan, -1, tg, plan, 0);
+    // this rank's rows of day 0 (un-thresholded copy, CalcSol.get_solutions leaves modelsol[0] as it is)
+    {
+        const int r0 = h->g.j0, r1 = std::min(h->g.j1, D);
+        CU(cudaMemsetAsync(h->out, 0, sizeof(double) * (size_t)h->g.Jr * D, ctx->stream));
+        if (r1 > r0)
+            CU(cudaMemcpy2DAsync(h->out, sizeof(double) * D, h->S0.p + (size_t)r0 * d.ldS, sizeof(double) * d.ldS, sizeof(double) * D, r1 - r0,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    (void)nW;
+    h->first = true;
+    TRY(check_launches(ctx, "pkb_dist_create"));
+    guard.p = nullptr;
+    *handle = h;
+    return 0;
+}
+
+extern "C" int pkb_dist_step_cols(pkb_dist* h, int day) {
+    if (!h || day < 1 || day >= h->nd) return fail(PKB_EINVAL, "pkb_dist_step_cols: bad argument");
+    pkb_ctx* ctx = h->ctx;
+    const ChainDims& d = h->d;
+    const FftPlan& plan = h->plan;
+    pkb_kset* ks = h->ks;
+    const int m = ks->hmeta[day].rad;
+    const double* K = ks->acc.p + (size_t)ks->W * ks->W * day;
+    const size_t sm1 = fft_smem_bytes(plan);
+    LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), plan.threads, sm1, K, ks->W, m, d, h->Krt.p, plan);
+    const int ncol = h->g.c1 - h->g.c0;
+    if (ncol > 0)
+        LAUNCH(ctx, k_cols_dist, std::min(ncol, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)h->Yt.p, (const cplx*)h->Krt.p, m, d, h->send,
+               h->cscr.p, plan, h->Shat.p, h->hstride, h->g, h->first ? 1 : 0);
+    h->first = false;
+    return check_launches(ctx, "pkb_dist_step_cols");
+}
+
+extern "C" int pkb_dist_step_rows(pkb_dist* h) {
+    if (!h) return fail(PKB_EINVAL, "pkb_dist_step_rows: NULL handle");
+    pkb_ctx* ctx = h->ctx;
+    const FftPlan& plan = h->plan;
+    const int njobs = (h->g.j1 - h->g.j0 + 1) / 2;
+    LAUNCH(ctx, k_rows_inv_dist, std::max(1, std::min(njobs, plan.grid_rows)), plan.threads, fft_smem_bytes(plan), (const cplx*)h->recv, h->d, h->Sloc.p,
+           h->ldL, h->rstat.p, 1e-8, plan, h->done.p, h->stats, h->g);
+    return check_launches(ctx, "pkb_dist_step_rows");
+}
+
+extern "C" int pkb_dist_step_emit(pkb_dist* h, int day) {
+    if (!h || day < 1 || day >= h->nd) return fail(PKB_EINVAL, "pkb_dist_step_emit: bad argument");
+    pkb_ctx* ctx = h->ctx;
+    LAUNCH(ctx, k_emit_dist, h->g.Jr, 256, 0, (const double*)h->Sloc.p, h->ldL, h->d, (const double*)h->allstats, h->g, 1e-8,
+           h->out + (size_t)day * h->g.Jr * h->d.D, h->meta.p + 4 * (size_t)day, h->worst.p);
+    return check_launches(ctx, "pkb_dist_step_emit");
+}
+
+extern "C" int pkb_dist_finish(pkb_dist* h, double* meta, int* ok) {
+    if (!h || !ok) return fail(PKB_EINVAL, "pkb_dist_finish: NULL argument");
+    pkb_ctx* ctx = h->ctx;
+    std::vector<double> hm((size_t)h->nd * 4);
+    CU(cudaMemcpyAsync(hm.data(), h->meta.p, sizeof(double) * hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sync_check(ctx, "pkb_dist_finish"));
+    // the criterion of chain.cuh (PKB_SPEC_EPS per day, PKB_SPEC_BUDGET accumulated) on the global maxima
+    double emax = 0.0, esum = 0.0;
+    int good = 1;
+    for (int n = 1; n < h->nd; ++n) {
+        const double pa = hm[4 * n + 3], pm = hm[4 * n + 2];
+        emax = std::max(emax, pa);
+        esum += 2.0 * emax;
+        if (!(pa <= PKB_SPEC_EPS) || pm > 1e-8 || !(esum <= PKB_SPEC_BUDGET)) good = 0;
+    }
+    if (meta) memcpy(meta, hm.data(), sizeof(double) * hm.size());
+    *ok = good;
+    return 0;
+}
+
+extern "C" int pkb_dist_destroy(pkb_dist* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    delete h;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -1770,8 +2043,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (lo < 0 || hi >= D) break;
         }
     }
-    const bool spec_try = ctx->use_spectral && (a->prob_model || a->r_dur == 1) && reach >= ctx->spec_min_reach;
-    ch->fixed_torus = spec_try;
+    const bool spec_arm = ctx->use_spectral && (a->prob_model || a->r_dur == 1) && reach >= ctx->spec_min_reach;
+    const int spec_try = spec_arm ? (a->prob_model ? 2 : 1) : 0;      // (row windows: the emission of the probability model knows about them)
+    ch->fixed_torus = spec_arm;
     const ChainDims d = ch->d;
     res->P = d.P;
     res->N = d.N;
@@ -1828,6 +2102,11 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         *out = nullptr;
         *out_t = nullptr;
         if (krad(n) <= ctx->stencil_max_radius) return 0;
+        if (kr_wait && !side) {     // first request by the chain since a block was launched on the side stream: join it BEFORE
+            // anything else touches krt_all* (a relaunch below would otherwise race with that block's writes)
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kr[1], 0));
+            kr_wait = false;
+        }
         if (kr_first < 0 || n >= kr_first + kr_chunk) {
             kr_first = n;
             const int cnt = std::min(kr_chunk, nd - n);
@@ -1878,10 +2157,6 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                 CU(cudaEventRecord(ctx->ev_kr[1], ctx->aux));
                 kr_wait = true;
             }
-        }
-        if (kr_wait && !side) {     // first use by the chain of a block that was launched on the side stream
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kr[1], 0));
-            kr_wait = false;
         }
         *out = krt_all.p + krt_stride * (n - kr_first);
         if (krt_all_t.p) {
@@ -1984,9 +2259,10 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         const int first = a->prob_model ? 1 : a->r_dur;
         int nf = -1;
         for (int n = first; n < nd && nf < 0; ++n)
-            if (krad(n) > ctx->stencil_max_radius) nf = n;
-        // (the block starts at the first day the chain will ask for, exactly as the lazy path would)
-        if (nf >= 0 && nf == first) {
+            if (krad(n) > ctx->stencil_max_radius && win_slot[n] < 0) nf = n;
+        // (the block starts at the first day the chain will ask these spectra for -- the first FFT step that is not a
+        // support-window step, known from the dry run above -- exactly as the lazy path would)
+        if (nf >= 0) {
             cplx *k0 = nullptr, *k1 = nullptr;
             TRY(day_spectra(nf, &k0, &k1, true));
         }
@@ -1996,8 +2272,8 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         TRY(set_state_kernel_dev(ch, kern(0), ks->W, krad(0)));
         if (!lead) {
             if (sink) LAUNCH(ctx, k_copy_domain_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, sink->cells, sink->K, sink->out);
-            else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p);
-            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p);
+            else LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->dense.p, (const StepMeta*)nullptr);
+            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p, (const StepMeta*)nullptr);
             TRY(emitted(0, ctx->stream));
         }
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
@@ -2013,7 +2289,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
-            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * (n - lead));
+            if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * (n - lead), (const StepMeta*)(dsm.p + n));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
@@ -2284,6 +2560,7 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         lane->use_trunc_torus = ctx->use_trunc_torus;
         lane->use_spectral = ctx->use_spectral;
         lane->spec_min_reach = ctx->spec_min_reach;
+        lane->use_rowwin = ctx->use_rowwin;
         lane->ring_tol = ctx->ring_tol;
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;

@@ -468,7 +468,7 @@ def test_step_torus_matches_chain_torus(pkb):
 
 
 def test_spectral_steps_match_exact_steps(pkb):
-    """Option spectral: while the content outside the domain is below 1e-14 the chain keeps the product spectrum
+    """Option spectral: while the content outside the domain is below 1e-13 the chain keeps the product spectrum
     k_cols forms anyway and starts the next step from it (the reference's own chain state is spectral,
     CalcSol.py:66,189-201) instead of re-transforming the folded real state.  The device decides per step; the
     bound on the difference is 1e-12 (chain.cuh).  Calm wind: the mass stays inside, spectral steps must happen
@@ -486,7 +486,7 @@ def test_spectral_steps_match_exact_steps(pkb):
     drift[:, :, 2] = np.hypot(drift[:, :, 0], drift[:, :, 1])
     args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
     ctx = pkb._lib.ctx()
-    seen_spec = seen_flag = 0
+    seen_spec = seen_flag = seen_rows = 0
     try:
         for windows in (0, 1):
             ctx.set_option('windows', windows)
@@ -498,10 +498,12 @@ def test_spectral_steps_match_exact_steps(pkb):
                         with warnings.catch_warnings():
                             warnings.simplefilter('ignore')
                             res = pkb.Run.solve(wind, nd, *args, want_coo=False, want_dense=True, keep_pre=True, **kw)
-                        out[sp] = ([res.dense(d) for d in range(nd)], res.flags(), res.spectral_steps(), [res.pre(d) for d in range(nd)])
+                        out[sp] = ([res.dense(d) for d in range(nd)], res.flags(), res.spectral_steps(), [res.pre(d) for d in range(nd)],
+                                   res.row_windows())
                         res.close()
                     assert out[0][2] == []
                     assert out[1][1] == out[0][1]
+                    seen_rows += sum(1 for w_ in out[1][4] if w_ is not None)
                     # a spectral step never follows a flagged state
                     assert not any(out[1][1][d - 1] for d in out[1][2])
                     seen_spec += len(out[1][2])
@@ -518,6 +520,7 @@ def test_spectral_steps_match_exact_steps(pkb):
         ctx.set_option('spectral', 1)
         ctx.set_option('windows', 1)
     assert seen_spec >= 8, 'no spectral-resident steps in the calm case'
+    assert seen_rows >= 4, 'no row-windowed spectral step (option spectral_rows) in the calm case'
     assert seen_flag > 0, 'no flagged step in the drift case'
 
 
