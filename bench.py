@@ -767,24 +767,28 @@ def main():
     prof = {k: ctx.profile_get(k) for k in kernels}
     chain_k = ['k_rows_fwd', 'k_cols', 'k_rows_inv', 'k_kernel_rows', 'k_kernel_rows_batch', 'k_emit_dense', 'k_step_finalize', 'k_zero_pad']
     phase1_ms = sum(prof[k][1] for k in ('k_period', 'k_day_finalize', 'k_drift', 'k_hprob', 'k_bvn_setup'))
-    nsteps_chain = prof['k_cols'][0]
+    nsteps_chain = prof['k_cols'][0] + prof['k_cols_win'][0]
     peak, peak_src = peaks()
-    dom = max(chain_k, key=lambda k: prof[k][1])
-    # algorithmic bytes per launch of each chain kernel = its share of B_day; the
-    # per-kernel roofline is taken on the whole-torus launches only (support-window steps run the same
-    # kernels on a smaller torus and are accounted separately as k_*_win)
+    # algorithmic bytes per launch of each chain kernel = its share of B_day.  Support-window
+    # steps run the same three kernels on a torus sized for the (numerical) support of the state; they are profiled
+    # under k_*_win and belong to the same family: a launch of either kind advances one simulated day.
     share = {'k_rows_fwd': 8.0 * P * P,                      # kernel/state row pass: write one half-spectrum
              'k_cols': 40.0 * P * P,                         # column pass + multiply (24 P^2) and inverse column pass (16 P^2)
              'k_rows_inv': 16.0 * P * P,                     # inverse row pass: read half-spectrum, write real grid
-             'k_emit_dense': 16.0 * D * D,                   # renormalised output: read + write the domain
-             'k_kernel_rows': 0.0, 'k_kernel_rows_batch': 0.0, 'k_step_finalize': 0.0, 'k_zero_pad': 0.0}
-    cnt, ms = prof[dom]
+             'k_emit_dense': 16.0 * D * D}                   # renormalised output: read + write the domain
+    fam = {k: (prof[k][0] + prof.get(k + '_win', (0, 0.0))[0], prof[k][1] + prof.get(k + '_win', (0, 0.0))[1]) for k in share}
+    dom = max(('k_rows_fwd', 'k_cols', 'k_rows_inv'), key=lambda k: fam[k][1])
+    cnt, ms = fam[dom]
     roofline = None
     if cnt:
         ach = share[dom] / (ms / cnt / 1000.0) / 1e9
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': None if batch_mode else traffic_from_profiles(dom), 'peak_source': peak_src, 'launches': cnt,
-                    'avg_launch_ms': ms / cnt, 'algorithmic_bytes_per_launch': share[dom]}
+                    'avg_launch_ms': ms / cnt, 'algorithmic_bytes_per_launch': share[dom],
+                    'launches_on_support_windows': prof.get(dom + '_win', (0, 0.0))[0],
+                    'note': 'algorithmic bytes are SURVEY.md 8d\'s share of B_day(P) for one simulated day; launches on a support window move '
+                            'fewer bytes than that (cells below 1e-15 are neither transformed nor stored), which is how frac can exceed 1',
+                    'family_ms_per_solve': {k: round(fam[k][1] / args.steps, 4) for k in fam}}
     roofline_chain = None
     if nsteps_chain and not batch_mode and chain_total_ms > 0:      # batch mode: proposals differ in torus size; the per-kernel roofline above still applies
         nflag = sum(1 for f in flags if f)
@@ -837,7 +841,8 @@ def main():
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
                            'support_window_steps': window_steps, 'spectral_resident_steps': spectral_steps,
                            'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if (world > 1 or batch_mode) else 'single solve',
-                           'l2': 'working set per chain step (%.0f MB) exceeds the 126 MB L2; no explicit flush' % (3 * 8.0 * P * P / 1e6)},
+                           'l2': 'every solve writes %.1f GB of dense daily solutions (> 126 MB L2) between two timed solves; whole-torus chain '
+                                 'steps work on %.0f MB; no explicit flush' % (ndays * 8.0 * D * D / 1e9, 3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'roofline_chain': roofline_chain,
                 'roofline_phase1': None if batch_mode else phase1_roofline(prof['k_period'], ndays, int(wind.shape[1]), args.steps)}

@@ -78,8 +78,10 @@ typedef struct pkb_step_meta {
     long long kcnt;
     int flag;     /* boundary flag, CalcSol.py:36-40 */
     int spec;     /* this step started from the stored spectrum of the state (option "spectral") */
-    int wr0, wr1; /* spectral-resident step restricted to the rows [wr0, wr1) that can hold anything above 1e-15
-                   * (option "spectral_rows"); wr1 <= wr0: all rows */
+    int wr0, wr1; /* the step only computed the rows [wr0, wr1) -- the others hold nothing above 1e-15 (support-window
+                   * steps, option "tau_windows"; spectral-resident steps, option "spectral_rows"); wr1 <= wr0: all rows */
+    int wc0, wc1; /* ... and the columns [wc0, wc1) (support-window steps) */
+    int er0, er1, ec0, ec1;   /* measured extent [er0, er1) x [ec0, ec1) of the cells >= 1e-15 of the day's state */
 } pkb_step_meta;
 
 const char* pkb_last_error(void);
@@ -96,6 +98,8 @@ int pkb_sync(pkb_ctx* ctx);
  * "trunc_torus" (0/1: steps from a truncated (flagged) state on a torus >= dom_len + 2m, default 1),
  * "spectral" (0/1: spectral-resident chain steps while the content outside the domain is below 1e-13, default 1;
  *             the one option whose results differ by more than rounding: by at most 1e-11, see chain.cuh),
+ * "tau_windows" (0/1: support-window steps follow the numerical support -- cells >= 1e-15 -- instead of the exact one,
+ *                default 1; "tau_lag": they use the extent measured this many steps back, default 1),
  * "spectral_rows" (0/1: such a step inverse-transforms only the rows that can hold a cell above 1e-15, default 1),
  * "spectral_min_reach" (arm them only if the exact support stays inside the domain for this many steps, default 4),
  * "ring_tol" (support-ring decisions of get_mvn_cdf_values closer than this to cdf_eps are re-taken with the reference's

@@ -231,11 +231,20 @@ class SolveResult(object):
         return [d for d in range(self.ndays) if self.day_meta(d)[1].spec]
 
     def row_windows(self):
-        """(first row, one past the last row) a spectral-resident step computed on each day, None where all rows."""
+        """(first row, one past the last row) the step of each day computed, None where all rows."""
         out = []
         for d in range(self.ndays):
             sm = self.day_meta(d)[1]
             out.append((sm.wr0, sm.wr1) if sm.wr1 > sm.wr0 else None)
+        return out
+
+    def regions(self):
+        """Per day (rows computed, columns computed, measured extent of the cells >= 1e-15) as
+        ((wr0, wr1), (wc0, wc1), (er0, er1, ec0, ec1))."""
+        out = []
+        for d in range(self.ndays):
+            sm = self.day_meta(d)[1]
+            out.append(((sm.wr0, sm.wr1), (sm.wc0, sm.wc1), (sm.er0, sm.er1, sm.ec0, sm.ec1)))
         return out
 
     def radii(self):

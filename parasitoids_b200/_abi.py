@@ -39,7 +39,8 @@ class DayMeta(C.Structure):
 class StepMeta(C.Structure):
     _fields_ = [('padmax', C.c_double), ('ksum', C.c_double), ('add', C.c_double), ('padabs', C.c_double),
                 ('kcnt', C.c_longlong), ('flag', C.c_int), ('spec', C.c_int),
-                ('wr0', C.c_int), ('wr1', C.c_int)]
+                ('wr0', C.c_int), ('wr1', C.c_int), ('wc0', C.c_int), ('wc1', C.c_int),
+                ('er0', C.c_int), ('er1', C.c_int), ('ec0', C.c_int), ('ec1', C.c_int)]
 
 
 class SolveArgs(C.Structure):

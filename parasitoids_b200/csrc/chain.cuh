@@ -111,7 +111,7 @@ struct ChainCtrl {
     double eps_sum;   // bound on the deviation from the exact fold mod P accumulated since the state went spectral
     double eps_max;   // largest outside-domain content seen since then
     int er0, er1;     // rows [er0, er1) hold every cell of this state with |value| >= PKB_SPEC_TAU (er1 <= er0: unknown)
-    int pad_[2];
+    int ec0, ec1;     // the same for columns (measured by support-window steps only; ec1 <= ec0: unknown)
 };
 
 // Spectral-resident state.  The reference keeps its chain state in Fourier space and only inverse-transforms
@@ -163,6 +163,8 @@ struct StepMeta {   // one per emitted solution
     int flag;
     int spec;    // this step started from the stored spectrum (spectral-resident step)
     int wr0, wr1;   // rows [wr0, wr1) of the state were computed, the others are below PKB_SPEC_TAU (wr1 <= wr0: all rows)
+    int wc0, wc1;   // ... and columns [wc0, wc1) (support-window steps; wc1 <= wc0: all columns)
+    int er0, er1, ec0, ec1;   // measured extent of the cells >= PKB_SPEC_TAU of this state (copy of ChainCtrl's)
 };
 
 // ---------------------------------------------------------------------------
@@ -529,7 +531,9 @@ struct SpecIn {
     int stored;        // k_cols of this step wrote the product spectrum
     int was_spec;      // this step itself started from Shat
     double eps_sum, eps_max;
-    int rowwin, w0, w1;   // only the rows [w0, w1) were computed (spec_row_window)
+    int rowwin, w0, w1;   // only the rows [w0, w1) were computed (spec_row_window, or a support-window step)
+    int c0, c1;           // ... and only the columns [c0, c1) (support-window step; c1 <= c0: all)
+    int* colflag;         // optional [P]: columns in which this step saw a cell >= PKB_SPEC_TAU (cleared again here)
 };
 
 // Flag / kept sum / kept count / largest outside-domain magnitude of a state from its per-row statistics
@@ -569,9 +573,11 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
         meta->spec = si.was_spec;
         meta->wr0 = si.rowwin ? si.w0 : 0;
         meta->wr1 = si.rowwin ? si.w1 : 0;
+        meta->wc0 = si.c1 > si.c0 ? si.c0 : 0;
+        meta->wc1 = si.c1 > si.c0 ? si.c1 : 0;
         ctrl->flag = flag;
-        ctrl->er0 = red[71] >= 0.0 ? (int)(-red[68]) : 0;
-        ctrl->er1 = red[71] >= 0.0 ? (int)red[71] + 1 : 0;
+        meta->er0 = ctrl->er0 = red[71] >= 0.0 ? (int)(-red[68]) : 0;
+        meta->er1 = ctrl->er1 = red[71] >= 0.0 ? (int)red[71] + 1 : 0;
         // a fresh convolution result is a full P x P state; it becomes a
         // truncated one only where the caller applies CalcSol.py:200-201
         ctrl->trunc = apply_trunc ? flag : 0;
@@ -586,6 +592,27 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
         ctrl->eps_sum = spec ? esum : 0.0;
         ctrl->eps_max = spec ? emax : 0.0;
     }
+    // column extent of the cells >= PKB_SPEC_TAU (support-window steps mark the columns in colflag)
+    if (si.colflag) {
+        __syncthreads();
+        double cs[8] = {-INFINITY, 0.0, 0.0, -INFINITY, -INFINITY, 0.0, 0.0, -INFINITY};
+        for (int c = tid; c < d.P; c += T)
+            if (si.colflag[c]) {
+                cs[0] = fmax(cs[0], -(double)c);
+                cs[3] = fmax(cs[3], (double)c);
+                si.colflag[c] = 0;
+            }
+        const double cr = block_reduce8(cs, red, tid, T);
+        if (tid < 4) red[64 + tid] = cr;
+        __syncthreads();
+        if (tid == 0) {
+            meta->ec0 = ctrl->ec0 = red[67] >= 0.0 ? (int)(-red[64]) : 0;
+            meta->ec1 = ctrl->ec1 = red[67] >= 0.0 ? (int)red[67] + 1 : 0;
+        }
+    } else if (tid == 0) {
+        meta->ec0 = ctrl->ec0 = 0;
+        meta->ec1 = ctrl->ec1 = 0;
+    }
 }
 
 // grid = 1, block = 256 (stencil path and re-thresholding; the FFT path finalises
@@ -593,7 +620,7 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
 __global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* ctrl, StepMeta* __restrict__ meta,
                                 int apply_trunc, double flag_thresh) {
     PKB_SHARED(double, red, PKB_RED_DOUBLES);
-    SpecIn si = {0, 0, 0.0, 0.0, 0, 0, 0};
+    SpecIn si = {0, 0, 0.0, 0.0, 0, 0, 0, 0, 0, nullptr};
     step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x, si, flag_thresh);
 }
 
@@ -657,9 +684,9 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* ctrl, StepMeta* __restrict__ meta, int apply_trunc,
                                        cplx* __restrict__ Yt_next, const ChainCtrl* src_ctrl, TruncGeom tg, FftPlan plan_t,
-                                       int desc_order, int rowwin_ok) {
+                                       int desc_order, int rowwin_ok, int* __restrict__ colflag) {
     const volatile ChainCtrl* sc = src_ctrl;
-    SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max, 0, 0, 0};
+    SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max, 0, 0, 0, 0, 0, nullptr};
     const bool tr = tg.N && !d.win && sc->trunc;      // truncated source on its smaller torus (TruncGeom)
     // row window of a spectral-resident step (the same decision k_cols took from the same control block)
     si.rowwin = (!tr && !d.win && spec_row_window(rowwin_ok, si.was_spec, sc->er0, sc->er1, si.eps_sum, si.eps_max, m, d.D, si.w0, si.w1)) ? 1 : 0;
@@ -683,6 +710,13 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     __syncthreads();
     const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
     const int wout = d.wn + 2 * m;                       // window mode: side of the result
+    if (d.win) {
+        // only the rows / columns of the result window carry statistics of this step (windows may move and shrink
+        // from day to day when they follow the numerical support, pkb200.cu: tau windows)
+        si.rowwin = 1; si.w0 = d.wr0 - m; si.w1 = d.wr0 - m + wout;
+        si.c0 = d.wc0 - m; si.c1 = d.wc0 - m + wout;
+        si.colflag = colflag;
+    }
     const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : (si.rowwin ? (si.w1 - si.w0) / 2 : rows_inv_jobs(P, m)));
     const double scale = 1.0 / ((double)N * (double)N);
     const cplx zero = cmake(0.0, 0.0);
@@ -809,13 +843,17 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             }
             const double va = (fold ? z.x + z.y : z.x) * scale;
             dst_a[c] = va;
-            e_a |= fabs(va) >= PKB_SPEC_TAU;
+            const bool ea1 = fabs(va) >= PKB_SPEC_TAU;
+            e_a |= ea1;
+            if (ea1 && si.colflag) si.colflag[col0 + c] = 1;
             if (pad_a || c >= Dc) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
             else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
             if (out_b >= 0) {
                 const double vb = z.y * scale;
                 dst_b[c] = vb;
-                e_b |= fabs(vb) >= PKB_SPEC_TAU;
+                const bool eb1 = fabs(vb) >= PKB_SPEC_TAU;
+                e_b |= eb1;
+                if (eb1 && si.colflag) si.colflag[col0 + c] = 1;
                 if (pad_b || c >= Dc) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
                 else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
             }
@@ -866,6 +904,16 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     }
 }
 
+// S[r][c] = 0 outside the rows [r0, r1) x columns [c0, c1): leaving support-window mode, whose windows may have moved
+// and left older days' cells elsewhere in the buffer.  grid = P, block = 256
+__global__ void k_zero_outside(double* __restrict__ S, ChainDims d, int r0, int r1, int c0, int c1) {
+    const int r = blockIdx.x;
+    double* row = S + (size_t)r * d.ldS;
+    const bool inside = r >= r0 && r < r1;
+    for (int c = threadIdx.x; c < d.P; c += blockDim.x)
+        if (!inside || c < c0 || c >= c1) row[c] = 0.0;
+}
+
 // get_cursol's "Re-fft" decision taken after the fact (cuda_lib.py:130-136)
 __global__ void k_apply_trunc(ChainCtrl* __restrict__ ctrl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->trunc = ctrl->flag;
@@ -886,6 +934,7 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
     PKB_SHARED(int, cnt, 1);
     const double add = prob_model ? meta->add : 0.0;
     const int wr0 = meta->wr0, wr1 = meta->wr1;          // row-windowed step: the other rows were not computed (all below PKB_SPEC_TAU)
+    const int wc0 = meta->wc1 > meta->wc0 ? meta->wc0 : 0, wc1 = meta->wc1 > meta->wc0 ? meta->wc1 : d.D;      // ... and columns
     // rows blockIdx.x, blockIdx.x + gridDim.x, ...: one CTA per row (grid = D), or a few small persistent
     // CTAs that trickle through the day next to the FFT kernels of the following step (fused solve)
     for (int r = blockIdx.x; r < d.D; r += gridDim.x) {
@@ -907,7 +956,7 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
         for (; c + 3 * T < d.D; c += 4 * T) {          // four independent loads in flight per thread
             double v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = src[c + u * T];
+            for (int u = 0; u < 4; ++u) v[u] = (c + u * T >= wc0 && c + u * T < wc1) ? src[c + u * T] : 0.0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool keep = strict ? (v[u] > negval) : (v[u] != 0.0 && !(v[u] < negval));
@@ -917,7 +966,7 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
             }
         }
         for (; c < d.D; c += T) {
-            const double v = src[c];
+            const double v = (c >= wc0 && c < wc1) ? src[c] : 0.0;
             const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
             const double o = keep ? v + add : 0.0;
             dst[c] = o;
@@ -946,7 +995,9 @@ __global__ void k_zero_pad(double* __restrict__ S, ChainDims d, const ChainCtrl*
 __global__ void k_copy_domain(const double* __restrict__ S, ChainDims d, double* __restrict__ out, const StepMeta* __restrict__ meta) {
     const int r = blockIdx.x;
     const bool skip = meta && meta->wr1 > meta->wr0 && (r < meta->wr0 || r >= meta->wr1);
-    for (int c = threadIdx.x; c < d.D; c += blockDim.x) out[(size_t)r * d.D + c] = skip ? 0.0 : S[(size_t)r * d.ldS + c];
+    const int wc0 = (meta && meta->wc1 > meta->wc0) ? meta->wc0 : 0, wc1 = (meta && meta->wc1 > meta->wc0) ? meta->wc1 : d.D;
+    for (int c = threadIdx.x; c < d.D; c += blockDim.x)
+        out[(size_t)r * d.D + c] = (skip || c < wc0 || c >= wc1) ? 0.0 : S[(size_t)r * d.ldS + c];
 }
 
 // Place a dense centred kernel window (Wk x Wk, radius used: m) into a zeroed
@@ -1012,9 +1063,12 @@ __global__ void k_emit_dense_cells(const double* __restrict__ S, ChainDims d, co
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     const double add = prob_model ? meta->add : 0.0;
-    const int r = cells[2 * k];
-    if (meta->wr1 > meta->wr0 && (r < meta->wr0 || r >= meta->wr1)) { out[k] = 0.0; return; }      // row-windowed step
-    const double v = S[(size_t)r * d.ldS + cells[2 * k + 1]];
+    const int r = cells[2 * k], cc = cells[2 * k + 1];
+    if ((meta->wr1 > meta->wr0 && (r < meta->wr0 || r >= meta->wr1)) || (meta->wc1 > meta->wc0 && (cc < meta->wc0 || cc >= meta->wc1))) {
+        out[k] = 0.0;                                   // outside the rows / columns this step computed (all below PKB_SPEC_TAU)
+        return;
+    }
+    const double v = S[(size_t)r * d.ldS + cc];
     const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
     out[k] = keep ? v + add : 0.0;
 }

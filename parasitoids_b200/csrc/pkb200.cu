@@ -107,6 +107,10 @@ struct pkb_ctx {
     int use_fusion;         // fused solve: inverse row pass + next forward row pass in one kernel (option "fuse_rows")
     int use_trunc_torus;    // steps from a truncated (flagged) state on a torus >= D + 2m (option "trunc_torus")
     double ring_tol;        // ring-growth decisions closer than this to cdf_eps are re-taken in the reference's summation order (option "ring_tol")
+    int use_tau_windows;    // fused solve: support windows follow the NUMERICAL support (cells >= 1e-15) instead of the exact one (option "tau_windows")
+    int tau_lag;            // ... using the extent measured this many steps back (option "tau_lag": the host never waits for the step in flight)
+    std::vector<cudaEvent_t> box_events;
+    cudaEvent_t ring_events[4];
     int use_rowwin;         // ... restricted to the rows that can hold anything (option "spectral_rows", chain.cuh PKB_SPEC_TAU)
     int spec_min_reach;     // ... armed only if the exact support stays inside the domain for this many steps (option "spectral_min_reach")
     int use_spectral;       // fused solve: spectral-resident steps while nothing of consequence lies outside the domain (option "spectral")
@@ -343,6 +347,9 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_spectral = 1;
     ctx->spec_min_reach = 4;
     ctx->use_rowwin = 1;
+    ctx->use_tau_windows = 1;
+    ctx->tau_lag = 1;
+    for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&ctx->ring_events[i], cudaEventDisableTiming));
     ctx->ring_tol = 1e-12;
     ctx->occ_cap = 4;
     if (const char* env = getenv("PKB_FFT_OCC")) ctx->occ_cap = std::max(1, std::min(16, atoi(env)));
@@ -415,6 +422,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_emit[i]); }
     for (cudaEvent_t e : ctx->day_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->win_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->box_events) cudaEventDestroy(e);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ring_events[i]);
     cudaEventDestroy(ctx->ev_cp);
     cudaStreamDestroy(ctx->cp);
     cudaStreamDestroy(ctx->aux);
@@ -455,6 +464,15 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "ring_tol")) {
         if (!(value >= 0)) return fail(PKB_EINVAL, "ring_tol must be >= 0");
         ctx->ring_tol = value;
+        return 0;
+    }
+    if (!strcmp(key, "tau_windows")) {
+        ctx->use_tau_windows = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "tau_lag")) {
+        if (value < 1 || value > 8) return fail(PKB_EINVAL, "tau_lag must be 1..8");
+        ctx->tau_lag = (int)value;
         return 0;
     }
     if (!strcmp(key, "spectral_rows")) {
@@ -1122,6 +1140,7 @@ struct pkb_chain {
     size_t hstride;
     bool fixed_torus;       // every whole-torus step runs on the chain's own torus (spectral-resident steps need one torus)
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
+    DBuf<int> colflag;      // [P] columns in which a support-window step saw a cell >= PKB_SPEC_TAU (cleared by its finalize)
     size_t cscr_per_cta;
     int grid_rows, grid_cols;
     DBuf<RowStats> rstat;
@@ -1178,6 +1197,8 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     TRY(ch->rstat.alloc(ctx, d.P));
     TRY(ch->done.alloc(ctx, 1));
     CU(cudaMemsetAsync(ch->done.p, 0, sizeof(int), ctx->stream));
+    TRY(ch->colflag.alloc(ctx, d.P));
+    CU(cudaMemsetAsync(ch->colflag.p, 0, sizeof(int) * d.P, ctx->stream));
     CU(cudaMemsetAsync(ch->rstat.p, 0, sizeof(RowStats) * d.P, ctx->stream));    // rows a windowed step never touches are zero rows
     TRY(ch->ctrl.alloc(ctx, 1 + PKB_MAX_COHORTS));
     TRY(ch->meta.alloc(ctx, 1 + PKB_MAX_COHORTS));
@@ -1342,7 +1363,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0, 0);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0, ch->colflag.p);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
@@ -1360,7 +1381,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
            ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride, rowwin_ok);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
            ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc,
-           rowwin_ok);
+           rowwin_ok, (int*)nullptr);
     return 0;
 }
 
@@ -1855,6 +1876,7 @@ struct pkb_result {
     DBuf<long long> daytot; // [ndays][2]: (0, non-zeros of the day)
     HBuf<long long> tot_host;
     std::vector<char> counted;   // days whose rownnz the emission kernel already filled
+    std::vector<char> day_ready; // days whose row counts / event have been enqueued (coo_day_ready)
     HBuf<long long> dayoff;
     HBuf<int> rows, cols;
     HBuf<double> vals;
@@ -1866,7 +1888,7 @@ struct pkb_result {
 // scanned on the emitting stream (coo_day_ready); once the whole chain has been
 // ENQUEUED the host walks the days in order, learns each day's size from an
 // 16-byte D2H, and queues that day's compaction + triplet copy on the copy stream
-// (coo_collect) -- so the 16 bytes/non-zero cross PCIe while later days are still
+// (coo_pump) -- so the 16 bytes/non-zero cross PCIe while later days are still
 // being computed.
 static int coo_day_ready(pkb_ctx* ctx, pkb_result* r, int day, cudaStream_t strm) {
     const int D = r->D;
@@ -1877,6 +1899,7 @@ static int coo_day_ready(pkb_ctx* ctx, pkb_result* r, int day, cudaStream_t strm
               r->daytot.p + 2 * day);
     CU(cudaMemcpyAsync(r->tot_host.p + 2 * day, r->daytot.p + 2 * day, 2 * sizeof(long long), cudaMemcpyDeviceToHost, strm));
     CU(cudaEventRecord(ctx->day_events[day], strm));
+    r->day_ready[day] = 1;
     return 0;
 }
 
@@ -1891,58 +1914,68 @@ static int hbuf_grow(pkb_ctx* ctx, HBuf<T>& b, size_t used, size_t newcap) {
     return 0;       // nb's destructor returns the old block to the pool
 }
 
-static int coo_collect(pkb_ctx* ctx, pkb_result* r) {
-    const int D = r->D, nd = r->ndays;
-    const size_t nD = (size_t)D * D;
-    TRY(r->dayoff.alloc(ctx, nd + 1));
-    r->dayoff.p[0] = 0;
-    size_t cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)nd * D * 64);
-    TRY(r->rows.alloc(ctx, cap));
-    TRY(r->cols.alloc(ctx, cap));
-    TRY(r->vals.alloc(ctx, cap));
-    // one day's triplets at a time through a device staging area (worst case D*D entries)
+// Incremental form: coo_pump(block = false) handles the days whose dense solution already exists and returns; the
+// chain loop calls it after every step, so the triplets cross PCIe while later days are still being computed even
+// when the host paces the chain itself (tau windows wait for an older step's extent before every step).
+struct CooState {
     DBuf<int> srow, scol;
     DBuf<double> sval;
-    TRY(srow.alloc(ctx, nD));
-    TRY(scol.alloc(ctx, nD));
-    TRY(sval.alloc(ctx, nD));
-    const bool dbg = getenv("PKB_DEBUG_COO") != nullptr;
-    const auto t00 = std::chrono::steady_clock::now();
-    for (int day = 0; day < nd; ++day) {
-        cudaError_t e = cudaEventSynchronize(ctx->day_events[day]);
-        if (dbg && (day % 10 == 0 || day == nd - 1))
-            fprintf(stderr, "coo day %d ready at %.2f ms\n", day, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
+    size_t cap = 0;
+    int next_day = 0;
+    bool started = false;
+};
+
+static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
+    const int D = r->D, nd = r->ndays;
+    const size_t nD = (size_t)D * D;
+    if (!st->started) {
+        TRY(r->dayoff.alloc(ctx, nd + 1));
+        r->dayoff.p[0] = 0;
+        st->cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)nd * D * 64);
+        TRY(r->rows.alloc(ctx, st->cap));
+        TRY(r->cols.alloc(ctx, st->cap));
+        TRY(r->vals.alloc(ctx, st->cap));
+        // one day's triplets at a time through a device staging area (worst case D*D entries)
+        TRY(st->srow.alloc(ctx, nD));
+        TRY(st->scol.alloc(ctx, nD));
+        TRY(st->sval.alloc(ctx, nD));
+        st->started = true;
+    }
+    for (; st->next_day < nd; ++st->next_day) {
+        const int day = st->next_day;
+        if (!r->day_ready[day]) {
+            if (block) return fail(PKB_ESTATE, "COO collection: day %d was never emitted", day);
+            break;
+        }
+        cudaError_t e = block ? cudaEventSynchronize(ctx->day_events[day]) : cudaEventQuery(ctx->day_events[day]);
+        if (e == cudaErrorNotReady) break;
         if (e != cudaSuccess) return fail(PKB_ECUDA, "waiting for day %d of the solve failed: %s", day, cudaGetErrorString(e));
         const long long tot = r->tot_host.p[2 * day + 1];
         const size_t off = (size_t)r->dayoff.p[day];
         r->dayoff.p[day + 1] = (long long)(off + tot);
-        if (off + tot > cap) {
+        if (off + tot > st->cap) {
             CU(cudaStreamSynchronize(ctx->cp));                   // copies into the old blocks must have landed
-            const size_t newcap = std::max<size_t>(off + tot + (off + tot) / 4, cap * 2);
+            const size_t newcap = std::max<size_t>(off + tot + (off + tot) / 4, st->cap * 2);
             TRY(hbuf_grow(ctx, r->rows, off, newcap));
             TRY(hbuf_grow(ctx, r->cols, off, newcap));
             TRY(hbuf_grow(ctx, r->vals, off, newcap));
-            cap = newcap;
+            st->cap = newcap;
         }
         CU(cudaStreamWaitEvent(ctx->cp, ctx->day_events[day], 0));
         LAUNCH_ON(ctx, ctx->cp, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
-                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), srow.p, scol.p, sval.p);
+                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), st->srow.p, st->scol.p, st->sval.p);
         if (tot > 0) {
-            CU(cudaMemcpyAsync(r->rows.p + off, srow.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
-            CU(cudaMemcpyAsync(r->cols.p + off, scol.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
-            CU(cudaMemcpyAsync(r->vals.p + off, sval.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->rows.p + off, st->srow.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->cols.p + off, st->scol.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->vals.p + off, st->sval.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->cp));
         }
     }
-    if (dbg) {
-        cudaStreamSynchronize(ctx->stream);
-        fprintf(stderr, "chain done at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
-        cudaStreamSynchronize(ctx->cp);
-        fprintf(stderr, "copies done at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count());
+    if (block) {
+        CU(cudaEventRecord(ctx->ev_cp, ctx->cp));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp, 0));
+        ctx->coo_hint = (size_t)r->dayoff.p[nd];
+        r->have_coo = true;
     }
-    CU(cudaEventRecord(ctx->ev_cp, ctx->cp));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp, 0));
-    ctx->coo_hint = (size_t)r->dayoff.p[nd];
-    r->have_coo = true;
     return 0;
 }
 
@@ -2053,6 +2086,8 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     if (!sink) TRY(res->dense.alloc(ctx, nD * nout));
     if (!sink && a->keep_pre_device) TRY(res->pre.alloc(ctx, nD * nout));      // parity export (pkb_result_pre)
     res->counted.assign(nout, 0);
+    res->day_ready.assign(nout, 0);
+    CooState coo;
     if (a->want_coo) {
         TRY(res->rownnz.alloc(ctx, (size_t)nout * D));
         TRY(res->rowoff.alloc(ctx, (size_t)nout * D));
@@ -2065,7 +2100,11 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         }
     }
     // (day: chain day; nothing is emitted for the dropped leading day)
-    auto emitted = [&](int day, cudaStream_t strm) -> int { return a->want_coo && day >= lead ? coo_day_ready(ctx, res, day - lead, strm) : 0; };
+    auto emitted = [&](int day, cudaStream_t strm) -> int {
+        if (!a->want_coo || day < lead) return 0;
+        TRY(coo_day_ready(ctx, res, day - lead, strm));
+        return coo_pump(ctx, res, &coo, false);         // whatever is ready by now goes to the host
+    };
     DBuf<StepMeta> dsm, dcm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
@@ -2178,9 +2217,116 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     bool wmode = ctx->use_windows != 0;
     if (wmode) CU(cudaMemsetAsync(ch->S[1].p, 0, (size_t)d.P * d.ldS * sizeof(double), ctx->stream));
     int win[3];
+    // "tau windows" (probability model): the window follows the NUMERICAL support -- the extent of the cells with
+    // |value| >= PKB_SPEC_TAU = 1e-15, measured on the device by every window step (ChainCtrl::er0..ec1) and read by the
+    // host `tau_lag` steps late (pinned copy + event, so the host never waits for the step in flight).  A cell
+    // farther than m from that extent stays below TAU after the next convolution (a weighted average with unit mass),
+    // so state n - 1 has nothing above TAU outside  extent(n - L) grown by m_{n-L+1} .. m_{n-1} ; what a window step
+    // leaves out is charged to the same budget as the spectral-resident steps (<= 2 TAU per step).  The windows may
+    // shrink and move with the plume, so a day's emission only reads the region its step wrote (StepMeta::wr0..wc1).
+    struct Box {
+        int r0, r1, c0, c1;
+    };
+    const bool tau_mode_ok = wmode && ctx->use_tau_windows && a->prob_model;
+    bool tau_mode = tau_mode_ok;
+    std::vector<Box> reg(nd), meas(nd);
+    std::vector<char> have(nd, 0);
+    HBuf<int> hbox;
+    DBuf<cplx> krt_ring;
+    const int kRing = 4;
+    if (tau_mode) {
+        TRY(hbox.alloc(ctx, 4 * (size_t)nd));
+        TRY(krt_ring.alloc(ctx, krt_stride * kRing));
+        while ((int)ctx->box_events.size() < nd) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->box_events.push_back(e);
+        }
+        const int c0 = D / 2 - krad(0);
+        reg[0] = meas[0] = Box{c0, c0 + 2 * krad(0) + 1, c0, c0 + 2 * krad(0) + 1};
+        have[0] = 1;
+        CU(cudaEventRecord(ctx->ev_step[0], ctx->stream));            // the kernels exist (phase 1 ran on the main stream)
+        CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[0], 0));
+    }
+    int ring_used = 0;
+    // window of step n in tau mode (nullptr: the step cannot run as a window step any more -> whole-torus steps from here)
+    auto tau_window = [&](int n, int* rc) -> const int* {
+        *rc = 0;
+        const int m = krad(n), k = n - 1;
+        if (m <= ctx->stencil_max_radius) return nullptr;
+        const int src = std::max(0, n - std::max(1, ctx->tau_lag));
+        if (src >= 1 && !have[src]) {
+            cudaError_t e = cudaEventSynchronize(ctx->box_events[src]);
+            if (e != cudaSuccess) { *rc = fail(PKB_ECUDA, "waiting for the extent of day %d failed: %s", src, cudaGetErrorString(e)); return nullptr; }
+            const int* hb = hbox.p + 4 * src;
+            meas[src] = (hb[1] > hb[0] && hb[3] > hb[2]) ? Box{hb[0], hb[1], hb[2], hb[3]} : reg[src];
+            have[src] = 1;
+        }
+        Box b = have[src] ? meas[src] : reg[src];
+        for (int j = src + 1; j <= k; ++j) {
+            const int mj = krad(j);
+            b = Box{std::max(reg[j].r0, b.r0 - mj), std::min(reg[j].r1, b.r1 + mj), std::max(reg[j].c0, b.c0 - mj), std::min(reg[j].c1, b.c1 + mj)};
+        }
+        // square window of side s inside the region state k was written to
+        const Box& rk = reg[k];
+        const int s = std::min(std::max(b.r1 - b.r0, b.c1 - b.c0), std::min(rk.r1 - rk.r0, rk.c1 - rk.c0));
+        auto place = [&](int lo, int hi, int rlo, int rhi) {       // origin of a length-s interval covering [lo, hi) inside [rlo, rhi)
+            int o = lo - (s - (hi - lo)) / 2;
+            o = std::max(rlo, std::min(o, rhi - s));
+            return o;
+        };
+        const int or0 = place(b.r0, b.r1, rk.r0, rk.r1), oc0 = place(b.c0, b.c1, rk.c0, rk.c1);
+        if (or0 - m < 0 || oc0 - m < 0 || or0 + s + m > D || oc0 + s + m > D) return nullptr;
+        if (pkb_smooth_len(s + 2 * m) >= d.N) return nullptr;
+        win[0] = or0; win[1] = oc0; win[2] = s;
+        reg[n] = Box{or0 - m, or0 + s + m, oc0 - m, oc0 + s + m};
+        res->window_steps++;
+        return win;
+    };
+    // kernel row spectra of a tau-window step: just in time on the side stream, a ring of kRing slots
+    auto tau_spectra = [&](int n, const int* wp, cplx** out) -> int {
+        const int m = krad(n), slot = ring_used % kRing;
+        ChainDims dw = d;
+        FftPlan pw;
+        dw.N = pkb_smooth_len(std::max(2, wp[2] + 2 * m));
+        dw.Nc = dw.N / 2 + 1;
+        dw.ldK = roundup(2 * m + 1, 2);
+        TRY(get_plan(ctx, dw.N, &pw));
+        if (pw.grid_rows < 1) return fail(PKB_ELIMIT, "FFT kernels cannot be resident at torus side %d", dw.N);
+        if (ring_used >= kRing) CU(cudaStreamWaitEvent(ctx->aux, ctx->ring_events[slot], 0));      // the step that read this slot last is done
+        if (ctx->prof_on) prof_begin(ctx, "k_kernel_rows_win", ctx->aux);
+        PKB_LAUNCH(k_kernel_rows, std::min(m + 1, pw.grid_rows), pw.threads, fft_smem_bytes(pw), ctx->aux, kern(n), ks->W, m, dw,
+                   krt_ring.p + krt_stride * slot, pw);
+        if (ctx->prof_on) prof_end(ctx, ctx->aux);
+        ctx->launches++;
+        while ((int)ctx->win_events.size() < kRing) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->win_events.push_back(e);
+        }
+        CU(cudaEventRecord(ctx->win_events[slot], ctx->aux));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->win_events[slot], 0));
+        *out = krt_ring.p + krt_stride * slot;
+        return 0;
+    };
+    auto tau_after_step = [&](int n) -> int {          // the step has been enqueued: its slot may be reused, its extent travels to the host
+        CU(cudaEventRecord(ctx->ring_events[ring_used % kRing], ctx->stream));
+        ++ring_used;
+        CU(cudaMemcpyAsync(hbox.p + 4 * n, &ch->ctrl.p->er0, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->box_events[n], ctx->stream));
+        return 0;
+    };
+    // leaving tau mode before step n: older windows may have left cells outside the region of state n - 1
+    auto tau_leave = [&](int n) -> int {
+        const Box& rk = reg[n - 1];
+        LAUNCH(ctx, k_zero_outside, d.P, 256, 0, ch->S[ch->cur].p, d, rk.r0, rk.r1, rk.c0, rk.c1);
+        tau_mode = false;
+        wmode = false;
+        return 0;
+    };
     auto step_window = [&](int n) -> const int* {
         const int m = krad(n);
-        if (wmode && wr0 - m >= 0 && wr0 + wn + m <= D && pkb_smooth_len(wn + 2 * m) < d.N) {
+        if (wmode && !tau_mode_ok && wr0 - m >= 0 && wr0 + wn + m <= D && pkb_smooth_len(wn + 2 * m) < d.N) {
             win[0] = win[1] = wr0; win[2] = wn;
             wr0 -= m; wn += 2 * m;
             if (m <= ctx->stencil_max_radius) return nullptr;       // the stencil path works on the whole torus
@@ -2199,7 +2345,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     {
         const int first = a->prob_model ? 1 : a->r_dur;
         std::vector<std::array<int, 3> > wsteps;     // (day, window side, torus side)
-        if (a->prob_model || a->r_dur == 1) {
+        if ((a->prob_model || a->r_dur == 1) && !tau_mode_ok) {
             const int sv_wr0 = wr0, sv_wn = wn, sv_ws = res->window_steps;
             const bool sv_mode = wmode;
             for (int n = first; n < nd; ++n) {
@@ -2262,7 +2408,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (krad(n) > ctx->stencil_max_radius && win_slot[n] < 0) nf = n;
         // (the block starts at the first day the chain will ask these spectra for -- the first FFT step that is not a
         // support-window step, known from the dry run above -- exactly as the lazy path would)
-        if (nf >= 0) {
+        if (nf >= 0 && !tau_mode_ok) {      // (tau windows: which day leaves window mode depends on the data)
             cplx *k0 = nullptr, *k1 = nullptr;
             TRY(day_spectra(nf, &k0, &k1, true));
         }
@@ -2277,17 +2423,28 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(emitted(0, ctx->stream));
         }
         for (int n = 1; n < nd; ++n) {                                          // CalcSol.py:191-201
-            const int* wp = step_window(n);
+            const int* wp = nullptr;
             cplx* krt = nullptr;
             cplx* krt_t = nullptr;
+            bool tau_step = false;
+            if (tau_mode) {
+                int rcw = 0;
+                wp = tau_window(n, &rcw);
+                TRY(rcw);
+                if (wp) { TRY(tau_spectra(n, wp, &krt)); tau_step = true; }
+                else TRY(tau_leave(n));
+            } else {
+                wp = step_window(n);
+            }
             if (!wp) TRY(day_spectra(n, &krt, &krt_t));
-            else TRY(window_spectra(n, &krt));
+            else if (!tau_step) TRY(window_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
             const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
+            if (tau_step) TRY(tau_after_step(n));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * (n - lead), (const StepMeta*)(dsm.p + n));
             // r_small_vals + dense output on the side stream, overlapped with step n+1
@@ -2398,7 +2555,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     }
 
     // ---- outputs (the chain is enqueued, not finished: compaction and D2H overlap it) ----
-    if (a->want_coo) TRY(coo_collect(ctx, res));
+    if (a->want_coo) TRY(coo_pump(ctx, res, &coo, true));
     // (pageable destination: this copy blocks the host until the chain has finished, so it comes last)
     CU(cudaMemcpyAsync(res->smeta.data(), dsm.p + lead, sizeof(StepMeta) * nout, cudaMemcpyDeviceToHost, ctx->stream));
     if (want_cmeta) {
@@ -2561,6 +2718,8 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         lane->use_spectral = ctx->use_spectral;
         lane->spec_min_reach = ctx->spec_min_reach;
         lane->use_rowwin = ctx->use_rowwin;
+        lane->use_tau_windows = ctx->use_tau_windows;
+        lane->tau_lag = ctx->tau_lag;
         lane->ring_tol = ctx->ring_tol;
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
