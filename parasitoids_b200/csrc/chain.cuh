@@ -534,6 +534,8 @@ struct SpecIn {
     int rowwin, w0, w1;   // only the rows [w0, w1) were computed (spec_row_window, or a support-window step)
     int c0, c1;           // ... and only the columns [c0, c1) (support-window step; c1 <= c0: all)
     int* colflag;         // optional [P]: columns in which this step saw a cell >= PKB_SPEC_TAU (cleared again here)
+    int* host_box;        // optional, MAPPED PINNED HOST memory [6]: the measured extent (er0, er1, ec0, ec1), then a ticket the
+    int ticket;           //   host spins on -- written straight from the kernel so that the host learns it microseconds later
 };
 
 // Flag / kept sum / kept count / largest outside-domain magnitude of a state from its per-row statistics
@@ -608,6 +610,12 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
         if (tid == 0) {
             meta->ec0 = ctrl->ec0 = red[67] >= 0.0 ? (int)(-red[64]) : 0;
             meta->ec1 = ctrl->ec1 = red[67] >= 0.0 ? (int)red[67] + 1 : 0;
+            if (si.host_box) {
+                volatile int* hb = si.host_box;
+                hb[0] = ctrl->er0; hb[1] = ctrl->er1; hb[2] = ctrl->ec0; hb[3] = ctrl->ec1;
+                __threadfence_system();
+                hb[4] = si.ticket;
+            }
         }
     } else if (tid == 0) {
         meta->ec0 = ctrl->ec0 = 0;
@@ -620,7 +628,7 @@ __device__ __forceinline__ void step_finalize_block(const RowStats* rstat, const
 __global__ void k_step_finalize(const RowStats* __restrict__ rstat, ChainDims d, ChainCtrl* ctrl, StepMeta* __restrict__ meta,
                                 int apply_trunc, double flag_thresh) {
     PKB_SHARED(double, red, PKB_RED_DOUBLES);
-    SpecIn si = {0, 0, 0.0, 0.0, 0, 0, 0, 0, 0, nullptr};
+    SpecIn si = {0, 0, 0.0, 0.0, 0, 0, 0, 0, 0, nullptr, nullptr, 0};
     step_finalize_block(rstat, d, ctrl, meta, apply_trunc, red, threadIdx.x, blockDim.x, si, flag_thresh);
 }
 
@@ -684,9 +692,9 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
                                        RowStats* __restrict__ rstat, double negval, FftPlan plan, int* __restrict__ done,
                                        ChainCtrl* ctrl, StepMeta* __restrict__ meta, int apply_trunc,
                                        cplx* __restrict__ Yt_next, const ChainCtrl* src_ctrl, TruncGeom tg, FftPlan plan_t,
-                                       int desc_order, int rowwin_ok, int* __restrict__ colflag) {
+                                       int desc_order, int rowwin_ok, int* __restrict__ colflag, int* host_box, int ticket) {
     const volatile ChainCtrl* sc = src_ctrl;
-    SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max, 0, 0, 0, 0, 0, nullptr};
+    SpecIn si = {sc->stored, sc->spec, sc->eps_sum, sc->eps_max, 0, 0, 0, 0, 0, nullptr, nullptr, 0};
     const bool tr = tg.N && !d.win && sc->trunc;      // truncated source on its smaller torus (TruncGeom)
     // row window of a spectral-resident step (the same decision k_cols took from the same control block)
     si.rowwin = (!tr && !d.win && spec_row_window(rowwin_ok, si.was_spec, sc->er0, sc->er1, si.eps_sum, si.eps_max, m, d.D, si.w0, si.w1)) ? 1 : 0;
@@ -716,6 +724,8 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         si.rowwin = 1; si.w0 = d.wr0 - m; si.w1 = d.wr0 - m + wout;
         si.c0 = d.wc0 - m; si.c1 = d.wc0 - m + wout;
         si.colflag = colflag;
+        si.host_box = colflag ? host_box : nullptr;
+        si.ticket = ticket;
     }
     const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : (si.rowwin ? (si.w1 - si.w0) / 2 : rows_inv_jobs(P, m)));
     const double scale = 1.0 / ((double)N * (double)N);

@@ -1141,6 +1141,8 @@ struct pkb_chain {
     bool fixed_torus;       // every whole-torus step runs on the chain's own torus (spectral-resident steps need one torus)
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
     DBuf<int> colflag;      // [P] columns in which a support-window step saw a cell >= PKB_SPEC_TAU (cleared by its finalize)
+    int* host_box;          // tau windows: mapped pinned host slot the next window step reports its extent to (+ ticket), or NULL
+    int host_ticket;
     size_t cscr_per_cta;
     int grid_rows, grid_cols;
     DBuf<RowStats> rstat;
@@ -1213,6 +1215,8 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ch->flag_thresh = 1e-8;
     ch->hstride = 0;
     ch->fixed_torus = false;
+    ch->host_box = nullptr;
+    ch->host_ticket = 0;
     for (int i = 0; i < PKB_MAX_COHORTS; ++i) ch->kcache_m[i] = -1;
     guard.c = nullptr;
     *out = ch;
@@ -1303,7 +1307,10 @@ static ChainDims trunc_dims(const ChainDims& d, const TruncGeom& tg) {
 
 static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl, double* dst, const double* K, int Wk, int m,
                      cplx* krt, bool krt_ready, int slot, int apply_trunc, const int* win = nullptr, bool fuse_next = false,
-                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true, int spec_try = 0) {
+                     int pre_m = -1, bool allow_trunc = false, cplx* krt_t = nullptr, bool krt_t_ready = true, int spec_try = 0,
+                     cudaEvent_t krt_event = nullptr) {
+    // krt_event: the kernel row spectra are being computed on another stream; the column pass waits for this event (the
+    // forward row pass does not need them and starts at once)
     // spec_try: 0 exact steps only; 1 spectral-resident steps allowed; 2 ... with row windows (ChainCtrl::er0, probability model)
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
@@ -1360,10 +1367,12 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     if (win) {
         if (!krt_ready) LAUNCH_AS(ctx, "k_kernel_rows_win", k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
         LAUNCH_AS(ctx, "k_rows_fwd_win", k_rows_fwd, std::min((rows_in + 1) / 2, plan.grid_rows), T, sm1, src, d, src_ctrl, ch->Yt.p, plan, -1, tg, plan_t, 0);
+        if (krt_event) CU(cudaStreamWaitEvent(ctx->stream, krt_event, 0));
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0, 0);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0, ch->colflag.p);
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0, ch->colflag.p,
+                  ch->host_box, ch->host_ticket);
         return 0;
     }
     if (!krt_ready) LAUNCH(ctx, k_kernel_rows, std::min(m + 1, plan.grid_rows), T, sm1, K, Wk, m, d, krt, plan);
@@ -1381,7 +1390,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
            ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride, rowwin_ok);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
            ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc,
-           rowwin_ok, (int*)nullptr);
+           rowwin_ok, (int*)nullptr, (int*)nullptr, 0);
     return 0;
 }
 
@@ -1445,10 +1454,10 @@ static int upload_filter(pkb_chain* ch, const double* B, int k, int* m_out) {
 }
 
 static int chain_conv_main(pkb_chain* ch, const double* K, int Wk, int m, int apply_trunc, cplx* krt = nullptr, const int* win = nullptr,
-                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr, int spec_try = 0) {
+                           bool fuse_next = false, int pre_m = -1, cplx* krt_t = nullptr, int spec_try = 0, cudaEvent_t krt_event = nullptr) {
     const int nxt = ch->cur ^ 1;
     TRY(conv_step(ch, ch->S[ch->cur].p, ch->ctrl.p, ch->S[nxt].p, K, Wk, m, krt ? krt : ch->Krt.p, krt != nullptr, 0, apply_trunc, win,
-                  fuse_next, pre_m, true, krt_t, true, spec_try));
+                  fuse_next, pre_m, true, krt_t, true, spec_try, krt_event));
     ch->cur = nxt;
     return 0;
 }
@@ -2235,7 +2244,8 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     DBuf<cplx> krt_ring;
     const int kRing = 4;
     if (tau_mode) {
-        TRY(hbox.alloc(ctx, 4 * (size_t)nd));
+        TRY(hbox.alloc(ctx, 8 * (size_t)nd));
+        memset(hbox.p, 0, sizeof(int) * 8 * (size_t)nd);
         TRY(krt_ring.alloc(ctx, krt_stride * kRing));
         while ((int)ctx->box_events.size() < nd) {
             cudaEvent_t e;
@@ -2249,6 +2259,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[0], 0));
     }
     int ring_used = 0;
+    cudaEvent_t tau_event = nullptr;
     // window of step n in tau mode (nullptr: the step cannot run as a window step any more -> whole-torus steps from here)
     auto tau_window = [&](int n, int* rc) -> const int* {
         *rc = 0;
@@ -2256,9 +2267,25 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         if (m <= ctx->stencil_max_radius) return nullptr;
         const int src = std::max(0, n - std::max(1, ctx->tau_lag));
         if (src >= 1 && !have[src]) {
-            cudaError_t e = cudaEventSynchronize(ctx->box_events[src]);
-            if (e != cudaSuccess) { *rc = fail(PKB_ECUDA, "waiting for the extent of day %d failed: %s", src, cudaGetErrorString(e)); return nullptr; }
-            const int* hb = hbox.p + 4 * src;
+            // the finalising CTA of step `src` writes its extent and then the ticket src + 1 straight into this pinned slot
+            volatile int* hv = hbox.p + 8 * src;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (long spins = 0; hv[4] != src + 1; ++spins) {
+                if ((spins & 1023) == 1023) {
+                    if (cudaEventQuery(ctx->box_events[src]) == cudaSuccess && hv[4] != src + 1) {
+                        // (emulation build / no mapped write seen: fall back to the device copy of the control block)
+                        int tmp[4];
+                        if (cudaMemcpy(tmp, &ch->ctrl.p->er0, sizeof tmp, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+                        hv[0] = tmp[0]; hv[1] = tmp[1]; hv[2] = tmp[2]; hv[3] = tmp[3]; hv[4] = src + 1;
+                        break;
+                    }
+                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) {
+                        *rc = fail(PKB_ECUDA, "timed out waiting for the extent of day %d", src);
+                        return nullptr;
+                    }
+                }
+            }
+            const int* hb = hbox.p + 8 * src;
             meas[src] = (hb[1] > hb[0] && hb[3] > hb[2]) ? Box{hb[0], hb[1], hb[2], hb[3]} : reg[src];
             have[src] = 1;
         }
@@ -2305,15 +2332,15 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             ctx->win_events.push_back(e);
         }
         CU(cudaEventRecord(ctx->win_events[slot], ctx->aux));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->win_events[slot], 0));
+        tau_event = ctx->win_events[slot];              // (the step's column pass waits for it, conv_step)
         *out = krt_ring.p + krt_stride * slot;
         return 0;
     };
     auto tau_after_step = [&](int n) -> int {          // the step has been enqueued: its slot may be reused, its extent travels to the host
         CU(cudaEventRecord(ctx->ring_events[ring_used % kRing], ctx->stream));
         ++ring_used;
-        CU(cudaMemcpyAsync(hbox.p + 4 * n, &ch->ctrl.p->er0, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->box_events[n], ctx->stream));
+        ch->host_box = nullptr;
         return 0;
     };
     // leaving tau mode before step n: older windows may have left cells outside the region of state n - 1
@@ -2431,7 +2458,12 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
                 int rcw = 0;
                 wp = tau_window(n, &rcw);
                 TRY(rcw);
-                if (wp) { TRY(tau_spectra(n, wp, &krt)); tau_step = true; }
+                if (wp) {
+                    TRY(tau_spectra(n, wp, &krt));
+                    tau_step = true;
+                    ch->host_box = hbox.p + 8 * n;      // this step reports its extent here (ticket n + 1)
+                    ch->host_ticket = n + 1;
+                }
                 else TRY(tau_leave(n));
             } else {
                 wp = step_window(n);
@@ -2442,7 +2474,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
             const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
-            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try));
+            TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try, tau_step ? tau_event : (cudaEvent_t)nullptr));
             fused_m = fuse ? krad(n) : -1;
             if (tau_step) TRY(tau_after_step(n));
             CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));

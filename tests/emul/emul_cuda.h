@@ -99,6 +99,7 @@ static inline unsigned long long atomicAdd(unsigned long long* addr, unsigned lo
 }
 static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int atomicOr(int* addr, int val) { return __atomic_fetch_or(addr, val, __ATOMIC_RELAXED); }
 static inline int atomicMax(int* addr, int val) {
     int old = __atomic_load_n(addr, __ATOMIC_RELAXED);
