@@ -81,6 +81,8 @@ struct pkb_ctx {
     cudaStream_t own_stream;   // the stream created with the context (ctx->stream unless pkb_set_stream lent another one)
     cudaStream_t aux;       // side stream: output emission overlapped with the next chain step
     cudaStream_t cp;        // copy stream: per-day COO compaction + D2H while the chain is still running
+    cudaStream_t cp2;       // second copy stream: the days alternate, so one day's compaction overlaps the previous day's copies
+    cudaEvent_t ev_cp2;
     std::vector<cudaEvent_t> day_events;
     std::vector<cudaEvent_t> win_events;
     cudaEvent_t ev_cp;
@@ -303,6 +305,7 @@ static int sync_check(pkb_ctx* ctx, const char* where) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->aux);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->cp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->cp2);
     if (e != cudaSuccess) return fail(PKB_ECUDA, "stream synchronize failed in %s: %s", where, cudaGetErrorString(e));
     if (!ctx->prof_pending.empty()) prof_collect(ctx);
     return 0;
@@ -370,8 +373,10 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&ctx->cp, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&ctx->cp2, cudaStreamNonBlocking, hi));
     }
     CU(cudaEventCreateWithFlags(&ctx->ev_cp, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_cp2, cudaEventDisableTiming));
     ctx->coo_hint = 0;
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&ctx->ev_step[i], cudaEventDisableTiming));
@@ -425,6 +430,8 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (cudaEvent_t e : ctx->box_events) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ring_events[i]);
     cudaEventDestroy(ctx->ev_cp);
+    cudaEventDestroy(ctx->ev_cp2);
+    cudaStreamDestroy(ctx->cp2);
     cudaStreamDestroy(ctx->cp);
     cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->own_stream);
@@ -1927,8 +1934,8 @@ static int hbuf_grow(pkb_ctx* ctx, HBuf<T>& b, size_t used, size_t newcap) {
 // chain loop calls it after every step, so the triplets cross PCIe while later days are still being computed even
 // when the host paces the chain itself (tau windows wait for an older step's extent before every step).
 struct CooState {
-    DBuf<int> srow, scol;
-    DBuf<double> sval;
+    DBuf<int> srow[2], scol[2];      // two staging areas, one per copy stream (days alternate)
+    DBuf<double> sval[2];
     size_t cap = 0;
     int next_day = 0;
     bool started = false;
@@ -1945,9 +1952,11 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
         TRY(r->cols.alloc(ctx, st->cap));
         TRY(r->vals.alloc(ctx, st->cap));
         // one day's triplets at a time through a device staging area (worst case D*D entries)
-        TRY(st->srow.alloc(ctx, nD));
-        TRY(st->scol.alloc(ctx, nD));
-        TRY(st->sval.alloc(ctx, nD));
+        for (int b = 0; b < 2; ++b) {
+            TRY(st->srow[b].alloc(ctx, nD));
+            TRY(st->scol[b].alloc(ctx, nD));
+            TRY(st->sval[b].alloc(ctx, nD));
+        }
         st->started = true;
     }
     for (; st->next_day < nd; ++st->next_day) {
@@ -1964,24 +1973,30 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
         r->dayoff.p[day + 1] = (long long)(off + tot);
         if (off + tot > st->cap) {
             CU(cudaStreamSynchronize(ctx->cp));                   // copies into the old blocks must have landed
+            CU(cudaStreamSynchronize(ctx->cp2));
             const size_t newcap = std::max<size_t>(off + tot + (off + tot) / 4, st->cap * 2);
             TRY(hbuf_grow(ctx, r->rows, off, newcap));
             TRY(hbuf_grow(ctx, r->cols, off, newcap));
             TRY(hbuf_grow(ctx, r->vals, off, newcap));
             st->cap = newcap;
         }
-        CU(cudaStreamWaitEvent(ctx->cp, ctx->day_events[day], 0));
-        LAUNCH_ON(ctx, ctx->cp, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
-                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), st->srow.p, st->scol.p, st->sval.p);
+        const int b = day & 1;
+        cudaStream_t cs = b ? ctx->cp2 : ctx->cp;
+        CU(cudaStreamWaitEvent(cs, ctx->day_events[day], 0));
+        LAUNCH_ON(ctx, cs, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
+                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), st->srow[b].p, st->scol[b].p,
+                  st->sval[b].p);
         if (tot > 0) {
-            CU(cudaMemcpyAsync(r->rows.p + off, st->srow.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
-            CU(cudaMemcpyAsync(r->cols.p + off, st->scol.p, sizeof(int) * tot, cudaMemcpyDeviceToHost, ctx->cp));
-            CU(cudaMemcpyAsync(r->vals.p + off, st->sval.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->cp));
+            CU(cudaMemcpyAsync(r->rows.p + off, st->srow[b].p, sizeof(int) * tot, cudaMemcpyDeviceToHost, cs));
+            CU(cudaMemcpyAsync(r->cols.p + off, st->scol[b].p, sizeof(int) * tot, cudaMemcpyDeviceToHost, cs));
+            CU(cudaMemcpyAsync(r->vals.p + off, st->sval[b].p, sizeof(double) * tot, cudaMemcpyDeviceToHost, cs));
         }
     }
     if (block) {
         CU(cudaEventRecord(ctx->ev_cp, ctx->cp));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp, 0));
+        CU(cudaEventRecord(ctx->ev_cp2, ctx->cp2));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp2, 0));
         ctx->coo_hint = (size_t)r->dayoff.p[nd];
         r->have_coo = true;
     }
