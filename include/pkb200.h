@@ -229,6 +229,8 @@ typedef struct pkb_solve_args {
     double sprd_drift[2];
     const double* sprd_factors; /* pkb_solve_batch only: one sprd_factor per proposal (it is a sampled variable of its own,
                                  * Bayes_Run.py:202); NULL: sprd_factor for all */
+    int out_on_device;       /* pkb_solve_batch(_projected) only: `out` is DEVICE memory (e.g. the tensor the caller all-gathers
+                              * over NCCL): the results never visit the host */
     int keep_pre_device;     /* parity export: also keep every day's UN-thresholded domain grid (the `A[:D,:D]` of
                               * CalcSol.py:189-190 / the cohort sum of :322 before r_small_vals) for pkb_result_pre */
 } pkb_solve_args;

@@ -49,7 +49,7 @@ class SolveArgs(C.Structure):
                 ('r_number', C.c_double), ('r_dist', c_double_p), ('r_start', C.c_double), ('negval', C.c_double),
                 ('want_dense_host', C.c_int), ('want_coo', C.c_int), ('keep_dense_device', C.c_int),
                 ('sprd', C.c_int), ('sprd_factor', C.c_double), ('sprd_drift', C.c_double * 2), ('sprd_factors', c_double_p),
-                ('keep_pre_device', C.c_int)]
+                ('out_on_device', C.c_int), ('keep_pre_device', C.c_int)]
 
 
 class Projection(C.Structure):

@@ -31,14 +31,32 @@ def unpack_proposal(p):
     return hparams, tuple(p[6:9]), tuple(p[9:12]), float(p[14]), int(round(p[13]))
 
 
-def shard(n_items, world, rank):
-    """Indices of the items rank ``rank`` of ``world`` owns: contiguous blocks,
-    the first ``n_items % world`` ranks take one extra item."""
+def shard(n_items, world, rank, cost=None):
+    """Indices of the items rank ``rank`` of ``world`` owns.  Without ``cost``: contiguous blocks, the first
+    ``n_items % world`` ranks take one extra item.  With ``cost`` (one number per item): the items are dealt out in
+    order of decreasing cost, back and forth over the ranks, so that every rank gets the same number of items (+-1) and
+    about the same total cost -- the ranks of a likelihood batch are timed by the slowest one."""
     if world < 1 or not 0 <= rank < world:
         raise ValueError('bad rank {} of {}'.format(rank, world))
-    base, extra = divmod(int(n_items), world)
+    n_items = int(n_items)
+    if cost is not None:
+        order = np.argsort(-np.asarray(cost, dtype=float), kind='stable')
+        mine = []
+        for pos, item in enumerate(order):
+            rnd, k = divmod(pos, world)
+            if (k if rnd % 2 == 0 else world - 1 - k) == rank:
+                mine.append(int(item))
+        return sorted(mine)
+    base, extra = divmod(n_items, world)
     lo = rank * base + min(rank, extra)
     return list(range(lo, lo + base + (1 if rank < extra else 0)))
+
+
+def proposal_cost(proposals):
+    """Relative cost of a proposal's solve, known before anything is computed: the kernel radii -- and with them the
+    torus every chain step runs on -- grow with the flight advection scale mu_r * n_periods and the in-flow spread."""
+    p = np.asarray(proposals, dtype=float).reshape(-1, len(PROPOSAL_FIELDS))
+    return p[:, 14] * p[:, 13] + 0.02 * np.maximum(p[:, 6], p[:, 7])
 
 
 def _dist():
@@ -50,7 +68,7 @@ def _dist():
 
 
 def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number, r_dist, r_start, device,
-                 wind_device_ptr, wind_shape, ids, sprd_factors=None, sprd_drift=(-25., 15.), projection=None):
+                 wind_device_ptr, wind_shape, ids, sprd_factors=None, sprd_drift=(-25., 15.), projection=None, out_device=None):
     """This rank's proposals through ONE library call (``pkb_solve_batch``: kernel construction
     batched over groups of proposals, chains back to back on the device-resident kernels)."""
     import ctypes as C
@@ -67,15 +85,19 @@ def _solve_shard(wind, props, cells, ndays, rad_dist, rad_res, prob_model, r_dur
     props = np.ascontiguousarray(props, dtype=np.float64)
     n = props.shape[0]
     status = np.zeros((n, ndays), dtype=np.int32)
+    if out_device is not None:          # results straight into the caller's device tensor (the one it all-gathers)
+        a.out_on_device = 1
+        out, optr = out_device, C.cast(C.c_void_p(out_device.data_ptr()), _abi.c_double_p)
+    else:
+        out = np.empty((n, ndays, cells.shape[0]) if projection is None else (n, projection.nrows))
+        optr = _lib.dptr(out)
     if projection is None:
-        out = np.empty((n, ndays, cells.shape[0]))
         _lib.check(_lib.lib().pkb_solve_batch(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells), cells.shape[0],
-                                              _lib.dptr(out), _lib.iptr(status)))
+                                              optr, _lib.iptr(status)))
     else:
         # the likelihood projection of every proposal on the device (Bayes_Run.py:298-306): only its rows come back
-        out = np.empty((n, projection.nrows))
         _lib.check(_lib.lib().pkb_solve_batch_projected(_lib.ctx(device).h, C.byref(a), _lib.dptr(props), n, _lib.iptr(cells),
-                                                        cells.shape[0], C.byref(projection.c), _lib.dptr(out), _lib.iptr(status)))
+                                                        cells.shape[0], C.byref(projection.c), optr, _lib.iptr(status)))
     del keep
     # the reference's assertion / warning sites, per (proposal, day) kernel (ParasitoidModel.py:529-599)
     for i in range(n):
@@ -115,26 +137,33 @@ def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=Fal
     dist = _dist()
     world = dist.get_world_size(group) if dist else 1
     rank = dist.get_rank(group) if dist else 0
-    mine = shard(B, world, rank)
+    # the ranks finish together only if their shares cost about the same: deal the proposals out by estimated cost
+    cost = proposal_cost(proposals) if world > 1 else None
+    mine = shard(B, world, rank, cost)
     per = -(-B // world)                      # padded shard length
-    local = np.zeros((per,) + tail)
     sf = None if sprd_factor is None else np.broadcast_to(np.asarray(sprd_factor, dtype=float), (B,))
-    if mine:
-        local[:len(mine)] = _solve_shard(wind, proposals[mine], cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number,
-                                         r_dist, r_start, device, wind_device_ptr, wind_shape, mine,
-                                         None if sf is None else sf[mine], sprd_drift, projection)
+    shard_args = (wind, proposals[mine], cells, ndays, rad_dist, rad_res, prob_model, r_dur, r_number, r_dist, r_start, device,
+                  wind_device_ptr, wind_shape, mine, None if sf is None else sf[mine], sprd_drift, projection)
     if world == 1:
-        return local[:B]
+        return _solve_shard(*shard_args)[:B] if mine else np.zeros((0,) + tail)
     import torch
-    backend = dist.get_backend(group)
-    t = torch.from_numpy(local)
-    if backend == 'nccl':
-        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    if dist.get_backend(group) == 'nccl':
+        # the library writes this rank's results straight into the tensor that is all-gathered over NVLink; the only
+        # host copy is the one of the gathered result
+        dev = torch.device('cuda', device if device is not None else torch.cuda.current_device())
+        t = torch.zeros((per,) + tail, dtype=torch.float64, device=dev)
+        if mine:
+            _solve_shard(*shard_args, out_device=t)
+    else:
+        local = np.zeros((per,) + tail)
+        if mine:
+            local[:len(mine)] = _solve_shard(*shard_args)
+        t = torch.from_numpy(local)
     out = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)       # concatenated along dim 0 (gloo and nccl both accept this form)
     out = out.cpu().numpy().reshape((world, per) + tuple(t.shape[1:]))
     full = np.empty((B,) + tail)
     for r in range(world):
-        idx = shard(B, world, r)
+        idx = shard(B, world, r, cost)
         full[idx] = out[r, :len(idx)]
     return full

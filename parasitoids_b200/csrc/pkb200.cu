@@ -2823,13 +2823,12 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         if (pend.rc) rc = pend.rc;
         if (!rc) {
             cudaError_t e;
+            const cudaMemcpyKind kind = base->out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
             if (proj) {
                 launch_project(ctx, dproj, dout[pend.buf].p, nd, K, pend.np, dprojout.p);
-                e = cudaMemcpyAsync(out + (size_t)pend.p0 * proj->nrows, dprojout.p, sizeof(double) * pend.np * proj->nrows, cudaMemcpyDeviceToHost,
-                                    ctx->stream);
+                e = cudaMemcpyAsync(out + (size_t)pend.p0 * proj->nrows, dprojout.p, sizeof(double) * pend.np * proj->nrows, kind, ctx->stream);
             } else
-                e = cudaMemcpyAsync(out + (size_t)pend.p0 * nd * K, dout[pend.buf].p, sizeof(double) * pend.np * nd * K,
-                                            cudaMemcpyDeviceToHost, ctx->stream);
+                e = cudaMemcpyAsync(out + (size_t)pend.p0 * nd * K, dout[pend.buf].p, sizeof(double) * pend.np * nd * K, kind, ctx->stream);
             if (e != cudaSuccess) rc = fail(PKB_ECUDA, "pkb_solve_batch: output copy failed: %s", cudaGetErrorString(e));
             else rc = sync_check(ctx, "pkb_solve_batch outputs");
         }

@@ -48,6 +48,17 @@ def test_shard_partitions_every_item_once():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     with pytest.raises(ValueError):
         batch.shard(4, 2, 2)
+    # cost-aware dealing: still a partition into equal counts, and the shares cost about the same
+    rng = np.random.default_rng(0)
+    for n in (5, 64, 512):
+        cost = rng.gamma(2.0, 1.0, n)
+        for world in (2, 3, 8):
+            parts = [batch.shard(n, world, r, cost) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            if n == 512:
+                tot = [cost[p].sum() for p in parts]
+                assert max(tot) - min(tot) < 0.02 * np.mean(tot)
 
 
 def test_unpack_proposal_order():
