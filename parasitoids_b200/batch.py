@@ -59,6 +59,19 @@ def proposal_cost(proposals):
     return p[:, 14] * p[:, 13] + 0.02 * np.maximum(p[:, 6], p[:, 7])
 
 
+_PINNED = {}
+_COPY_OUT = False      # the returned array is a view of a cached pinned buffer: valid until the next solve_batch of that shape
+
+
+def _pinned(shape):
+    """Cached pinned host tensor for the gathered result (allocating pinned memory costs more than the copy)."""
+    import torch
+    if shape not in _PINNED:
+        _PINNED.clear()
+        _PINNED[shape] = torch.empty(shape, dtype=torch.float64).pin_memory()
+    return _PINNED[shape]
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -121,7 +134,8 @@ def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=Fal
     projection: a ``Bayes_funcs.Projection`` (then ``cells`` is ignored, its own sample cells are used): every
                 proposal's solution is folded into the values ``popdensity_to_emergence`` / ``popdensity_grid`` return,
                 on the device; the result is (B, projection.nrows), ``projection.split(row)`` gives the arrays
-    returns     (B, ndays, K) float64, identical on every rank
+    returns     (B, ndays, K) float64, identical on every rank (with NCCL: a view of a cached pinned buffer, overwritten
+                by the next call with the same shape -- copy it to keep it)
 
     With an initialised ``torch.distributed`` process group the proposals are
     sharded over the ranks (``shard``) and the results all-gathered; without
@@ -161,9 +175,15 @@ def solve_batch(wind, proposals, cells, ndays, rad_dist, rad_res, prob_model=Fal
         t = torch.from_numpy(local)
     out = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)       # concatenated along dim 0 (gloo and nccl both accept this form)
-    out = out.cpu().numpy().reshape((world, per) + tuple(t.shape[1:]))
-    full = np.empty((B,) + tail)
+    # back to proposal order where the data is (one gather on the device), then ONE copy into pinned host memory
+    pos = np.empty(B, dtype=np.int64)
     for r in range(world):
         idx = shard(B, world, r, cost)
-        full[idx] = out[r, :len(idx)]
-    return full
+        pos[idx] = r * per + np.arange(len(idx))
+    full = out.index_select(0, torch.from_numpy(pos).to(out.device))
+    if full.is_cuda:
+        host = _pinned(tuple(full.shape))
+        host.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(full.device).synchronize()
+        return host.numpy().copy() if _COPY_OUT else host.numpy()
+    return full.numpy()

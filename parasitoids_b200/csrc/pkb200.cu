@@ -24,7 +24,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pkb;
@@ -123,6 +126,8 @@ struct pkb_ctx {
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
     int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
+    int batch_threads;      // ... enqueued by one host thread per lane (option "batch_threads", default 1 = yes): a Kalbar-sized
+                            // chain is ~90 launches of 20-60 us kernels, so one thread issuing four lanes is the bottleneck
     std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
     cudaEvent_t ev_lane;
     cudaEvent_t ev_kr[2];      // fused solve: kernel row spectra batched on the side stream (before / after)
@@ -344,6 +349,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_windows = 1;
     ctx->use_fusion = 1;
     ctx->batch_lanes = 4;
+    ctx->batch_threads = 1;
     ctx->batch_group = 32;
     ctx->use_step_torus = 1;
     ctx->use_trunc_torus = 1;
@@ -501,6 +507,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "batch_group")) {
         if (value < 1 || value > 1024) return fail(PKB_EINVAL, "batch_group must be 1..1024");
         ctx->batch_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "batch_threads")) {
+        ctx->batch_threads = value != 0;
         return 0;
     }
     if (!strcmp(key, "batch_lanes")) {
@@ -1148,6 +1158,7 @@ struct pkb_chain {
     bool fixed_torus;       // every whole-torus step runs on the chain's own torus (spectral-resident steps need one torus)
     DBuf<int> done;         // k_rows_inv: CTAs finished (the last one finalises the step)
     DBuf<int> colflag;      // [P] columns in which a support-window step saw a cell >= PKB_SPEC_TAU (cleared by its finalize)
+    StepMeta* meta_main;    // fused solve: where the main chain's next step writes its StepMeta (the per-day array; saves a copy per step)
     int* host_box;          // tau windows: mapped pinned host slot the next window step reports its extent to (+ ticket), or NULL
     int host_ticket;
     size_t cscr_per_cta;
@@ -1224,6 +1235,7 @@ static int chain_create(pkb_ctx* ctx, int D, int mmax, pkb_chain** out) {
     ch->fixed_torus = false;
     ch->host_box = nullptr;
     ch->host_ticket = 0;
+    ch->meta_main = nullptr;
     for (int i = 0; i < PKB_MAX_COHORTS; ++i) ch->kcache_m[i] = -1;
     guard.c = nullptr;
     *out = ch;
@@ -1322,12 +1334,13 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     pkb_ctx* ctx = ch->ctx;
     if (m > ch->mmax) return fail(PKB_ELIMIT, "filter radius %d exceeds the chain's max_shape//2 = %d", m, ch->mmax);
     if (2 * m > ch->d.P) return fail(PKB_ELIMIT, "filter radius %d does not fit the %d-cell padded domain", m, ch->d.P);
+    StepMeta* meta_dst = (slot == 0 && ch->meta_main) ? ch->meta_main : ch->meta.p + slot;
     if (m <= ctx->stencil_max_radius) {
         const ChainDims& d = ch->d;
         const size_t smem = ((size_t)(8 + 2 * m) * (32 + 2 * m) + (size_t)(2 * m + 1) * (2 * m + 1)) * sizeof(double);
         LAUNCH(ctx, k_stencil, dim3((d.P + 31) / 32, (d.P + 7) / 8), dim3(32, 8), smem, src, K, Wk, m, d, src_ctrl, dst);
         LAUNCH(ctx, k_row_stats, d.P, 256, 0, (const double*)dst, d, ch->rstat.p, ch->negval);
-        LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, 1e-8);
+        LAUNCH(ctx, k_step_finalize, 1, 256, 0, (const RowStats*)ch->rstat.p, d, ch->ctrl.p + slot, meta_dst, apply_trunc, 1e-8);
         return 0;
     }
     // geometry of this step: the chain's torus, or a smaller one around the state's support window
@@ -1378,7 +1391,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
         LAUNCH_AS(ctx, "k_cols_win", k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt,
                   m, d, src_ctrl_w, ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt, (cplx*)nullptr, (size_t)0, 0);
         LAUNCH_AS(ctx, "k_rows_inv_win", k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p,
-                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0, ch->colflag.p,
+                  ch->negval, plan, ch->done.p, ch->ctrl.p + slot, meta_dst, apply_trunc, (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc, 0, ch->colflag.p,
                   ch->host_box, ch->host_ticket);
         return 0;
     }
@@ -1396,7 +1409,7 @@ static int conv_step(pkb_chain* ch, const double* src, const ChainCtrl* src_ctrl
     LAUNCH(ctx, k_cols, std::min(d.Nc, plan.grid_cols), plan.cols_threads, sm1, (const cplx*)ch->Yt.p, (const cplx*)krt, m, d, src_ctrl_w,
            ch->Wt.p, ch->cscr.p, plan, tg, plan_t, (const cplx*)krt_t, shat, ch->hstride, rowwin_ok);
     LAUNCH(ctx, k_rows_inv, std::min(njobs, plan.grid_rows), T, sm1, (const cplx*)ch->Wt.p, m, d, dst, ch->rstat.p, ch->negval, plan,
-           ch->done.p, ch->ctrl.p + slot, ch->meta.p + slot, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc,
+           ch->done.p, ch->ctrl.p + slot, meta_dst, apply_trunc, fuse_next ? ch->Yt.p : (cplx*)nullptr, src_ctrl, tg, plan_t, ctx->rows_desc,
            rowwin_ok, (int*)nullptr, (int*)nullptr, 0);
     return 0;
 }
@@ -2286,6 +2299,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             volatile int* hv = hbox.p + 8 * src;
             const auto t0 = std::chrono::steady_clock::now();
             for (long spins = 0; hv[4] != src + 1; ++spins) {
+#if defined(__x86_64__) && !defined(PKB_EMUL)
+                __builtin_ia32_pause();
+#endif
                 if ((spins & 1023) == 1023) {
                     if (cudaEventQuery(ctx->box_events[src]) == cudaSuccess && hv[4] != src + 1) {
                         // (emulation build / no mapped write seen: fall back to the device copy of the control block)
@@ -2486,29 +2502,31 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (!wp) TRY(day_spectra(n, &krt, &krt_t));
             else if (!tau_step) TRY(window_spectra(n, &krt));
             // step n overwrites the state buffer that the emission of day n-2 reads
-            if (n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
+            if (n >= 3 && !sink) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[n & 1], 0));
             // whole-torus step followed by another one: its inverse row pass also does the next step's forward row pass
             const bool fuse = !wp && !wmode && n + 1 < nd && fusable(n);
+            ch->meta_main = dsm.p + n;          // the step's flag / sums / windows go straight to the day's record
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, krt, wp, fuse, fused_m, krt_t, spec_try, tau_step ? tau_event : (cudaEvent_t)nullptr));
             fused_m = fuse ? krad(n) : -1;
             if (tau_step) TRY(tau_after_step(n));
-            CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             if (res->pre.p) LAUNCH(ctx, k_copy_domain, D, 256, 0, (const double*)ch->S[ch->cur].p, d, res->pre.p + nD * (n - lead), (const StepMeta*)(dsm.p + n));
+            if (sink) {
+                // (a few hundred cells: on the chain's own stream, no events -- the likelihood batch is bound by the host's launch rate)
+                LAUNCH(ctx, k_emit_dense_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval,
+                       1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * (n - lead));
+                continue;
+            }
             // r_small_vals + dense output on the side stream, overlapped with step n+1
             CU(cudaEventRecord(ctx->ev_step[n & 1], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
-            if (sink)
-                LAUNCH_ON(ctx, ctx->aux, k_emit_dense_cells, sgrid, 256, 0, (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval,
-                          1, 0, sink->cells, sink->K, sink->out + (size_t)sink->K * (n - lead));
-            else
-                LAUNCH_ON(ctx, ctx->aux, k_emit_dense, ctx->emit_ctas > 0 ? std::min(D, ctx->emit_ctas) : D, ctx->emit_ctas > 0 ? 64 : PKB_EMIT_T, 0,
-                          (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
-                          res->dense.p + nD * (n - lead), a->want_coo ? res->rownnz.p + (size_t)D * (n - lead) : (int*)nullptr);
+            LAUNCH_ON(ctx, ctx->aux, k_emit_dense, ctx->emit_ctas > 0 ? std::min(D, ctx->emit_ctas) : D, ctx->emit_ctas > 0 ? 64 : PKB_EMIT_T, 0,
+                      (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
+                      res->dense.p + nD * (n - lead), a->want_coo ? res->rownnz.p + (size_t)D * (n - lead) : (int*)nullptr);
             if (a->want_coo) res->counted[n - lead] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
             TRY(emitted(n, ctx->aux));
         }
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2 && !sink; ++i)
             if (nd - 1 - i >= 1) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_emit[(nd - 1 - i) & 1], 0));
     } else {
         const int rd = a->r_dur;
@@ -2574,9 +2592,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             if (!wp) TRY(day_spectra(n, &kday, &kday_t));
             else TRY(window_spectra(n, &kday));
             const bool fuse = rd == 1 && !wp && !wmode && n + 1 < nd && fusable(n);
+            ch->meta_main = dsm.p + n;
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
-            CU(cudaMemcpyAsync(dsm.p + n, ch->meta.p, sizeof(StepMeta), cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready, krt_t, ready_t));
             TRY(keep_cmeta(n, rd - 1));
             for (int c = 0; c < rd; ++c) {
@@ -2815,12 +2833,27 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         int p0 = 0, np = 0, buf = 0;
         int rc = 0;           // first error while its chains were enqueued
         bool live = false;
+        // the group's chains are enqueued by one host thread per lane; what they read lives here until they are joined
+        std::vector<std::thread> workers;
+        std::shared_ptr<std::vector<pkb_solve_args> > sa;
+        std::mutex mu;
+        std::string msg;
     } pend;
+    auto join_workers = [&]() {
+        for (auto& t : pend.workers)
+            if (t.joinable()) t.join();
+        pend.workers.clear();
+        if (pend.rc && !pend.msg.empty()) g_err = pend.msg;
+    };
     // wait for the group in flight, copy its samples out, release its kernels
     auto finish = [&]() -> int {
         if (!pend.live) return 0;
+        join_workers();
         int rc = drain();
-        if (pend.rc) rc = pend.rc;
+        if (pend.rc) {
+            rc = pend.rc;
+            if (!pend.msg.empty()) g_err = pend.msg;
+        }
         if (!rc) {
             cudaError_t e;
             const cudaMemcpyKind kind = base->out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -2833,13 +2866,14 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
             else rc = sync_check(ctx, "pkb_solve_batch outputs");
         }
         delete pend.ks;
-        pend = Pending();
+        pend.ks = nullptr; pend.p0 = pend.np = pend.buf = 0; pend.rc = 0; pend.live = false; pend.sa.reset(); pend.msg.clear();
         return rc;
     };
     int gi = 0;
     for (int p0 = 0; p0 < nprop; p0 += group, ++gi) {
         const int np = std::min(group, nprop - p0);
-        std::vector<pkb_solve_args> sa(np, *base);
+        auto sa_ptr = std::make_shared<std::vector<pkb_solve_args> >(np, *base);
+        std::vector<pkb_solve_args>& sa = *sa_ptr;
         const int nk = solve_nkernels(base), lead = nk - nd;      // kernels per proposal (leading spread kernel, Bayes_Run.py:245-270)
         std::vector<pkb_day_args> dargs((size_t)np * nk);
         for (int p = 0; p < np; ++p) {
@@ -2877,17 +2911,41 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         // the lanes start once the kernels (and, first group, the cells) are on the device
         cudaEventRecord(ctx->ev_lane, ctx->stream);
         for (int l = 0; l < nlanes; ++l) cudaStreamWaitEvent(ctx->lanes[l]->stream, ctx->ev_lane, 0);
-        pend.ks = ks; pend.p0 = p0; pend.np = np; pend.buf = gi & 1; pend.live = true;
-        for (int p = 0; p < np && !pend.rc; ++p) {
-            SampleSink sink = {dcells.p, K, dout[pend.buf].p + (size_t)p * nd * K};
-            pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nk, nullptr, &sink);
-        }
-        if (pend.rc) {
-            const std::string msg = g_err;
-            const int rc = pend.rc;
-            finish();
-            g_err = msg;
-            return rc;
+        pend.ks = ks; pend.p0 = p0; pend.np = np; pend.buf = gi & 1; pend.live = true; pend.sa = sa_ptr;
+        double* dgroup = dout[pend.buf].p;
+        const int* dcell_p = dcells.p;
+        auto lane_work = [&pend, ctx, ks, sa_ptr, nk, nd, K, nlanes, np, dgroup, dcell_p](int l) {
+            cudaSetDevice(ctx->device);                 // (the current device is per host thread)
+            for (int p = l; p < np; p += nlanes) {
+                { std::lock_guard<std::mutex> g(pend.mu); if (pend.rc) return; }
+                SampleSink sink = {dcell_p, K, dgroup + (size_t)p * nd * K};
+                const int rc = solve_chain(ctx->lanes[l], &(*sa_ptr)[p], ks, p * nk, nullptr, &sink);
+                if (rc) {
+                    std::lock_guard<std::mutex> g(pend.mu);
+                    if (!pend.rc) { pend.rc = rc; pend.msg = g_err; }
+                    return;
+                }
+            }
+        };
+#ifdef PKB_EMUL
+        const bool threaded = false;                    // (the CPU emulation of CUDA blocks is not re-entrant)
+#else
+        const bool threaded = ctx->batch_threads && nlanes > 1 && np > 1;
+#endif
+        if (threaded) {
+            // the workers keep enqueueing while this thread goes on to build the next group's kernels; finish() joins them
+            for (int l = 0; l < nlanes; ++l) pend.workers.emplace_back(lane_work, l);
+        } else {
+            for (int p = 0; p < np && !pend.rc; ++p) {
+                SampleSink sink = {dcell_p, K, dgroup + (size_t)p * nd * K};
+                pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nk, nullptr, &sink);
+                if (pend.rc) pend.msg = g_err;
+            }
+            if (pend.rc) {
+                const int rc = pend.rc;
+                finish();
+                return rc;
+            }
         }
     }
     return finish();

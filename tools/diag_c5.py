@@ -18,8 +18,9 @@ kw = dict(prob_model=False, r_dur=1, r_number=130000.0, device=0, wind_device_pt
 names = ['k_rows_fwd', 'k_cols', 'k_rows_inv', 'k_rows_fwd_win', 'k_cols_win', 'k_rows_inv_win', 'k_kernel_rows_win', 'k_kernel_rows',
          'k_kernel_rows_batch', 'k_emit_population_cells', 'k_emit_dense_cells', 'k_copy_domain_cells', 'k_step_finalize', 'k_zero_pad', 'k_period',
          'k_day_finalize', 'k_drift', 'k_hprob', 'k_bvn_setup', 'k_place_kernel', 'k_set_ctrl', 'k_stencil', 'k_row_stats']
-for lanes, prof in ((1, True), (1, False), (4, False), (4, False)):
+for lanes, prof, thr in ((1, True, 0), (1, False, 0), (4, False, 0), (4, False, 0), (4, False, 1), (4, False, 1), (6, False, 1), (8, False, 1)):
     ctx.set_option('batch_lanes', lanes)
+    ctx.set_option('batch_threads', thr)
     batch.solve_batch(None, props[:8], cells, 18, rad_dist, rad_res, **kw)
     if prof:
         ctx.profile_reset(); ctx.profile(True)
@@ -27,7 +28,7 @@ for lanes, prof in ((1, True), (1, False), (4, False), (4, False)):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     batch.solve_batch(None, props, cells, 18, rad_dist, rad_res, **kw)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    rec = {'lanes': lanes, 'profiled': prof, 'nprop': nprop, 'wall_ms': round((t1 - t0) * 1e3, 1), 'launches': ctx.launch_count() - l0,
+    rec = {'lanes': lanes, 'threads': thr, 'profiled': prof, 'nprop': nprop, 'wall_ms': round((t1 - t0) * 1e3, 1), 'launches': ctx.launch_count() - l0,
            'days_per_s': round(nprop * 18 / (t1 - t0), 1)}
     if prof:
         ctx.profile(False)
