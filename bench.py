@@ -473,13 +473,13 @@ def run_extras(args, ctx, torch, dist, rank, world, local, main_model, main_wind
             def one():
                 with warnings.catch_warnings():
                     warnings.simplefilter('ignore')
-                    res = Run.solve(wp, len(days), *m, want_coo=True, device=local, **skw)
-                    res.coo_arrays()
+                    res = Run.solve(wp, len(days), *m, want_coo='csr', device=local, **skw)
+                    res.csr_arrays()
                     res.close()
             ms = timed(one, 5, warmup=2)
             rec = {'workload': '%s %s model, 801x801, %d days (Run.py presets)' % (site, 'probability' if model == 'prob' else 'population', len(days)),
                    'e2e': {'value': len(days) / (ms / 1000.0), 'unit': 'days/s', 'ms_per_step': ms,
-                           'api': 'Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}}
+                           'api': "Run.solve(want_coo='csr'): wind from pinned host memory, CSR arrays of all days to host"}}
             if name in cpu_sites:
                 rec['cpu_baseline'] = cpu_sites[name]
             extra[name] = rec
@@ -694,8 +694,8 @@ def main():
                 warnings.simplefilter('ignore')
                 out = batch.solve_batch(wind_pinned.numpy(), proposals, cells, ndays, rad_dist, rad_res, device=local, **pop_kw)
             return None, out.size // 2        # counted below as 16 bytes per entry
-        res = Run.solve(wind_pinned.numpy(), ndays, *model, want_coo=True, device=local)
-        off, rows, cols, vals = res.coo_arrays()
+        res = Run.solve(wind_pinned.numpy(), ndays, *model, want_coo='csr', device=local)
+        off, rowoff, cols, vals = res.csr_arrays()
         return res, int(off[-1])
 
     def barrier():
@@ -824,11 +824,13 @@ def main():
     e2e = {'value': units * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
            # batch modes: every rank uploads the wind once per call plus its share of the proposals and the cells
            'h2d_bytes_per_step': int(wind.nbytes + (proposals[:-(-len(proposals) // world)].nbytes + cells.nbytes if (world > 1 or batch_mode) else 0)),
-           'd2h_bytes_per_step': int(nnz_tot / args.steps * 16 + (ndays + 1) * 8),
+           'd2h_bytes_per_step': (int(nnz_tot / args.steps * 16 + (ndays + 1) * 8) if (world > 1 or batch_mode) else
+                                  int(nnz_tot / args.steps * 12 + ndays * D * 8 + (ndays + 1) * 8)),
            'ms_per_step': e_ms / args.steps, 'timer': 'host wall clock between device synchronisations',
            'api': ('parasitoids_b200.batch.solve_batch: wind from pinned host memory on every rank, sampled cells of all proposals '
                    'all-gathered and copied to host') if (world > 1 or batch_mode) else
-                  'parasitoids_b200.Run.solve(want_coo=True): wind from pinned host memory, COO triplets of all days to host'}
+                  "parasitoids_b200.Run.solve(want_coo='csr'): wind from pinned host memory; the thresholded, renormalised solution of every day to "
+                  'host as CSR arrays (row offsets, int32 column, fp64 value: what Run.main saves, Run.py:490-510)'}
 
     extra = None
     if not args.no_extras and not batch_mode and args.workload == 'synthetic_4097x4097_60d':

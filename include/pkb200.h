@@ -221,7 +221,9 @@ typedef struct pkb_solve_args {
     double r_start;          /* start_time of day 0 for the population model; < 0 none */
     double negval;           /* 1e-8 */
     int want_dense_host;     /* copy dense solutions to host */
-    int want_coo;            /* build COO (row-major) on device and copy to host */
+    int want_coo;            /* 1: build COO (row-major) on device and copy to host (pkb_result_coo); 2: the same triplets as CSR --
+                              * per-row offsets instead of a row index per non-zero, 12 instead of 16 bytes each (pkb_result_csr;
+                              * the layout Run.main saves, Run.py:490-510) */
     int keep_dense_device;   /* keep [ndays][D][D] on device (bench / gather) */
     int sprd;                /* 1: prepend the day-0 spread kernel (pkb_day_args kind 1) built from day.dparams / day.dlparams,
                               * run the chain over ndays + 1 days and drop the first (Bayes_Run.py:245-296) */
@@ -318,6 +320,10 @@ int pkb_result_pre(pkb_result* r, int day, double* out);
 /* COO of all days (host pointers owned by the result, valid until destroy) */
 int pkb_result_coo(pkb_result* r, const long long** day_offsets /*[ndays+1]*/, const int** rows, const int** cols,
                    const double** vals);
+/* CSR of all days (want_coo = 2): triplets of day d are [day_offsets[d], day_offsets[d+1]) of cols / vals; row r of day d starts
+ * at day_offsets[d] + row_offsets[d * dom_len + r] */
+int pkb_result_csr(pkb_result* r, const long long** day_offsets /*[ndays+1]*/, const long long** row_offsets /*[ndays][dom_len]*/,
+                   const int** cols, const double** vals);
 /* gather values at K (row, col) cells for every day: out[ndays][K] */
 int pkb_result_sample(pkb_result* r, const int* cells /*[K][2]*/, int K, double* out);
 /* projection of one solve's dense device-resident days (keep_dense_device / want_dense_host): out[proj->nrows] */

@@ -273,6 +273,29 @@ class SolveResult(object):
         return (o, np.ctypeslib.as_array(rows, shape=(n,)), np.ctypeslib.as_array(cols, shape=(n,)),
                 np.ctypeslib.as_array(vals, shape=(n,)))
 
+    def csr_arrays(self):
+        """(day_offsets[ndays+1], row_offsets[ndays, dom_len], cols, vals) views on the result's pinned host buffers
+        (``solve(..., want_coo='csr')``): the non-zeros of day d are ``[day_offsets[d], day_offsets[d+1])``, row r of that day
+        starts at ``row_offsets[d, r]`` within them."""
+        off, roff, cols, vals = _abi.c_ll_p(), _abi.c_ll_p(), _abi.c_int_p(), _abi.c_double_p()
+        _lib.check(_lib.lib().pkb_result_csr(self.h, C.byref(off), C.byref(roff), C.byref(cols), C.byref(vals)))
+        o = np.ctypeslib.as_array(off, shape=(self.ndays + 1,))
+        ro = np.ctypeslib.as_array(roff, shape=(self.ndays, self.dom_len))
+        n = int(o[-1])
+        if n == 0:
+            return o, ro, np.zeros(0, np.int32), np.zeros(0)
+        return o, ro, np.ctypeslib.as_array(cols, shape=(n,)), np.ctypeslib.as_array(vals, shape=(n,))
+
+    def csr_list(self):
+        """One ``csr_matrix`` per day (what ``Run.main`` saves, Run.py:490-510)."""
+        o, ro, cols, vals = self.csr_arrays()
+        shp = (self.dom_len, self.dom_len)
+        out = []
+        for d in range(self.ndays):
+            indptr = np.append(ro[d], o[d + 1] - o[d]).astype(np.int32)
+            out.append(sparse.csr_matrix((vals[o[d]:o[d + 1]].copy(), cols[o[d]:o[d + 1]].copy(), indptr), shape=shp))
+        return out
+
     def coo_list(self):
         """One ``coo_matrix`` per day (copies out of the pinned buffers)."""
         o, rows, cols, vals = self.coo_arrays()
@@ -328,7 +351,7 @@ def _solve_args(wind, ndays, hparams, Dparams, Dlparams, mu_r, n_periods, rad_di
     a.r_start = -1.0 if r_start is None else float(r_start)
     a.negval = 1e-8
     a.want_dense_host = 1 if want_dense else 0
-    a.want_coo = 1 if want_coo else 0
+    a.want_coo = 2 if want_coo == 'csr' else (1 if want_coo else 0)
     a.keep_dense_device = 1 if keep_device else 0
     a.keep_pre_device = 1 if keep_pre else 0
     if sprd_factor is not None:          # leading local-spread day (Bayes_Run.py:245-270, Bayes_MAP.py:247-277)
@@ -383,11 +406,9 @@ def main(params):
     else:
         dist = params.r_mthd()
         res = solve(wind, ndays, *mp, prob_model=False, r_dur=params.r_dur, r_number=params.r_number,
-                    r_dist=[dist(d + 1) for d in range(params.r_dur)], r_start=params.r_start)
-    modelsol = res.coo_list()
+                    r_dist=[dist(d + 1) for d in range(params.r_dur)], r_start=params.r_start, want_coo='csr')
+    modelsol = res.coo_list() if params.PROB_MODEL else res.csr_list()      # (get_populations returns CSR, CalcSol.py:323)
     res.close()
-    if not params.PROB_MODEL:
-        modelsol = [m.tocsr() for m in modelsol]
     print('Time elapsed: {0}'.format(time.time() - tic))
 
     if params.OUTPUT:

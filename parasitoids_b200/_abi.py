@@ -121,6 +121,7 @@ _SIGS = {
     'pkb_result_dense': (C.c_int, [_H, C.c_int, c_double_p]),
     'pkb_result_pre': (C.c_int, [_H, C.c_int, c_double_p]),
     'pkb_result_coo': (C.c_int, [_H, C.POINTER(c_ll_p), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_double_p)]),
+    'pkb_result_csr': (C.c_int, [_H, C.POINTER(c_ll_p), C.POINTER(c_ll_p), C.POINTER(c_int_p), C.POINTER(c_double_p)]),
     'pkb_result_sample': (C.c_int, [_H, c_int_p, C.c_int, c_double_p]),
     'pkb_result_device_ptr': (C.c_int, [_H, _HP]),
     'pkb_result_destroy': (C.c_int, [_H]),

@@ -1191,7 +1191,8 @@ __global__ void k_coo_write(const double* __restrict__ G, int D, const long long
     for (int c = c0; c < c1; ++c) {
         const double v = row[c];
         if (v != 0.0) {
-            rows[pos] = rr; cols[pos] = c; vals[pos] = v;
+            if (rows) rows[pos] = rr;       // (CSR output carries the row offsets instead)
+            cols[pos] = c; vals[pos] = v;
             ++pos;
         }
     }

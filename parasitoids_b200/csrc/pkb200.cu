@@ -1907,6 +1907,8 @@ struct pkb_result {
     std::vector<char> counted;   // days whose rownnz the emission kernel already filled
     std::vector<char> day_ready; // days whose row counts / event have been enqueued (coo_day_ready)
     HBuf<long long> dayoff;
+    HBuf<long long> rowoff_host;   // CSR output: [ndays][D] first triplet of every row, relative to the day's start
+    bool csr;                      // the result holds CSR pieces (want_coo == 2): no row array
     HBuf<int> rows, cols;
     HBuf<double> vals;
     bool have_coo;
@@ -1961,7 +1963,8 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
         TRY(r->dayoff.alloc(ctx, nd + 1));
         r->dayoff.p[0] = 0;
         st->cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)nd * D * 64);
-        TRY(r->rows.alloc(ctx, st->cap));
+        if (r->csr) TRY(r->rowoff_host.alloc(ctx, (size_t)nd * D));
+        else TRY(r->rows.alloc(ctx, st->cap));
         TRY(r->cols.alloc(ctx, st->cap));
         TRY(r->vals.alloc(ctx, st->cap));
         // one day's triplets at a time through a device staging area (worst case D*D entries)
@@ -1988,7 +1991,7 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
             CU(cudaStreamSynchronize(ctx->cp));                   // copies into the old blocks must have landed
             CU(cudaStreamSynchronize(ctx->cp2));
             const size_t newcap = std::max<size_t>(off + tot + (off + tot) / 4, st->cap * 2);
-            TRY(hbuf_grow(ctx, r->rows, off, newcap));
+            if (!r->csr) TRY(hbuf_grow(ctx, r->rows, off, newcap));
             TRY(hbuf_grow(ctx, r->cols, off, newcap));
             TRY(hbuf_grow(ctx, r->vals, off, newcap));
             st->cap = newcap;
@@ -1997,10 +2000,12 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
         cudaStream_t cs = b ? ctx->cp2 : ctx->cp;
         CU(cudaStreamWaitEvent(cs, ctx->day_events[day], 0));
         LAUNCH_ON(ctx, cs, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
-                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day), st->srow[b].p, st->scol[b].p,
-                  st->sval[b].p);
+                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day),
+                  r->csr ? (int*)nullptr : st->srow[b].p, st->scol[b].p, st->sval[b].p);
+        if (r->csr)
+            CU(cudaMemcpyAsync(r->rowoff_host.p + (size_t)D * day, r->rowoff.p + (size_t)D * day, sizeof(long long) * D, cudaMemcpyDeviceToHost, cs));
         if (tot > 0) {
-            CU(cudaMemcpyAsync(r->rows.p + off, st->srow[b].p, sizeof(int) * tot, cudaMemcpyDeviceToHost, cs));
+            if (!r->csr) CU(cudaMemcpyAsync(r->rows.p + off, st->srow[b].p, sizeof(int) * tot, cudaMemcpyDeviceToHost, cs));
             CU(cudaMemcpyAsync(r->cols.p + off, st->scol[b].p, sizeof(int) * tot, cudaMemcpyDeviceToHost, cs));
             CU(cudaMemcpyAsync(r->vals.p + off, st->sval[b].p, sizeof(double) * tot, cudaMemcpyDeviceToHost, cs));
         }
@@ -2085,6 +2090,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     res->D = D;
     res->max_shape = 2 * mmax + 1;
     res->have_coo = false;
+    res->csr = a->want_coo == 2;
     res->window_steps = 0;
     res->kmeta.assign(ks->hmeta.begin() + k0 + lead, ks->hmeta.begin() + k0 + nd);
     res->smeta.assign(nout, StepMeta());
@@ -3013,9 +3019,19 @@ extern "C" int pkb_result_pre(pkb_result* r, int day, double* out) {
     return sync_check(ctx, "pkb_result_pre");
 }
 
+extern "C" int pkb_result_csr(pkb_result* r, const long long** day_offsets, const long long** row_offsets, const int** cols, const double** vals) {
+    if (!r) return fail(PKB_EINVAL, "pkb_result_csr: NULL result");
+    if (!r->have_coo || !r->csr) return fail(PKB_ESTATE, "pkb_result_csr: solve was run without want_coo = 2");
+    if (day_offsets) *day_offsets = r->dayoff.p;
+    if (row_offsets) *row_offsets = r->rowoff_host.p;
+    if (cols) *cols = r->cols.p;
+    if (vals) *vals = r->vals.p;
+    return 0;
+}
+
 extern "C" int pkb_result_coo(pkb_result* r, const long long** day_offsets, const int** rows, const int** cols, const double** vals) {
     if (!r) return fail(PKB_EINVAL, "pkb_result_coo: NULL result");
-    if (!r->have_coo) return fail(PKB_ESTATE, "pkb_result_coo: solve was run without want_coo");
+    if (!r->have_coo || r->csr) return fail(PKB_ESTATE, "pkb_result_coo: solve was run without want_coo = 1");
     if (day_offsets) *day_offsets = r->dayoff.p;
     if (rows) *rows = r->rows.p;
     if (cols) *cols = r->cols.p;

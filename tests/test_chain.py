@@ -120,6 +120,27 @@ def test_stencil_path_matches_fft_path(pkb):
     pkb._lib.ctx().set_option('stencil_max_radius', 3)
 
 
+def test_get_cursol_uses_the_callers_negval(pkb):
+    """cuda_lib.get_cursol(dom_shape, negval) keeps entries strictly above negval and raises the boundary flag -- and
+    truncates -- when something above NEGVAL (not a fixed 1e-8) has reached the padding (cuda_lib.py:117-136)."""
+    D = 21
+    A = np.zeros((D, D))
+    A[10, D - 1] = 1.0                                   # on the right edge: one third of the mass spills into the padding
+    B = np.full((3, 3), 1.0 / 9.0)
+    v = 1.0 / 9.0                                        # every touched cell holds exactly this (direct stencil, one term each)
+    for negval, kept, flag in ((1e-8, 6, True), (v, 0, False), (0.2, 0, False)):
+        s = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(A), (3, 3))
+        try:
+            s.fftconv2(sparse.csr_matrix(B))
+            sol = s.get_cursol([D, D], negval)
+            assert sol.nnz == kept, (negval, sol.nnz)
+            assert s.last_flag == flag, (negval, s.last_flag)
+            if kept:
+                assert np.all(sol.data > negval) and np.allclose(sol.data, v, rtol=0, atol=1e-16)
+        finally:
+            s.close()
+
+
 def test_filter_limits(pkb):
     A = np.ones((9, 9))
     solver = pkb.cuda_lib.CudaSolve(sparse.coo_matrix(A), (5, 5))
@@ -465,6 +486,31 @@ def test_step_torus_matches_chain_torus(pkb):
         ctx.set_option('step_torus', 1)
         ctx.set_option('windows', 1)
         ctx.set_option('spectral', 1)
+
+
+def test_csr_output_equals_coo_output(pkb):
+    """want_coo='csr': the same row-major triplets with per-row offsets instead of a row index per non-zero (12 instead of
+    16 bytes each across PCIe; the layout Run.main saves, Run.py:490-510)."""
+    rng = np.random.default_rng(2)
+    nd, periods, rad_res, rad_dist = 5, 48, 30, 1500.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        w[:, :, c] = 0.25 * np.sin(np.linspace(0, 5 + c, nd * periods)).reshape(nd, periods) + rng.normal(0, 0.05, (nd, periods))
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    for kw in (dict(prob_model=True), dict(prob_model=False, r_dur=2, r_number=1000.0)):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            a = pkb.Run.solve(w, nd, *args, want_coo=True, **kw)
+            b = pkb.Run.solve(w, nd, *args, want_coo='csr', **kw)
+        coo, csr = a.coo_list(), b.csr_list()
+        for d in range(nd):
+            assert sparse.isspmatrix_csr(csr[d]) and csr[d].nnz == coo[d].nnz
+            assert np.array_equal(csr[d].toarray(), coo[d].toarray())
+            assert csr[d].has_sorted_indices
+        with pytest.raises(pkb._lib.PkbError):
+            b.coo_arrays()
+        a.close(); b.close()
 
 
 def test_spectral_steps_match_exact_steps(pkb):
