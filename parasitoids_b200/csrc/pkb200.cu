@@ -13,6 +13,7 @@
 #include "../../include/pkb200.h"
 #include "phase1.cuh"
 #include "chain.cuh"
+#include "bchain.cuh"
 #include "project.cuh"
 #include "dist.cuh"
 
@@ -126,6 +127,7 @@ struct pkb_ctx {
     int use_step_torus;     // whole-torus steps on the smallest 7-smooth torus >= P + 2m of THAT day's kernel (option "step_torus")
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
     int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
+    int batch_chain;        // pkb_solve_batch: step n of every proposal of a group in ONE launch per pass (bchain.cuh; option "batch_chain", default 1)
     int batch_threads;      // ... enqueued by one host thread per lane (option "batch_threads", default 1 = yes): a Kalbar-sized
                             // chain is ~90 launches of 20-60 us kernels, so one thread issuing four lanes is the bottleneck
     std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
@@ -350,6 +352,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_fusion = 1;
     ctx->batch_lanes = 4;
     ctx->batch_threads = 1;
+    ctx->batch_chain = 1;
     ctx->batch_group = 32;
     ctx->use_step_torus = 1;
     ctx->use_trunc_torus = 1;
@@ -395,6 +398,9 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     TRY(opt_in_smem(k_kernel_rows_batch));
     TRY(opt_in_smem(k_cols));
     TRY(opt_in_smem(k_rows_inv));
+    TRY(opt_in_smem(kb_rows_fwd));
+    TRY(opt_in_smem(kb_cols));
+    TRY(opt_in_smem(kb_rows_inv));
     TRY(opt_in_smem(k_cols_dist));
     TRY(opt_in_smem(k_rows_inv_dist));
     TRY(opt_in_smem(k_fft_test));
@@ -507,6 +513,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "batch_group")) {
         if (value < 1 || value > 1024) return fail(PKB_EINVAL, "batch_group must be 1..1024");
         ctx->batch_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "batch_chain")) {
+        ctx->batch_chain = value != 0;
         return 0;
     }
     if (!strcmp(key, "batch_threads")) {
@@ -2647,6 +2657,252 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Batched chains of a likelihood group (bchain.cuh): step n of every proposal in one launch per pass.
+//
+// Handles what the likelihood batch asks for (sample-cell emission; probability model, or population model with a
+// one-day release, Bayes_Run.py's Kalbar setting) when every step of the proposal is an FFT step whose plans run with
+// PKB_BT threads; `rest` receives the proposals left for the per-proposal path (solve_chain) -- longer releases, stencil
+// steps, tori too large for four resident CTAs, and everything the per-proposal path reports as an error.
+// The geometry of every step follows solve_chain / conv_step exactly (support windows while the exact support fits the
+// domain, then the step's own torus >= P + 2m with the truncated-source torus >= D + 2m beside it), minus the
+// spectral-resident steps and the tau windows, which need a host decision per proposal and step.
+// Everything is enqueued on lc->stream; nothing here waits for the device.
+struct BGeom {
+    ChainDims d;
+    int mmax;
+    std::vector<BStep> steps;      // steps 1 .. nd-1, pointers not yet set
+    size_t oS, oYt, oWt, oKrt, oRs;
+};
+static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, pkb_kset* ks, int nk, const int* cells_dev, int K,
+                                double* dgroup, std::vector<int>* rest) {
+    rest->clear();
+    const pkb_solve_args& a0 = sa[0];
+    const int lead = a0.sprd ? 1 : 0, nd = a0.ndays + lead, nout = a0.ndays;
+    const int D = 2 * ks->rad_res + 1;
+    const double negval = a0.negval > 0 ? a0.negval : 1e-8;
+    if (!lc->batch_chain || nd < 2 || !(a0.prob_model || a0.r_dur == 1)) {
+        for (int p = 0; p < np; ++p) rest->push_back(p);
+        return 0;
+    }
+    std::vector<FftPlan> plans;
+    std::map<int, int> plan_of;         // torus side -> index (-1: not usable here)
+    auto plan_index = [&](int N) -> int {
+        auto it = plan_of.find(N);
+        if (it != plan_of.end()) return it->second;
+        FftPlan pl;
+        int idx = -1;
+        if (get_plan(lc, N, &pl) == 0 && pl.grid_rows >= 1 && pl.grid_cols >= 1 && pl.threads == PKB_BT && pl.cols_threads == PKB_BT) {
+            idx = (int)plans.size();
+            plans.push_back(pl);
+        }
+        plan_of[N] = idx;
+        return idx;
+    };
+    std::vector<BGeom> geo;
+    std::vector<int> who;               // proposal (index in the group) of geo[i]
+    geo.reserve(np);
+    for (int p = 0; p < np; ++p) {
+        const int k0 = p * nk;
+        auto krad = [&](int i) { return ks->hmeta[k0 + i].rad; };
+        BGeom g;
+        bool ok = true;
+        int mmax = 0;
+        for (int i = 0; i < nd; ++i) mmax = std::max(mmax, krad(i));
+        for (int i = 1; i < nd && ok; ++i) ok = krad(i) > lc->stencil_max_radius;
+        ChainDims& d = g.d;
+        memset(&d, 0, sizeof d);
+        d.D = D;
+        d.P = D + mmax;
+        d.N = pkb_smooth_len(std::max(2, d.P + 2 * mmax));
+        d.Nc = d.N / 2 + 1;
+        d.ldS = roundup(d.P, 16);
+        d.ldY = roundup(d.P, 2);
+        d.ldW = roundup(d.N, 2);
+        d.ldK = roundup(2 * mmax + 1, 2);
+        g.mmax = mmax;
+        ok = ok && krad(0) <= D / 2 && d.N > 0 && plan_index(d.N) >= 0;
+        int wr0 = D / 2 - krad(0), wn = 2 * krad(0) + 1;
+        bool wmode = lc->use_windows != 0;
+        for (int n = 1; n < nd && ok; ++n) {
+            const int m = krad(n);
+            if (2 * m > d.P) { ok = false; break; }
+            BStep s;
+            memset(&s, 0, sizeof s);
+            s.m = m;
+            s.Wk = ks->W;
+            s.d = d;
+            if (wmode && wr0 - m >= 0 && wr0 + wn + m <= D && pkb_smooth_len(wn + 2 * m) < d.N) {
+                s.d.win = 1; s.d.wr0 = s.d.wc0 = wr0; s.d.wn = wn;
+                s.d.N = pkb_smooth_len(std::max(2, wn + 2 * m));
+                s.d.Nc = s.d.N / 2 + 1;
+                s.d.ldY = roundup(wn, 2);
+                s.d.ldW = roundup(s.d.N, 2);
+                s.d.ldK = roundup(2 * m + 1, 2);
+                wr0 -= m; wn += 2 * m;
+                s.plan = s.plan_t = plan_index(s.d.N);
+            } else {
+                wmode = false;
+                if (lc->use_step_torus) {
+                    const int Nd = pkb_smooth_len(std::max(2, d.P + 2 * m));
+                    if (Nd < d.N && plan_index(Nd) >= 0) {
+                        s.d.N = Nd;
+                        s.d.Nc = Nd / 2 + 1;
+                        s.d.ldW = roundup(Nd, 2);
+                    }
+                }
+                s.plan = s.plan_t = plan_index(s.d.N);
+                if (lc->use_trunc_torus) {
+                    const int Nt = pkb_smooth_len(std::max(2, D + 2 * m));
+                    const int it = Nt < s.d.N ? plan_index(Nt) : -1;
+                    if (it >= 0) {
+                        s.tg.N = Nt; s.tg.Nc = Nt / 2 + 1; s.tg.ldW = roundup(Nt, 2);
+                        s.tg.cols_kb = plans[it].cols_kb;
+                        s.plan_t = it;
+                    }
+                }
+            }
+            if (s.plan < 0) { ok = false; break; }
+            s.cols_kb = plans[s.plan].cols_kb;
+            g.steps.push_back(s);
+        }
+        if (!ok) { rest->push_back(p); continue; }
+        geo.push_back(std::move(g));
+        who.push_back(p);
+    }
+    g_err.clear();                      // (plans that could not be made only mean "not here")
+    const int nb = (int)geo.size();
+    if (nb == 0) return 0;
+    CU(cudaEventRecord(lc->ev[1], lc->stream));
+
+    // one slab per kind of buffer, every proposal at its own offset (32-byte aligned: the spectra are accessed as 32-byte pairs)
+    size_t tS = 0, tYt = 0, tWt = 0, tKrt = 0, tRs = 0;
+    int mmax_all = 0;
+    for (BGeom& g : geo) {
+        const ChainDims& d = g.d;
+        g.oS = tS;   tS += 2 * (size_t)d.P * d.ldS;
+        g.oYt = tYt; tYt += spec_size(d.Nc + 1, d.ldY);       // (multiples of PKB_CB elements)
+        g.oWt = tWt; tWt += spec_size(d.Nc + 1, d.ldW);
+        g.oKrt = tKrt; tKrt += spec_size(d.Nc + 1, d.ldK);
+        g.oRs = tRs; tRs += (size_t)d.P;
+        mmax_all = std::max(mmax_all, g.mmax);
+    }
+    DBuf<double> S;
+    DBuf<cplx> Yt, Wt, Krt, scr;
+    DBuf<RowStats> rstat;
+    DBuf<ChainCtrl> ctrl;
+    DBuf<StepMeta> dsm;
+    TRY(S.alloc(lc, tS));
+    TRY(Yt.alloc(lc, tYt));
+    TRY(Wt.alloc(lc, tWt));
+    TRY(Krt.alloc(lc, tKrt));
+    TRY(rstat.alloc(lc, tRs));
+    TRY(ctrl.alloc(lc, nb));
+    TRY(dsm.alloc(lc, (size_t)nb * nd));
+    CU(cudaMemsetAsync(S.p, 0, tS * sizeof(double), lc->stream));
+    CU(cudaMemsetAsync(rstat.p, 0, tRs * sizeof(RowStats), lc->stream));       // rows a windowed step never touches are zero rows
+    CU(cudaMemsetAsync(ctrl.p, 0, sizeof(ChainCtrl) * nb, lc->stream));
+    CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nb * nd, lc->stream));
+
+    // descriptors: steps [n - 1][i], job tables [n - 1][pass][i], emissions [n][i], day-0 placement [i]
+    const int ns = nd - 1;
+    std::vector<BStep> hsteps((size_t)ns * nb);
+    std::vector<int> hjobs((size_t)ns * 3 * (nb + 1), 0);
+    std::vector<BEmit> hemit((size_t)nd * nb);
+    std::vector<BInit> hinit(nb);
+    for (int i = 0; i < nb; ++i) {
+        const BGeom& g = geo[i];
+        const pkb_solve_args& a = sa[who[i]];
+        const ChainDims& d = g.d;
+        const int k0 = who[i] * nk;
+        const size_t nW = (size_t)ks->W * ks->W;
+        double* Sb[2] = {S.p + g.oS, S.p + g.oS + (size_t)d.P * d.ldS};
+        double* outp = dgroup + (size_t)who[i] * nout * K;
+        const double w0 = (!a.prob_model && a.r_dist) ? a.r_dist[0] : 1.0;
+        BInit& bi = hinit[i];
+        bi.K = ks->acc.p + nW * k0; bi.S = Sb[0]; bi.ctrl = ctrl.p + i; bi.Wk = ks->W; bi.m = ks->hmeta[k0].rad; bi.ldS = d.ldS; bi.D = D;
+        BEmit& e0 = hemit[i];
+        e0.S = Sb[0]; e0.meta = dsm.p + (size_t)i * nd; e0.out = outp; e0.ldS = d.ldS;
+        e0.mode = lead ? -1 : (a.prob_model ? 0 : 2);
+        e0.w0 = w0; e0.centre_extra = a.r_number * (1 - w0);
+        int cur = 0;
+        for (int n = 1; n < nd; ++n) {
+            BStep s = g.steps[n - 1];
+            s.K = ks->acc.p + nW * (k0 + n);
+            s.src = Sb[cur]; s.dst = Sb[cur ^ 1];
+            cur ^= 1;
+            s.Yt = Yt.p + g.oYt; s.Wt = Wt.p + g.oWt; s.Krt = Krt.p + g.oKrt;
+            s.rstat = rstat.p + g.oRs; s.ctrl = ctrl.p + i; s.meta = dsm.p + (size_t)i * nd + n;
+            hsteps[(size_t)(n - 1) * nb + i] = s;
+            int* jt = hjobs.data() + (size_t)(n - 1) * 3 * (nb + 1);
+            const int rows_in = s.d.win ? s.d.wn : d.P;
+            const int jf = s.m + 1 + (rows_in + 1) / 2;
+            const int jc = s.d.Nc;
+            const int ji = s.d.win ? (s.d.wn + 2 * s.m + 1) / 2
+                                   : std::max(rows_inv_jobs(d.P, s.m), s.tg.N ? rows_inv_jobs_trunc(d.P, d.D, s.m) : 0);
+            jt[0 * (nb + 1) + i + 1] = jf;
+            jt[1 * (nb + 1) + i + 1] = jc;
+            jt[2 * (nb + 1) + i + 1] = ji;
+            BEmit& e = hemit[(size_t)n * nb + i];
+            e.S = s.dst; e.meta = s.meta; e.ldS = d.ldS;
+            e.mode = n < lead ? -1 : (a.prob_model ? 1 : 3);
+            e.out = outp + (size_t)std::max(0, n - lead) * K;
+            e.w0 = w0; e.centre_extra = 0.0;
+        }
+    }
+    for (int n = 0; n < ns; ++n)
+        for (int k = 0; k < 3; ++k) {
+            int* jt = hjobs.data() + ((size_t)n * 3 + k) * (nb + 1);
+            for (int i = 0; i < nb; ++i) jt[i + 1] += jt[i];
+        }
+    DBuf<BStep> dsteps;
+    DBuf<int> djobs;
+    DBuf<BEmit> demit;
+    DBuf<BInit> dinit;
+    DBuf<FftPlan> dplans;
+    TRY(dsteps.alloc(lc, hsteps.size()));
+    TRY(djobs.alloc(lc, hjobs.size()));
+    TRY(demit.alloc(lc, hemit.size()));
+    TRY(dinit.alloc(lc, hinit.size()));
+    TRY(dplans.alloc(lc, plans.size()));
+    // (pageable sources: the copies are staged before these calls return)
+    CU(cudaMemcpyAsync(dsteps.p, hsteps.data(), sizeof(BStep) * hsteps.size(), cudaMemcpyHostToDevice, lc->stream));
+    CU(cudaMemcpyAsync(djobs.p, hjobs.data(), sizeof(int) * hjobs.size(), cudaMemcpyHostToDevice, lc->stream));
+    CU(cudaMemcpyAsync(demit.p, hemit.data(), sizeof(BEmit) * hemit.size(), cudaMemcpyHostToDevice, lc->stream));
+    CU(cudaMemcpyAsync(dinit.p, hinit.data(), sizeof(BInit) * hinit.size(), cudaMemcpyHostToDevice, lc->stream));
+    CU(cudaMemcpyAsync(dplans.p, plans.data(), sizeof(FftPlan) * plans.size(), cudaMemcpyHostToDevice, lc->stream));
+
+    // persistent grids at the largest footprint of the group
+    size_t smem = 1024, scr_per_cta = 0;
+    for (const FftPlan& pl : plans) {
+        smem = std::max(smem, fft_smem_bytes(pl));
+        scr_per_cta = std::max(scr_per_cta, (size_t)pl.cols_kb * plan_radix(pl, pl.nstage - 1) * PKB_BT);
+    }
+    int occ_f = 0, occ_c = 0, occ_i = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, kb_rows_fwd, PKB_BT, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, kb_cols, PKB_BT, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, kb_rows_inv, PKB_BT, smem));
+    if (occ_f < 1 || occ_c < 1 || occ_i < 1) return fail(PKB_ELIMIT, "batched chain kernels cannot be resident with %zu bytes of shared memory", smem);
+    const int cap = std::max(lc->occ_cap, 1);
+    const int gmax_f = std::min(occ_f, cap) * lc->sm_count, gmax_c = std::min(occ_c, cap) * lc->sm_count, gmax_i = std::min(occ_i, cap) * lc->sm_count;
+    TRY(scr.alloc(lc, (size_t)gmax_c * scr_per_cta));
+
+    const double rn = a0.r_number;
+    LAUNCH(lc, kb_init, dim3(2 * mmax_all + 1, nb), 128, 0, (const BInit*)dinit.p);
+    LAUNCH(lc, kb_finish, nb, PKB_BT, 0, (const BStep*)nullptr, (const BEmit*)demit.p, cells_dev, K, D, rn, negval);
+    for (int n = 1; n < nd; ++n) {
+        const BStep* st = dsteps.p + (size_t)(n - 1) * nb;
+        const int* jt = djobs.p + (size_t)(n - 1) * 3 * (nb + 1);
+        const int* hj = hjobs.data() + (size_t)(n - 1) * 3 * (nb + 1);
+        LAUNCH(lc, kb_rows_fwd, std::min(hj[0 * (nb + 1) + nb], gmax_f), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt, nb);
+        LAUNCH(lc, kb_cols, std::min(hj[1 * (nb + 1) + nb], gmax_c), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt + (nb + 1), nb, scr.p, scr_per_cta);
+        LAUNCH(lc, kb_rows_inv, std::min(hj[2 * (nb + 1) + nb], gmax_i), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt + 2 * (nb + 1), nb, negval);
+        LAUNCH(lc, kb_finish, nb, PKB_BT, 0, st, (const BEmit*)(demit.p + (size_t)n * nb), cells_dev, K, D, rn, negval);
+    }
+    CU(cudaEventRecord(lc->ev[2], lc->stream));
+    return check_launches(lc, "pkb_solve_batch batched chains");
+}
+
 extern "C" int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* a, pkb_result** out) {
     if (!ctx || !a || !out || !a->wind) return fail(PKB_EINVAL, "pkb_solve: NULL argument");
     *out = nullptr;
@@ -2794,6 +3050,7 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         lane->ring_tol = ctx->ring_tol;
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
+        lane->batch_chain = ctx->batch_chain;
     }
     // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel
     // profile into the parent (what pkb_launch_count / pkb_profile_get report)
@@ -2920,9 +3177,22 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         pend.ks = ks; pend.p0 = p0; pend.np = np; pend.buf = gi & 1; pend.live = true; pend.sa = sa_ptr;
         double* dgroup = dout[pend.buf].p;
         const int* dcell_p = dcells.p;
-        auto lane_work = [&pend, ctx, ks, sa_ptr, nk, nd, K, nlanes, np, dgroup, dcell_p](int l) {
+        // step n of every proposal in one launch per pass (bchain.cuh), on lane 0; what that path does not take is left in `rest`
+        auto rest_ptr = std::make_shared<std::vector<int> >();
+        {
+            const int rcc = solve_chains_batched(ctx->lanes[0], sa.data(), np, ks, nk, dcell_p, K, dgroup, rest_ptr.get());
+            if (rcc) {
+                const std::string msg = g_err;
+                finish();
+                g_err = msg;
+                return rcc;
+            }
+        }
+        const int nrest = (int)rest_ptr->size();
+        auto lane_work = [&pend, ctx, ks, sa_ptr, rest_ptr, nrest, nk, nd, K, nlanes, dgroup, dcell_p](int l) {
             cudaSetDevice(ctx->device);                 // (the current device is per host thread)
-            for (int p = l; p < np; p += nlanes) {
+            for (int ir = l; ir < nrest; ir += nlanes) {
+                const int p = (*rest_ptr)[ir];
                 { std::lock_guard<std::mutex> g(pend.mu); if (pend.rc) return; }
                 SampleSink sink = {dcell_p, K, dgroup + (size_t)p * nd * K};
                 const int rc = solve_chain(ctx->lanes[l], &(*sa_ptr)[p], ks, p * nk, nullptr, &sink);
@@ -2936,15 +3206,16 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
 #ifdef PKB_EMUL
         const bool threaded = false;                    // (the CPU emulation of CUDA blocks is not re-entrant)
 #else
-        const bool threaded = ctx->batch_threads && nlanes > 1 && np > 1;
+        const bool threaded = ctx->batch_threads && nlanes > 1 && nrest > 1;
 #endif
         if (threaded) {
             // the workers keep enqueueing while this thread goes on to build the next group's kernels; finish() joins them
             for (int l = 0; l < nlanes; ++l) pend.workers.emplace_back(lane_work, l);
         } else {
-            for (int p = 0; p < np && !pend.rc; ++p) {
+            for (int ir = 0; ir < nrest && !pend.rc; ++ir) {
+                const int p = (*rest_ptr)[ir];
                 SampleSink sink = {dcell_p, K, dgroup + (size_t)p * nd * K};
-                pend.rc = solve_chain(ctx->lanes[p % nlanes], &sa[p], ks, p * nk, nullptr, &sink);
+                pend.rc = solve_chain(ctx->lanes[ir % nlanes], &sa[p], ks, p * nk, nullptr, &sink);
                 if (pend.rc) pend.msg = g_err;
             }
             if (pend.rc) {

@@ -107,6 +107,61 @@ def test_solve_batch_matches_single_solves(pkb, prob_model, lanes, group):
         ctx.set_option('batch_group', 32)
 
 
+@pytest.mark.parametrize('prob_model,group,sprd,big', [(False, 32, None, False), (False, 2, None, True), (True, 32, None, True),
+                                                       (False, 32, 0.6, False)])
+def test_batched_chain_matches_per_proposal_chain(pkb, prob_model, group, sprd, big):
+    """Batched chain kernels (csrc/bchain.cuh: step n of every proposal of a group in one launch per pass) against
+    (i) the per-proposal chains of the same library call (option batch_chain = 0) and (ii) one Run.solve per proposal,
+    for the population model with a one-day release (the Kalbar setting of Bayes_Run.py), the probability model and
+    the leading spread day.  The launch count shows which path ran.  Small domain: every step flagged (truncated-source
+    torus) and one proposal with stencil-sized kernels, which the batched path leaves to the per-proposal one; big domain:
+    support-window steps, un-flagged and flagged whole-torus steps side by side in one launch."""
+    import warnings
+    from parasitoids_b200 import batch
+    w, props = _wind(nd=8 if big else 6), _proposals(5)
+    props[1, 14] *= 2.5                     # one plume that reaches the boundary early
+    props[1, 13] = 3
+    kw = dict(SOLVE_KW, ndays=6, r_dur=1, r_start=None)
+    if big:
+        props[:, 14] *= 0.25
+        kw.update(ndays=8, rad_dist=3000.0, rad_res=60)
+    if prob_model:
+        kw.update(prob_model=True, r_number=1.0)
+    if sprd is not None:
+        kw.update(ndays=5, sprd_factor=sprd)
+    ctx = pkb._lib.ctx()
+    ctx.set_option('batch_group', group)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            l0 = ctx.launch_count()
+            got = batch.solve_batch(w, props, CELLS, **kw)
+            n_batched = ctx.launch_count() - l0
+            ctx.set_option('batch_chain', 0)
+            l0 = ctx.launch_count()
+            ref = batch.solve_batch(w, props, CELLS, **kw)
+            n_single = ctx.launch_count() - l0
+            assert n_batched < n_single, (n_batched, n_single)
+            assert ((got != 0) != (ref != 0)).sum() == 0
+            assert np.allclose(got, ref, rtol=1e-12, atol=1e-15)
+            if not prob_model:
+                # same steps, same jobs, same summation orders: the population path (no spectral-resident steps, no tau windows) is bit-identical
+                assert np.array_equal(got, ref)
+            if sprd is None:
+                for b in range(5):
+                    hp, dp, dl, mu_r, n_periods = batch.unpack_proposal(props[b])
+                    res = pkb.Run.solve(w, kw['ndays'], hp, dp, dl, mu_r, n_periods, kw['rad_dist'], kw['rad_res'],
+                                        prob_model=prob_model, r_dur=kw['r_dur'], r_number=kw['r_number'], r_start=kw['r_start'],
+                                        want_coo=False, keep_device=True)
+                    one = res.sample(CELLS)
+                    res.close()
+                    assert ((got[b] != 0) != (one != 0)).sum() == 0
+                    assert np.allclose(got[b], one, rtol=1e-12, atol=1e-15)
+    finally:
+        ctx.set_option('batch_chain', 1)
+        ctx.set_option('batch_group', 32)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
