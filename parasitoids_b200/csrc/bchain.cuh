@@ -22,6 +22,10 @@
 #include "chain.cuh"
 
 #define PKB_BT 128          // CTA size of every batched chain kernel (what get_plan picks whenever >= 4 transforms fit an SM)
+#ifndef PKB_BCH_B
+#define PKB_BCH_B 4         // resident CTAs per SM the batched kernels are compiled for (register cap 65536 / (PKB_BT * PKB_BCH_B))
+#endif
+#define PKB_BCH_LB __launch_bounds__(PKB_BT, PKB_BCH_B)
 
 namespace pkb {
 
@@ -103,7 +107,7 @@ __device__ __forceinline__ void b_select(BShared* sh, cplx* x, const BStep* __re
 
 // grid = persistent over job0[nprob] jobs, block = PKB_BT.  Jobs of proposal p: [job0[p], job0[p] + m + 1) kernel rows,
 // then (rows + 1) / 2 forward row pairs (host upper bound; a truncated source has fewer).
-__global__ void PKB_ROWS_LB kb_rows_fwd(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob) {
+__global__ void PKB_BCH_LB kb_rows_fwd(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(BShared, shm, 1);
     BShared* sh = shm;
@@ -147,7 +151,7 @@ __global__ void PKB_ROWS_LB kb_rows_fwd(const BStep* __restrict__ steps, const F
 
 // grid = persistent, block = PKB_BT.  Jobs of proposal p: its spectral columns (Nc of the step's own torus; the
 // truncated-source torus has fewer).  scr: gridDim.x slices of scr_per_cta complex.
-__global__ void PKB_COLS_LB kb_cols(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob,
+__global__ void PKB_BCH_LB kb_cols(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob,
                                     cplx* __restrict__ scr, size_t scr_per_cta) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(BShared, shm, 1);
@@ -215,7 +219,7 @@ __global__ void PKB_COLS_LB kb_cols(const BStep* __restrict__ steps, const FftPl
 
 // grid = persistent, block = PKB_BT.  Jobs of proposal p: the inverse row jobs of k_rows_inv (host upper bound over
 // both geometries).  The step's flag / sums are reduced by kb_finish.
-__global__ void PKB_ROWS_LB kb_rows_inv(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob,
+__global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob,
                                         double negval) {
     PKB_DYN_SMEM(raw);
     PKB_SHARED(BShared, shm, 1);

@@ -128,6 +128,7 @@ struct pkb_ctx {
     int batch_group;        // pkb_solve_batch: proposals per kernel-construction group (option "batch_group", default PKB_BATCH_GROUP)
     int batch_lanes;        // pkb_solve_batch: proposals in flight at once, each on its own child context (option "batch_lanes")
     int batch_chain;        // pkb_solve_batch: step n of every proposal of a group in ONE launch per pass (bchain.cuh; option "batch_chain", default 1)
+    int batch_occ;          // ... with this many resident CTAs per SM (option "batch_occ", default PKB_BCH_B)
     int batch_threads;      // ... enqueued by one host thread per lane (option "batch_threads", default 1 = yes): a Kalbar-sized
                             // chain is ~90 launches of 20-60 us kernels, so one thread issuing four lanes is the bottleneck
     std::vector<pkb_ctx*> lanes;     // child contexts (own streams, pools and plans) of the likelihood batch
@@ -353,6 +354,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->batch_lanes = 4;
     ctx->batch_threads = 1;
     ctx->batch_chain = 1;
+    ctx->batch_occ = PKB_BCH_B;
     ctx->batch_group = 32;
     ctx->use_step_torus = 1;
     ctx->use_trunc_torus = 1;
@@ -513,6 +515,11 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "batch_group")) {
         if (value < 1 || value > 1024) return fail(PKB_EINVAL, "batch_group must be 1..1024");
         ctx->batch_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "batch_occ")) {
+        if (value < 1 || value > 16) return fail(PKB_EINVAL, "batch_occ must be 1..16");
+        ctx->batch_occ = (int)value;
         return 0;
     }
     if (!strcmp(key, "batch_chain")) {
@@ -2662,8 +2669,10 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
 //
 // Handles what the likelihood batch asks for (sample-cell emission; probability model, or population model with a
 // one-day release, Bayes_Run.py's Kalbar setting) when every step of the proposal is an FFT step whose plans run with
-// PKB_BT threads; `rest` receives the proposals left for the per-proposal path (solve_chain) -- longer releases, stencil
-// steps, tori too large for four resident CTAs, and everything the per-proposal path reports as an error.
+// PKB_BT threads; `rest` receives the proposals left for the per-proposal path (solve_chain) -- longer releases, tori too
+// large for four resident CTAs, and everything the per-proposal path reports as an error.  (Days whose kernel is small
+// enough for the direct stencil take the FFT path here: the same convolution to rounding, and a proposal with one calm
+// day stays in the group.)
 // The geometry of every step follows solve_chain / conv_step exactly (support windows while the exact support fits the
 // domain, then the step's own torus >= P + 2m with the truncated-source torus >= D + 2m beside it), minus the
 // spectral-resident steps and the tau windows, which need a host decision per proposal and step.
@@ -2709,7 +2718,6 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
         bool ok = true;
         int mmax = 0;
         for (int i = 0; i < nd; ++i) mmax = std::max(mmax, krad(i));
-        for (int i = 1; i < nd && ok; ++i) ok = krad(i) > lc->stencil_max_radius;
         ChainDims& d = g.d;
         memset(&d, 0, sizeof d);
         d.D = D;
@@ -2883,10 +2891,22 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, kb_cols, PKB_BT, smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, kb_rows_inv, PKB_BT, smem));
     if (occ_f < 1 || occ_c < 1 || occ_i < 1) return fail(PKB_ELIMIT, "batched chain kernels cannot be resident with %zu bytes of shared memory", smem);
-    const int cap = std::max(lc->occ_cap, 1);
+    const int cap = std::max(lc->batch_occ, 1);
     const int gmax_f = std::min(occ_f, cap) * lc->sm_count, gmax_c = std::min(occ_c, cap) * lc->sm_count, gmax_i = std::min(occ_i, cap) * lc->sm_count;
     TRY(scr.alloc(lc, (size_t)gmax_c * scr_per_cta));
 
+    if (getenv("PKB_BCHAIN_DEBUG")) {
+        long long jf = 0, jc = 0, ji = 0, wsteps = 0, sumN = 0, sumP = 0, summ = 0;
+        for (int n = 0; n < ns; ++n) {
+            const int* hj = hjobs.data() + (size_t)n * 3 * (nb + 1);
+            jf += hj[nb]; jc += hj[(nb + 1) + nb]; ji += hj[2 * (nb + 1) + nb];
+        }
+        for (const BStep& s : hsteps) { wsteps += s.d.win; sumN += s.d.N; sumP += s.d.P; summ += s.m; }
+        fprintf(stderr, "bchain: %d of %d proposals, %d steps each (%lld window steps), mean N %.0f P %.0f m %.0f, %zu plans, smem %zu, occ %d/%d/%d (cap %d), "
+                "jobs fwd %lld cols %lld inv %lld, slabs S %.0f MB Yt %.0f Wt %.0f Krt %.0f\n", nb, np, ns, wsteps, (double)sumN / hsteps.size(),
+                (double)sumP / hsteps.size(), (double)summ / hsteps.size(), plans.size(), smem, occ_f, occ_c, occ_i, cap, jf, jc, ji, tS * 8e-6, tYt * 16e-6,
+                tWt * 16e-6, tKrt * 16e-6);
+    }
     const double rn = a0.r_number;
     LAUNCH(lc, kb_init, dim3(2 * mmax_all + 1, nb), 128, 0, (const BInit*)dinit.p);
     LAUNCH(lc, kb_finish, nb, PKB_BT, 0, (const BStep*)nullptr, (const BEmit*)demit.p, cells_dev, K, D, rn, negval);
@@ -3051,6 +3071,7 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         lane->rows_desc = ctx->rows_desc;
         lane->prof_on = ctx->prof_on;
         lane->batch_chain = ctx->batch_chain;
+        lane->batch_occ = ctx->batch_occ;
     }
     // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel
     // profile into the parent (what pkb_launch_count / pkb_profile_get report)

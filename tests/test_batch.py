@@ -114,7 +114,7 @@ def test_batched_chain_matches_per_proposal_chain(pkb, prob_model, group, sprd, 
     (i) the per-proposal chains of the same library call (option batch_chain = 0) and (ii) one Run.solve per proposal,
     for the population model with a one-day release (the Kalbar setting of Bayes_Run.py), the probability model and
     the leading spread day.  The launch count shows which path ran.  Small domain: every step flagged (truncated-source
-    torus) and one proposal with stencil-sized kernels, which the batched path leaves to the per-proposal one; big domain:
+    torus) and one proposal with stencil-sized kernels (FFT steps on the batched path); big domain:
     support-window steps, un-flagged and flagged whole-torus steps side by side in one launch."""
     import warnings
     from parasitoids_b200 import batch
@@ -145,8 +145,9 @@ def test_batched_chain_matches_per_proposal_chain(pkb, prob_model, group, sprd, 
             assert ((got != 0) != (ref != 0)).sum() == 0
             assert np.allclose(got, ref, rtol=1e-12, atol=1e-15)
             if not prob_model:
-                # same steps, same jobs, same summation orders: the population path (no spectral-resident steps, no tau windows) is bit-identical
-                assert np.array_equal(got, ref)
+                # same steps, same jobs, same summation orders: the population path (no spectral-resident steps, no tau windows) is
+                # bit-identical -- except for a proposal with stencil-sized kernels, which the batched path runs through the FFT
+                assert np.array_equal(np.delete(got, 1, axis=0), np.delete(ref, 1, axis=0))
             if sprd is None:
                 for b in range(5):
                     hp, dp, dl, mu_r, n_periods = batch.unpack_proposal(props[b])
