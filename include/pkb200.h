@@ -105,7 +105,11 @@ int pkb_sync(pkb_ctx* ctx);
  * "ring_tol" (support-ring decisions of get_mvn_cdf_values closer than this to cdf_eps are re-taken with the reference's
  *             own running sum, ParasitoidModel.py:345-373; default 1e-12, 1.0 forces that path everywhere),
  * "batch_lanes" (1..8: proposals of pkb_solve_batch in flight at once, default 4),
- * "batch_group" (proposals per kernel-construction group of pkb_solve_batch, default 32).
+ * "batch_group" (proposals per kernel-construction group of pkb_solve_batch, default 32),
+ * "batch_chain" (0/1: the chains of a group run as batched kernels -- step n of every proposal in one launch per pass,
+ *               csrc/bchain.cuh -- instead of one chain per proposal on the lanes, default 1; probability model and
+ *               one-day releases, the other proposals take the per-proposal path either way),
+ * "batch_occ" (resident CTAs per SM the batched chain kernels are launched for, default 4).
  * All of them select between implementations of the same arithmetic; results agree to rounding. */
 int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
 /* device time in ms of the phases of the last pkb_solve: [0] phase 1,
@@ -244,7 +248,8 @@ int pkb_solve(pkb_ctx* ctx, const pkb_solve_args* args, pkb_result** out);
  * n_periods mu_r); everything else (wind, domain, release settings) from `base`.  out[nprop][ndays][K]
  * receives the model at the K (row, col) sample cells -- what popdensity_to_emergence / popdensity_grid
  * read (Bayes_funcs.py:58-74,167-173); status[nprop][ndays] (may be NULL) the PKB_ST_* bits of every
- * (proposal, day) kernel.  Kernel construction is batched over groups of proposals. */
+ * (proposal, day) kernel.  Kernel construction is batched over groups of proposals, and so are the chains: step n of
+ * every proposal of a group is one launch per pass (csrc/bchain.cuh). */
 int pkb_solve_batch(pkb_ctx* ctx, const pkb_solve_args* base, const double* proposals, int nprop, const int* cells /*[K][2]*/, int K,
                     double* out, int* status);
 /* ---- likelihood projection: Bayes_funcs.py:20-180 on the device --------------------------------------------
