@@ -109,7 +109,9 @@ int pkb_sync(pkb_ctx* ctx);
  * "batch_chain" (0/1: the chains of a group run as batched kernels -- step n of every proposal in one launch per pass,
  *               csrc/bchain.cuh -- instead of one chain per proposal on the lanes, default 1; probability model and
  *               one-day releases, the other proposals take the per-proposal path either way),
- * "batch_occ" (resident CTAs per SM the batched chain kernels are launched for, default 4).
+ * "batch_occ" (resident CTAs per SM the batched chain kernels are launched for, default 4),
+ * "coo_thread" (0/1: the per-day COO / CSR compaction and D2H of pkb_solve are enqueued by a helper host thread instead of
+ *              the thread that paces the chain, default 1).
  * All of them select between implementations of the same arithmetic; results agree to rounding. */
 int pkb_set_option(pkb_ctx* ctx, const char* key, double value);
 /* device time in ms of the phases of the last pkb_solve: [0] phase 1,

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -88,6 +90,8 @@ struct pkb_ctx {
     cudaStream_t cp2;       // second copy stream: the days alternate, so one day's compaction overlaps the previous day's copies
     cudaEvent_t ev_cp2;
     std::vector<cudaEvent_t> day_events;
+    std::vector<cudaEvent_t> emit_events;   // day d of the fused solve has been emitted (the COO worker thread waits for it)
+    int coo_thread;         // the per-day COO / CSR compaction + D2H of pkb_solve is driven by a helper host thread (option "coo_thread", default 1)
     std::vector<cudaEvent_t> win_events;
     cudaEvent_t ev_cp;
     size_t coo_hint;        // triplets of the last solve (initial size of the next one's host buffers)
@@ -146,7 +150,10 @@ static size_t bucket(size_t n) {
     return ((n + step - 1) / step) * step;
 }
 
+// (the pools of a context are touched by its COO worker thread as well as by the thread that owns the context)
+static std::mutex g_pool_mu;
 static int dev_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
     const size_t b = bucket(bytes);
     std::vector<void*>& fl = ctx->dev_free[b];
     if (!fl.empty()) {
@@ -171,12 +178,14 @@ static int dev_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
 }
 static void dev_release(pkb_ctx* ctx, void* p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
     auto it = ctx->dev_live.find(p);
     if (it == ctx->dev_live.end()) return;
     ctx->dev_free[it->second].push_back(p);
     ctx->dev_live.erase(it);
 }
 static int host_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
     const size_t b = bucket(bytes);
     std::vector<void*>& fl = ctx->host_free[b];
     if (!fl.empty()) {
@@ -193,6 +202,7 @@ static int host_alloc(pkb_ctx* ctx, size_t bytes, void** out) {
 }
 static void host_release(pkb_ctx* ctx, void* p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
     auto it = ctx->host_live.find(p);
     if (it == ctx->host_live.end()) return;
     ctx->host_free[it->second].push_back(p);
@@ -353,6 +363,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->use_fusion = 1;
     ctx->batch_lanes = 4;
     ctx->batch_threads = 1;
+    ctx->coo_thread = 1;
     ctx->batch_chain = 1;
     ctx->batch_occ = PKB_BCH_B;
     ctx->batch_group = 32;
@@ -440,6 +451,7 @@ extern "C" int pkb_destroy(pkb_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_step[i]); cudaEventDestroy(ctx->ev_emit[i]); }
     for (cudaEvent_t e : ctx->day_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->emit_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->win_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->box_events) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ring_events[i]);
@@ -524,6 +536,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "batch_chain")) {
         ctx->batch_chain = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "coo_thread")) {
+        ctx->coo_thread = value != 0;
         return 0;
     }
     if (!strcmp(key, "batch_threads")) {
@@ -1938,13 +1954,20 @@ struct pkb_result {
 // 16-byte D2H, and queues that day's compaction + triplet copy on the copy stream
 // (coo_pump) -- so the 16 bytes/non-zero cross PCIe while later days are still
 // being computed.
-static int coo_day_ready(pkb_ctx* ctx, pkb_result* r, int day, cudaStream_t strm) {
+// wl != nullptr: called from the COO worker thread -- launches are counted there instead of in the context (whose counters
+// and profile records belong to the thread that runs the chain)
+#define COO_LAUNCH(wl, ctx, strm, kern, grid, block, smem, ...)                 \
+    do {                                                                        \
+        if (wl) { PKB_LAUNCH(kern, grid, block, smem, (strm), __VA_ARGS__); ++*(wl); } \
+        else LAUNCH_ON(ctx, strm, kern, grid, block, smem, __VA_ARGS__);        \
+    } while (0)
+static int coo_day_ready(pkb_ctx* ctx, pkb_result* r, int day, cudaStream_t strm, long long* wl = nullptr) {
     const int D = r->D;
     const size_t nD = (size_t)D * D;
     if (!r->counted[day])
-        LAUNCH_ON(ctx, strm, k_row_nnz, D, 256, 0, (const double*)(r->dense.p + nD * day), D, r->rownnz.p + (size_t)D * day);
-    LAUNCH_ON(ctx, strm, k_row_scan, 1, 1024, 0, (const int*)(r->rownnz.p + (size_t)D * day), D, 1, r->rowoff.p + (size_t)D * day,
-              r->daytot.p + 2 * day);
+        COO_LAUNCH(wl, ctx, strm, k_row_nnz, D, 256, 0, (const double*)(r->dense.p + nD * day), D, r->rownnz.p + (size_t)D * day);
+    COO_LAUNCH(wl, ctx, strm, k_row_scan, 1, 1024, 0, (const int*)(r->rownnz.p + (size_t)D * day), D, 1, r->rowoff.p + (size_t)D * day,
+               r->daytot.p + 2 * day);
     CU(cudaMemcpyAsync(r->tot_host.p + 2 * day, r->daytot.p + 2 * day, 2 * sizeof(long long), cudaMemcpyDeviceToHost, strm));
     CU(cudaEventRecord(ctx->day_events[day], strm));
     r->day_ready[day] = 1;
@@ -1973,14 +1996,15 @@ struct CooState {
     bool started = false;
 };
 
-static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
-    const int D = r->D, nd = r->ndays;
+// upto: handle days < upto only; finish: join the copy streams into the main stream (the last call)
+static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block, int upto = 1 << 30, bool finish = true, long long* wl = nullptr) {
+    const int D = r->D, nd = std::min(r->ndays, upto);
     const size_t nD = (size_t)D * D;
     if (!st->started) {
-        TRY(r->dayoff.alloc(ctx, nd + 1));
+        TRY(r->dayoff.alloc(ctx, r->ndays + 1));
         r->dayoff.p[0] = 0;
-        st->cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)nd * D * 64);
-        if (r->csr) TRY(r->rowoff_host.alloc(ctx, (size_t)nd * D));
+        st->cap = std::max<size_t>(ctx->coo_hint + ctx->coo_hint / 16, (size_t)r->ndays * D * 64);
+        if (r->csr) TRY(r->rowoff_host.alloc(ctx, (size_t)r->ndays * D));
         else TRY(r->rows.alloc(ctx, st->cap));
         TRY(r->cols.alloc(ctx, st->cap));
         TRY(r->vals.alloc(ctx, st->cap));
@@ -2016,9 +2040,9 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
         const int b = day & 1;
         cudaStream_t cs = b ? ctx->cp2 : ctx->cp;
         CU(cudaStreamWaitEvent(cs, ctx->day_events[day], 0));
-        LAUNCH_ON(ctx, cs, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
-                  (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day),
-                  r->csr ? (int*)nullptr : st->srow[b].p, st->scol[b].p, st->sval[b].p);
+        COO_LAUNCH(wl, ctx, cs, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
+                   (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day),
+                   r->csr ? (int*)nullptr : st->srow[b].p, st->scol[b].p, st->sval[b].p);
         if (r->csr)
             CU(cudaMemcpyAsync(r->rowoff_host.p + (size_t)D * day, r->rowoff.p + (size_t)D * day, sizeof(long long) * D, cudaMemcpyDeviceToHost, cs));
         if (tot > 0) {
@@ -2027,7 +2051,7 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
             CU(cudaMemcpyAsync(r->vals.p + off, st->sval[b].p, sizeof(double) * tot, cudaMemcpyDeviceToHost, cs));
         }
     }
-    if (block) {
+    if (block && finish) {
         CU(cudaEventRecord(ctx->ev_cp, ctx->cp));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_cp, 0));
         CU(cudaEventRecord(ctx->ev_cp2, ctx->cp2));
@@ -2037,6 +2061,66 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block) {
     }
     return 0;
 }
+
+// The per-day output work of the fused solve -- row scan, a 16-byte D2H to learn the day's size, compaction kernel, the copies
+// of the day's triplets -- is ~10 runtime calls per day.  The chain of a probability-model solve is paced by its own host
+// thread (tau windows: step n is sized from the extent step n - 1 reports), so on the chain's thread those calls sat between
+// one step's ticket and the next step's launch (C4: chain phase 13.2 -> 20.7 ms with CSR output).  Here a helper thread does
+// them: the chain's thread records one event per emitted day and hands the day over.
+struct CooWorker {
+    pkb_ctx* ctx = nullptr;
+    pkb_result* r = nullptr;
+    CooState* st = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> q;
+    bool done = false, running = false;
+    int rc = 0;
+    std::string msg;
+    long long launches = 0;
+    void start(pkb_ctx* c, pkb_result* res, CooState* s) {
+        ctx = c; r = res; st = s;
+        running = true;
+        th = std::thread([this]() { run(); });
+    }
+    void push(int day) {
+        { std::lock_guard<std::mutex> g(mu); q.push_back(day); }
+        cv.notify_one();
+    }
+    void run() {
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            int day;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [this]() { return done || !q.empty(); });
+                if (q.empty()) return;
+                day = q.front();
+                q.pop_front();
+            }
+            if (rc) continue;                   // (drain the queue after an error)
+            cudaStream_t cs = (day & 1) ? ctx->cp2 : ctx->cp;
+            int e = 0;
+            if (cudaStreamWaitEvent(cs, ctx->emit_events[day], 0) != cudaSuccess) e = fail(PKB_ECUDA, "COO worker: waiting for day %d failed", day);
+            if (!e) e = coo_day_ready(ctx, r, day, cs, &launches);
+            if (!e) e = coo_pump(ctx, r, st, true, day + 1, false, &launches);
+            if (e) { rc = e; msg = g_err; }
+        }
+    }
+    // all days handed over: wait for the worker; its error (if any) becomes this thread's
+    int join() {
+        if (!running) return 0;
+        { std::lock_guard<std::mutex> g(mu); done = true; }
+        cv.notify_one();
+        th.join();
+        running = false;
+        ctx->launches += launches;
+        if (rc) g_err = msg;
+        return rc;
+    }
+    ~CooWorker() { join(); }
+};
 
 static int check_solve_args(const pkb_solve_args* a) {
     if (a->ndays < 1 || a->ndays > a->nd_wind) return fail(PKB_EINVAL, "pkb_solve: ndays %d must be in [1, %d]", a->ndays, a->nd_wind);
@@ -2160,8 +2244,27 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
         }
     }
     // (day: chain day; nothing is emitted for the dropped leading day)
+#ifdef PKB_EMUL
+    const bool coo_threaded = false;                    // (the CPU emulation of CUDA blocks is not re-entrant)
+#else
+    const bool coo_threaded = a->want_coo && ctx->coo_thread && !ctx->prof_on;      // (the per-kernel profile belongs to this thread)
+#endif
+    CooWorker worker;
+    if (coo_threaded) {
+        while ((int)ctx->emit_events.size() < nout) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->emit_events.push_back(e);
+        }
+        worker.start(ctx, res, &coo);
+    }
     auto emitted = [&](int day, cudaStream_t strm) -> int {
         if (!a->want_coo || day < lead) return 0;
+        if (coo_threaded) {
+            CU(cudaEventRecord(ctx->emit_events[day - lead], strm));
+            worker.push(day - lead);
+            return 0;
+        }
         TRY(coo_day_ready(ctx, res, day - lead, strm));
         return coo_pump(ctx, res, &coo, false);         // whatever is ready by now goes to the host
     };
@@ -2643,6 +2746,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     }
 
     // ---- outputs (the chain is enqueued, not finished: compaction and D2H overlap it) ----
+    if (coo_threaded) TRY(worker.join());
     if (a->want_coo) TRY(coo_pump(ctx, res, &coo, true));
     // (pageable destination: this copy blocks the host until the chain has finished, so it comes last)
     CU(cudaMemcpyAsync(res->smeta.data(), dsm.p + lead, sizeof(StepMeta) * nout, cudaMemcpyDeviceToHost, ctx->stream));
