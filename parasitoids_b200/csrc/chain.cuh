@@ -939,8 +939,11 @@ __global__ void k_set_ctrl(ChainCtrl* __restrict__ ctrl, int trunc, int flag) {
 // out[r][c] = r_small_vals(S[:D,:D], prob_model) densely (CalcSol.py:112-136)
 // grid = D, block = 256
 // strict != 0: keep v > negval (cuda_lib.py:117-119) instead of !(v < negval)
+// sparse_only != 0: `out` is only an intermediate of the COO / CSR compaction (k_coo_write with the same meta), which reads
+// nothing outside the rows and columns this step computed -- the zeros there are not written (a support-window day of the
+// 4097^2 solve touches a few hundred columns of its 134 MB grid)
 __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const StepMeta* __restrict__ meta, double negval, int prob_model,
-                             int strict, double* __restrict__ out, int* __restrict__ rownnz) {
+                             int strict, double* __restrict__ out, int* __restrict__ rownnz, int sparse_only) {
     PKB_SHARED(int, cnt, 1);
     const double add = prob_model ? meta->add : 0.0;
     const int wr0 = meta->wr0, wr1 = meta->wr1;          // row-windowed step: the other rows were not computed (all below PKB_SPEC_TAU)
@@ -951,7 +954,8 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
         const double* src = S + (size_t)r * d.ldS;
         double* dst = out + (size_t)r * d.D;
         if (wr1 > wr0 && (r < wr0 || r >= wr1)) {
-            for (int c = threadIdx.x; c < d.D; c += blockDim.x) dst[c] = 0.0;
+            if (!sparse_only)
+                for (int c = threadIdx.x; c < d.D; c += blockDim.x) dst[c] = 0.0;
             if (rownnz && threadIdx.x == 0) rownnz[r] = 0;
             continue;
         }
@@ -962,8 +966,9 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
         }
         int n = 0;
         const int T = blockDim.x;
-        int c = threadIdx.x;
-        for (; c + 3 * T < d.D; c += 4 * T) {          // four independent loads in flight per thread
+        const int cbeg = sparse_only ? wc0 : 0, cend = sparse_only ? wc1 : d.D;
+        int c = cbeg + threadIdx.x;
+        for (; c + 3 * T < cend; c += 4 * T) {          // four independent loads in flight per thread
             double v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = (c + u * T >= wc0 && c + u * T < wc1) ? src[c + u * T] : 0.0;
@@ -975,7 +980,7 @@ __global__ void k_emit_dense(const double* __restrict__ S, ChainDims d, const St
                 n += o != 0.0 ? 1 : 0;
             }
         }
-        for (; c < d.D; c += T) {
+        for (; c < cend; c += T) {
             const double v = (c >= wc0 && c < wc1) ? src[c] : 0.0;
             const bool keep = strict ? (v > negval) : (v != 0.0 && !(v < negval));
             const double o = keep ? v + add : 0.0;
@@ -1167,13 +1172,15 @@ __global__ void __launch_bounds__(1024) k_row_scan(const int* __restrict__ rownn
 }
 // grid = ndays*D, block = 256.  Each thread owns a contiguous segment of the row: count its
 // non-zeros, one block-wide exclusive scan of the 256 counts, ordered write.
+// meta (optional): only the columns [wc0, wc1) this day's step computed can hold a non-zero (k_emit_dense, sparse_only)
 __global__ void k_coo_write(const double* __restrict__ G, int D, const long long* __restrict__ rowoff, const int* __restrict__ rownnz,
-                            int* __restrict__ rows, int* __restrict__ cols, double* __restrict__ vals) {
+                            int* __restrict__ rows, int* __restrict__ cols, double* __restrict__ vals, const StepMeta* __restrict__ meta) {
     PKB_SHARED(int, cnt, 256);
     const int r = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     if (rownnz[r] == 0) return;        // thresholded solutions are mostly empty rows: do not even read them
-    const int seg = (D + T - 1) / T;
-    const int c0 = tid * seg, c1 = c0 + seg < D ? c0 + seg : D;
+    const int w0 = (meta && meta->wc1 > meta->wc0) ? meta->wc0 : 0, w1 = (meta && meta->wc1 > meta->wc0) ? meta->wc1 : D;
+    const int seg = (w1 - w0 + T - 1) / T;
+    const int c0 = w0 + tid * seg, c1 = c0 + seg < w1 ? c0 + seg : w1;
     const double* row = G + (size_t)r * D;
     int n = 0;
     for (int c = c0; c < c1; ++c) n += row[c] != 0.0 ? 1 : 0;

@@ -1554,7 +1554,7 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
     }
     if (out) {
         if (mode == 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)S, d, ch->dout.p, (const StepMeta*)nullptr);
-        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, mode == 1 ? 1 : 0, ch->dout.p, (int*)nullptr);
+        else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)S, d, (const StepMeta*)ch->meta.p, negval, mode == 2 ? 1 : 0, mode == 1 ? 1 : 0, ch->dout.p, (int*)nullptr, 0);
         CU(cudaMemcpyAsync(out, ch->dout.p, (size_t)d.D * d.D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (apply_trunc) {
@@ -1610,7 +1610,7 @@ extern "C" int pkb_chain_back_solve(pkb_chain* ch, const double* const* filters,
         TRY(conv_step(ch, src, src_ctrl, ch->coh[j].p, ch->kup.p, 2 * m + 1, m, ch->Krt.p, false, 1 + j, 1));
         if (out) {
             if (threshold < 0) LAUNCH(ctx, k_copy_domain, d.D, 256, 0, (const double*)ch->coh[j].p, d, ch->dout.p, (const StepMeta*)nullptr);
-            else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p, (int*)nullptr);
+            else LAUNCH(ctx, k_emit_dense, d.D, 256, 0, (const double*)ch->coh[j].p, d, (const StepMeta*)(ch->meta.p + 1 + j), threshold, 0, 1, ch->dout.p, (int*)nullptr, 0);
             CU(cudaMemcpyAsync(out + nd * j, ch->dout.p, nd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
         src = ch->coh[j].p;
@@ -1945,6 +1945,8 @@ struct pkb_result {
     HBuf<int> rows, cols;
     HBuf<double> vals;
     bool have_coo;
+    const StepMeta* win_meta;   // during the solve: per-day step records, when the dense days are only an intermediate of the compaction
+                                // (k_emit_dense sparse_only: nothing outside a day's computed window was written)
 };
 
 // ---- COO output, pipelined with the chain ------------------------------------
@@ -2042,7 +2044,7 @@ static int coo_pump(pkb_ctx* ctx, pkb_result* r, CooState* st, bool block, int u
         CU(cudaStreamWaitEvent(cs, ctx->day_events[day], 0));
         COO_LAUNCH(wl, ctx, cs, k_coo_write, D, 256, 0, (const double*)(r->dense.p + nD * day), D,
                    (const long long*)(r->rowoff.p + (size_t)D * day), (const int*)(r->rownnz.p + (size_t)D * day),
-                   r->csr ? (int*)nullptr : st->srow[b].p, st->scol[b].p, st->sval[b].p);
+                   r->csr ? (int*)nullptr : st->srow[b].p, st->scol[b].p, st->sval[b].p, r->win_meta ? r->win_meta + day : (const StepMeta*)nullptr);
         if (r->csr)
             CU(cudaMemcpyAsync(r->rowoff_host.p + (size_t)D * day, r->rowoff.p + (size_t)D * day, sizeof(long long) * D, cudaMemcpyDeviceToHost, cs));
         if (tot > 0) {
@@ -2191,6 +2193,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     res->D = D;
     res->max_shape = 2 * mmax + 1;
     res->have_coo = false;
+    res->win_meta = nullptr;
     res->csr = a->want_coo == 2;
     res->window_steps = 0;
     res->kmeta.assign(ks->hmeta.begin() + k0 + lead, ks->hmeta.begin() + k0 + nd);
@@ -2271,6 +2274,14 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     DBuf<StepMeta> dsm, dcm;
     TRY(dsm.alloc(ctx, nd));
     CU(cudaMemsetAsync(dsm.p, 0, sizeof(StepMeta) * nd, ctx->stream));
+    // the dense days are only an intermediate of the COO / CSR compaction: the emission writes, and the compaction reads, nothing
+    // outside the rows and columns a day's step computed (probability model; k_emit_population writes whole days)
+    const bool sparse_only = a->prob_model && a->want_coo && !a->want_dense_host && !a->keep_dense_device && !a->keep_pre_device && !sink;
+    res->win_meta = sparse_only ? dsm.p + lead : nullptr;
+    struct WmGuard {        // (the step records live as long as this call)
+        pkb_result* r;
+        ~WmGuard() { r->win_meta = nullptr; }
+    } wm_guard{res};
     const bool want_cmeta = !sink && !a->prob_model && a->r_dur > 1;
     if (want_cmeta) {
         TRY(dcm.alloc(ctx, (size_t)nd * PKB_MAX_COHORTS));
@@ -2647,7 +2658,7 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_step[n & 1], 0));
             LAUNCH_ON(ctx, ctx->aux, k_emit_dense, ctx->emit_ctas > 0 ? std::min(D, ctx->emit_ctas) : D, ctx->emit_ctas > 0 ? 64 : PKB_EMIT_T, 0,
                       (const double*)ch->S[ch->cur].p, d, (const StepMeta*)(dsm.p + n), negval, 1, 0,
-                      res->dense.p + nD * (n - lead), a->want_coo ? res->rownnz.p + (size_t)D * (n - lead) : (int*)nullptr);
+                      res->dense.p + nD * (n - lead), a->want_coo ? res->rownnz.p + (size_t)D * (n - lead) : (int*)nullptr, sparse_only ? 1 : 0);
             if (a->want_coo) res->counted[n - lead] = 1;
             CU(cudaEventRecord(ctx->ev_emit[n & 1], ctx->aux));
             TRY(emitted(n, ctx->aux));
