@@ -27,7 +27,9 @@ namespace pkb {
 #define PKB_ST_BORDERLINE 128     // ring-growth test within ring_tol of cdf_eps: decided by the reference-order running sum (:345-373)
 
 #define PKB_CDF_EPS 0.001
-#define PKB_LATTICE_CAP 5120      // doubles of shared memory for the corner lattice tile
+#define PKB_LATTICE_CAP 5120      // doubles of shared memory for the corner lattice tile, at most (lattices up to CAP / 2 corners per side)
+#define PKB_TILE_TARGET 3840      // ... and what k_period is launched with unless a lattice row pair needs more: with 6 nmax doubles of
+                                  // marginals beside it, six 128-thread CTAs fit an SM (85 registers, __launch_bounds__(256, 3))
 #define PKB_BVN_SEG 12            // lattice corners a thread marches along one column (k_period)
 
 // Per-period contributions are accumulated EXACTLY and order-independently: every contribution x = h[t] * cdf (a
@@ -344,7 +346,7 @@ __device__ __forceinline__ int py_slice_len(int start, int stop, int n) {
 // ---------------------------------------------------------------------------
 // grid = (periods, problems), block = 64 / 128 / 256 by lattice size (pkb200.cu), dyn smem = (6*nmax + tile_cap) doubles, tile_cap = min(PKB_LATTICE_CAP, nmax^2)
 // acc: per problem (2*racc+1)^2 window centred on the release cell
-__global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
+__global__ void __launch_bounds__(256, 3) k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
                          const double* __restrict__ hprob, int periods, int nmax, int tile_cap, double* __restrict__ acc,
                          double* __restrict__ acc_lo, int racc, double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
     PKB_DYN_SMEM(raw);
@@ -463,8 +465,11 @@ __global__ void k_period(const DayParams* __restrict__ dps, const BvnPar* __rest
         }
         __syncthreads();
         const int ncell = ny * nc;
-        for (int q = tid; q < ncell; q += T) {
-            const int iy = q / nc, ix = q - iy * nc;
+        // (row / column of a thread's cells advance incrementally: an integer division per cell was a fifth of this loop)
+        int iy = tid / nc, ix = tid - iy * nc;
+        const int dyT = T / nc, dxT = T - dyT * nc;
+        for (int q = tid; q < ncell; q += T, iy += dyT, ix += dxT) {
+            if (ix >= nc) { ix -= nc; ++iy; }
             const double* u = U + iy * n + ix;
             const double v = u[0] - u[1] - u[n] + u[n + 1];     // BVNMVN 4-term difference
             const int jj = y0 + iy - h;                          // y index (up)

@@ -999,7 +999,9 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
     if (keep_pre) TRY(ks->pre.alloc(ctx, nel * nprob));
 
     // lattice tile: the whole (nmax x nmax) corner lattice when it fits, so that small supports leave room for more CTAs per SM
-    const int tile_cap = (int)std::min<size_t>(PKB_LATTICE_CAP, (size_t)nmax * nmax);
+    int tile_target = PKB_TILE_TARGET;
+    if (const char* env = getenv("PKB_TILE_TARGET")) tile_target = std::max(256, std::min(PKB_LATTICE_CAP, atoi(env)));      // tuning hook
+    const int tile_cap = (int)std::min<size_t>(nmax > tile_target / 2 ? PKB_LATTICE_CAP : tile_target, (size_t)nmax * nmax);
     const size_t smem = (6 * (size_t)nmax + tile_cap) * sizeof(double);
     // CTA size: a period is a short, latency-bound job (set-up, lattice, differencing, with barriers in between), so
     // small supports get small CTAs and more of them per SM (C4, 48 x 48 lattice: 256 threads 1.83 ms, 64 threads 1.23 ms)
