@@ -335,28 +335,10 @@ __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const Ff
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
         const int Dc = D - col0;                                     // first pad column, relative to col0
         bool e_a = false, e_b = false;                               // a cell >= PKB_SPEC_TAU in this row (RowStats::has_e)
-        for (int c = tid; c < ncols; c += T) {
-            cplx z;
-            if (tr) {
-                // columns fold like the rows: lin[c] (c < E) + lin[c - P] (c >= Lo), straight from the transform
-                z = (c < E && !zjob) ? x[c] : zero;
-                if (c >= Lo && !zjob) z = cadd(z, x[N - (P - c)]);
-            } else {
-                z = x[d.win ? (c < m ? c - m + N : c - m) : c];
-            }
-            const double va = (fold ? z.x + z.y : z.x) * scale;
-            dst_a[c] = va;
-            e_a |= fabs(va) >= PKB_SPEC_TAU;
-            if (pad_a || c >= Dc) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
-            else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
-            if (out_b >= 0) {
-                const double vb = z.y * scale;
-                dst_b[c] = vb;
-                e_b |= fabs(vb) >= PKB_SPEC_TAU;
-                if (pad_b || c >= Dc) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
-                else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
-            }
-        }
+        unsigned cmask = 0;                                          // (column extents are not tracked here: exact support windows)
+        if (tr) rows_inv_emit<2>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, (int*)nullptr, tid, T);
+        else if (d.win) rows_inv_emit<1>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, (int*)nullptr, tid, T);
+        else rows_inv_emit<0>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, (int*)nullptr, tid, T);
         if (e_a) st[2] += PKB_HAS_E_UNIT;
         if (e_b) st[6] += PKB_HAS_E_UNIT;
         __syncthreads();                               // every thread is done reading x: reuse it as scratch

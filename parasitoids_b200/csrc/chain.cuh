@@ -681,6 +681,50 @@ __device__ __forceinline__ void rows_inv_decode_trunc(int job, int m, int P, int
     }
 }
 
+// Output loop of an inverse-row job: the new state row(s) from the transform buffer x, with the per-row statistics
+// (st[0..3]: row a -- pad max, kept sum, kept count, max |pad|; st[4..7]: row b) and the "holds a cell >= PKB_SPEC_TAU" flags.
+// One instantiation per geometry so that the loop carries no mode tests: MODE 0 whole torus (columns already folded in
+// place), 1 support window (the result lies inside the domain: no pad cells, no fold; the columns holding a cell >= TAU are
+// collected in a per-thread bit mask -- bit k for column tid + k T -- instead of one global store per cell), 2 truncated
+// source (columns fold like the rows, straight from the transform).  Same arithmetic and order as one generic loop.
+template <int MODE>
+__device__ __forceinline__ void rows_inv_emit(const cplx* x, double* __restrict__ dst_a, double* __restrict__ dst_b, bool has_b, bool fold, bool zjob,
+                                              int ncols, int m, int N, int P, int E, int Lo, bool pad_a, bool pad_b, int Dc, double scale,
+                                              double negval, double (&st)[8], bool& e_a, bool& e_b, unsigned& cmask, int* colflag_far, int tid, int T) {
+    const cplx zero = cmake(0.0, 0.0);
+    int kk = 0;
+    for (int c = tid; c < ncols; c += T, ++kk) {
+        cplx z;
+        if (MODE == 2) {
+            z = (c < E && !zjob) ? x[c] : zero;
+            if (c >= Lo && !zjob) z = cadd(z, x[N - (P - c)]);
+        } else if (MODE == 1) {
+            z = x[c < m ? c - m + N : c - m];
+        } else {
+            z = x[c];
+        }
+        const double va = ((MODE != 1 && fold) ? z.x + z.y : z.x) * scale;
+        dst_a[c] = va;
+        const bool ea1 = fabs(va) >= PKB_SPEC_TAU;
+        e_a |= ea1;
+        if (MODE != 1 && (pad_a || c >= Dc)) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
+        else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
+        bool eb1 = false;
+        if (has_b) {
+            const double vb = z.y * scale;
+            dst_b[c] = vb;
+            eb1 = fabs(vb) >= PKB_SPEC_TAU;
+            e_b |= eb1;
+            if (MODE != 1 && (pad_b || c >= Dc)) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
+            else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
+        }
+        if (MODE == 1 && (ea1 || eb1)) {
+            if (kk < 32) cmask |= 1u << kk;
+            else if (colflag_far) colflag_far[c] = 1;      // (more than 32 columns per thread: straight to the flags)
+        }
+    }
+}
+
 // grid = persistent over rows_inv_jobs(P, m) jobs, block = T
 // A job is one inverse transform.  "Pair" jobs carry two interior output rows as
 // real and imaginary part; "fold" jobs carry the two linear-convolution rows that
@@ -735,6 +779,7 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
     // one output row and never a fused forward transform -- so they go last and the partial final round of
     // the persistent grid is made of short jobs instead of the longest ones.
     const bool descending = desc_order && !d.win && !tr && !si.rowwin;
+    unsigned cmask = 0;      // support-window steps: columns (tid + k T of the result window) in which this thread saw a cell >= PKB_SPEC_TAU
     for (int it = blockIdx.x; it < njobs; it += gridDim.x) {
         const int job = descending ? njobs - 1 - it : it;
         int ra, rb, out_a, out_b;
@@ -842,32 +887,10 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
         const bool pad_a = out_a >= D, pad_b = out_b >= D;
         const int Dc = D - col0;                                     // first pad column, relative to col0
         bool e_a = false, e_b = false;                               // a cell >= PKB_SPEC_TAU in this row (RowStats::has_e)
-        for (int c = tid; c < ncols; c += T) {
-            cplx z;
-            if (tr) {
-                // columns fold like the rows: lin[c] (c < E) + lin[c - P] (c >= Lo), straight from the transform
-                z = (c < E && !zjob) ? x[c] : zero;
-                if (c >= Lo && !zjob) z = cadd(z, x[N - (P - c)]);
-            } else {
-                z = x[d.win ? (c < m ? c - m + N : c - m) : c];
-            }
-            const double va = (fold ? z.x + z.y : z.x) * scale;
-            dst_a[c] = va;
-            const bool ea1 = fabs(va) >= PKB_SPEC_TAU;
-            e_a |= ea1;
-            if (ea1 && si.colflag) si.colflag[col0 + c] = 1;
-            if (pad_a || c >= Dc) { st[0] = fmax(st[0], va); st[3] = fmax(st[3], fabs(va)); }
-            else if (!(va < negval)) { st[1] += va; st[2] += 1.0; }
-            if (out_b >= 0) {
-                const double vb = z.y * scale;
-                dst_b[c] = vb;
-                const bool eb1 = fabs(vb) >= PKB_SPEC_TAU;
-                e_b |= eb1;
-                if (eb1 && si.colflag) si.colflag[col0 + c] = 1;
-                if (pad_b || c >= Dc) { st[4] = fmax(st[4], vb); st[7] = fmax(st[7], fabs(vb)); }
-                else if (!(vb < negval)) { st[5] += vb; st[6] += 1.0; }
-            }
-        }
+        int* cfar = si.colflag ? si.colflag + col0 : (int*)nullptr;
+        if (tr) rows_inv_emit<2>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, cfar, tid, T);
+        else if (d.win) rows_inv_emit<1>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, cfar, tid, T);
+        else rows_inv_emit<0>(x, dst_a, dst_b, out_b >= 0, fold, zjob, ncols, m, N, P, E, Lo, pad_a, pad_b, Dc, scale, negval, st, e_a, e_b, cmask, cfar, tid, T);
         if (e_a) st[2] += PKB_HAS_E_UNIT;
         if (e_b) st[6] += PKB_HAS_E_UNIT;
         __syncthreads();                               // every thread is done reading x: reuse it as scratch
@@ -898,6 +921,12 @@ __global__ void PKB_ROWS_LB k_rows_inv(const cplx* __restrict__ Wt, int m, Chain
             __syncthreads();
         }
     }
+    if (si.colflag && cmask) {
+        int* cf = si.colflag + (d.wc0 - m);
+        for (int kk = 0; kk < 32; ++kk)
+            if ((cmask >> kk) & 1u) cf[tid + kk * T] = 1;
+    }
+    __syncthreads();
     // the CTA that finishes last reduces the row statistics of the whole state
     if (tid == 0) {
         __threadfence();

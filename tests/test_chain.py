@@ -513,6 +513,40 @@ def test_csr_output_equals_coo_output(pkb):
         a.close(); b.close()
 
 
+def test_sparse_outputs_equal_dense_output(pkb):
+    """COO / CSR output against the dense days of a separate solve, bit for bit.  With sparse output only, the emission
+    writes and the compaction reads just the rows and columns a day's step computed (support windows, k_emit_dense
+    sparse_only), and on the GPU a helper host thread drives the per-day compaction and copies (option coo_thread);
+    neither may change a value or an index."""
+    rng = np.random.default_rng(5)
+    nd, periods, rad_res, rad_dist = 7, 48, 60, 3000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        w[:, :, c] = 0.25 * np.sin(np.linspace(0, 5 + c, nd * periods)).reshape(nd, periods) + rng.normal(0, 0.05, (nd, periods))
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, 0.3 * H.MU_R, 2, rad_dist, rad_res)
+    ctx = pkb._lib.ctx()
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            dense = pkb.Run.solve(w, nd, *args, prob_model=True, want_coo=False, want_dense=True)
+            assert dense.window_steps() >= 2          # the case the sparse-only emission is about
+            ref = [dense.dense(d).copy() for d in range(nd)]
+            dense.close()
+            for thread in (1, 0):
+                ctx.set_option('coo_thread', thread)
+                a = pkb.Run.solve(w, nd, *args, prob_model=True, want_coo=True)
+                b = pkb.Run.solve(w, nd, *args, prob_model=True, want_coo='csr')
+                coo, csr = a.coo_list(), b.csr_list()
+                for d in range(nd):
+                    assert np.array_equal(coo[d].toarray(), ref[d]), (thread, d)
+                    assert np.array_equal(csr[d].toarray(), ref[d]), (thread, d)
+                    assert csr[d].nnz == np.count_nonzero(ref[d]) and csr[d].has_sorted_indices
+                a.close(); b.close()
+    finally:
+        ctx.set_option('coo_thread', 1)
+
+
 def test_spectral_steps_match_exact_steps(pkb):
     """Option spectral: while the content outside the domain is below 1e-13 the chain keeps the product spectrum
     k_cols forms anyway and starts the next step from it (the reference's own chain state is spectral,
