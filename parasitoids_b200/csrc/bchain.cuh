@@ -45,6 +45,7 @@ struct BStep {
     RowStats* rstat;
     ChainCtrl* ctrl;
     StepMeta* meta;         // the day's record
+    int* hint;              // set by kb_rows_inv once a DOMAIN row of the new state shows a cell above the flag threshold outside the domain
 };
 
 // sample-cell emission of one (proposal, day): mode 0 copy (probability model day 0, Run.py:454-458), 1 r_small_vals +
@@ -68,7 +69,7 @@ struct BInit {
 struct BShared {
     BStep st;
     FftPlan plan;
-    int tr, c_trunc;
+    int tr, c_trunc, skip;
 };
 
 // Descriptor of proposal p -> shared memory, geometry switched to the truncated-source torus if the source state is
@@ -217,8 +218,13 @@ __global__ void PKB_BCH_LB kb_cols(const BStep* __restrict__ steps, const FftPla
     }
 }
 
-// grid = persistent, block = PKB_BT.  Jobs of proposal p: the inverse row jobs of k_rows_inv (host upper bound over
-// both geometries).  The step's flag / sums are reduced by kb_finish.
+// grid = persistent, block = PKB_BT.  The job table has TWO entries per proposal: [0, nprob) the inverse row jobs of
+// k_rows_inv (host upper bound over both geometries), [nprob, 2 nprob) -- truncated-source torus only -- the jobs whose
+// output rows all lie outside the domain, which that geometry takes last (rows ascending).  Once a domain row has shown a pad
+// cell above the flag threshold the step is flagged whatever those rows hold (CalcSol.py:36-37), and a flagged state is read
+// as truncated to the domain (:200-201): nobody will read them.  The first pass sets BStep::hint, the second one -- a whole
+// pass over the group later -- skips its jobs when it is set: 38 % of the inverse row jobs of a Kalbar-sized flagged step.
+// The step's flag / sums are reduced by kb_finish.
 __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const FftPlan* __restrict__ plans, const int* __restrict__ job0, int nprob,
                                         double negval) {
     PKB_DYN_SMEM(raw);
@@ -227,15 +233,20 @@ __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const Ff
     cplx* x = reinterpret_cast<cplx*>(raw);
     double* red = reinterpret_cast<double*>(raw);       // reduction scratch: start of the transform buffer, idle when used
     const int tid = threadIdx.x, T = blockDim.x;
-    const int total = job0[nprob];
+    const int total = job0[2 * nprob];
     const cplx zero = cmake(0.0, 0.0);
     int p = -1, pn = 0;
     for (int g = blockIdx.x; g < total; g += gridDim.x) {
         while (g >= job0[pn + 1]) ++pn;
         if (pn != p) {
             p = pn;
-            b_select(sh, x, steps, plans, p, tid, T);
+            b_select(sh, x, steps, plans, p < nprob ? p : p - nprob, tid, T);
+            if (p >= nprob) {
+                if (tid == 0) sh->skip = *reinterpret_cast<volatile int*>(sh->st.hint);
+                __syncthreads();
+            }
         }
+        const int part = p < nprob ? 0 : 1;
         const FftPlan& plan = sh->plan;
         const ChainDims& d = sh->st.d;
         cplx* tws = x + plan.N;
@@ -244,7 +255,10 @@ __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const Ff
         const int P = d.P, N = d.N, D = d.D, Nc = d.Nc;
         const int wout = d.wn + 2 * m;                       // window mode: side of the result
         const int njobs = d.win ? (wout + 1) / 2 : (tr ? rows_inv_jobs_trunc(P, D, m) : rows_inv_jobs(P, m));
-        const int job = g - job0[p];
+        const int ndom = tr ? (D + 1) / 2 : njobs;          // truncated-source torus: the row pairs that start inside the domain come first
+        int job = g - job0[p];
+        if (part == 0 && job >= ndom) continue;
+        if (part == 1) job += ndom;
         if (job >= njobs) continue;
         const double scale = 1.0 / ((double)N * (double)N);
         const int E = D + m, Lo = P - m;                     // truncated mode: extent of the positive rows / columns, first folded one
@@ -267,6 +281,15 @@ __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const Ff
             else { rb = -1; out_b = -1; }
         } else {
             rows_inv_decode(job, m, P, N, ra, rb, out_a, out_b, fold);
+        }
+        if (part == 1 && sh->skip) {
+            // (see the kernel's header: the step is flagged whatever these rows hold; only its recorded pad maximum differs)
+            if (tid == 0 || (tid == 1 && out_b >= 0)) {
+                RowStats rs;
+                rs.padmax = 1.0; rs.ksum = 0.0; rs.padabs = 1.0; rs.kcnt = 0; rs.has_e = 0;
+                sh->st.rstat[tid ? out_b : out_a] = rs;
+            }
+            continue;
         }
         // scatter the Hermitian pair Z = A + iB into digit-reversed order; each thread
         // handles two adjacent columns (32-byte loads per row)
@@ -352,6 +375,7 @@ __global__ void PKB_BCH_LB kb_rows_inv(const BStep* __restrict__ steps, const Ff
             rs.has_e = q[2] >= PKB_HAS_E_UNIT ? 1 : 0;
             rs.kcnt = (int)(q[2] - floor(q[2] / PKB_HAS_E_UNIT) * PKB_HAS_E_UNIT);
             sh->st.rstat[tid ? out_b : out_a] = rs;
+            if (!d.win && (tid ? out_b : out_a) < D && rs.padmax > 1e-8) *reinterpret_cast<volatile int*>(sh->st.hint) = 1;
         }
         __syncthreads();
     }
@@ -398,7 +422,7 @@ __global__ void kb_finish(const BStep* __restrict__ steps, const BEmit* __restri
             si.c0 = s.d.wc0 - s.m; si.c1 = si.c0 + wout;
         }
         step_finalize_block(s.rstat, s.d, s.ctrl, s.meta, 1, red, tid, T, si, 1e-8);
-        if (tid == 0) s.ctrl->fused = 0;
+        if (tid == 0) { s.ctrl->fused = 0; *s.hint = 0; }
         __syncthreads();                                 // (the emission below reads the record thread 0 just wrote)
     }
     const BEmit e = emits[p];

@@ -2917,6 +2917,9 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
     DBuf<RowStats> rstat;
     DBuf<ChainCtrl> ctrl;
     DBuf<StepMeta> dsm;
+    DBuf<int> hint;
+    TRY(hint.alloc(lc, nb));
+    CU(cudaMemsetAsync(hint.p, 0, sizeof(int) * nb, lc->stream));
     TRY(S.alloc(lc, tS));
     TRY(Yt.alloc(lc, tYt));
     TRY(Wt.alloc(lc, tWt));
@@ -2932,7 +2935,8 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
     // descriptors: steps [n - 1][i], job tables [n - 1][pass][i], emissions [n][i], day-0 placement [i]
     const int ns = nd - 1;
     std::vector<BStep> hsteps((size_t)ns * nb);
-    std::vector<int> hjobs((size_t)ns * 3 * (nb + 1), 0);
+    const int jstride = 2 * (nb + 1) + (2 * nb + 1);      // per step: forward rows [nb + 1], columns [nb + 1], inverse rows [2 nb + 1] (two passes)
+    std::vector<int> hjobs((size_t)ns * jstride, 0);
     std::vector<BEmit> hemit((size_t)nd * nb);
     std::vector<BInit> hinit(nb);
     for (int i = 0; i < nb; ++i) {
@@ -2957,17 +2961,21 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
             s.src = Sb[cur]; s.dst = Sb[cur ^ 1];
             cur ^= 1;
             s.Yt = Yt.p + g.oYt; s.Wt = Wt.p + g.oWt; s.Krt = Krt.p + g.oKrt;
-            s.rstat = rstat.p + g.oRs; s.ctrl = ctrl.p + i; s.meta = dsm.p + (size_t)i * nd + n;
+            s.rstat = rstat.p + g.oRs; s.ctrl = ctrl.p + i; s.meta = dsm.p + (size_t)i * nd + n; s.hint = hint.p + i;
             hsteps[(size_t)(n - 1) * nb + i] = s;
-            int* jt = hjobs.data() + (size_t)(n - 1) * 3 * (nb + 1);
+            int* jt = hjobs.data() + (size_t)(n - 1) * jstride;
             const int rows_in = s.d.win ? s.d.wn : d.P;
             const int jf = s.m + 1 + (rows_in + 1) / 2;
             const int jc = s.d.Nc;
-            const int ji = s.d.win ? (s.d.wn + 2 * s.m + 1) / 2
-                                   : std::max(rows_inv_jobs(d.P, s.m), s.tg.N ? rows_inv_jobs_trunc(d.P, d.D, s.m) : 0);
+            // inverse rows: first pass every job of the step's own geometry (on the truncated-source torus only the (D + 1) / 2 row
+            // pairs that start inside the domain), second pass the rest of the truncated-source torus (kb_rows_inv)
+            const int ndom_t = (d.D + 1) / 2;
+            const int ji = s.d.win ? (s.d.wn + 2 * s.m + 1) / 2 : std::max(rows_inv_jobs(d.P, s.m), s.tg.N ? ndom_t : 0);
+            const int ji2 = (!s.d.win && s.tg.N) ? std::max(0, rows_inv_jobs_trunc(d.P, d.D, s.m) - ndom_t) : 0;
             jt[0 * (nb + 1) + i + 1] = jf;
             jt[1 * (nb + 1) + i + 1] = jc;
             jt[2 * (nb + 1) + i + 1] = ji;
+            jt[2 * (nb + 1) + nb + i + 1] = ji2;
             BEmit& e = hemit[(size_t)n * nb + i];
             e.S = s.dst; e.meta = s.meta; e.ldS = d.ldS;
             e.mode = n < lead ? -1 : (a.prob_model ? 1 : 3);
@@ -2975,11 +2983,12 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
             e.w0 = w0; e.centre_extra = 0.0;
         }
     }
-    for (int n = 0; n < ns; ++n)
-        for (int k = 0; k < 3; ++k) {
-            int* jt = hjobs.data() + ((size_t)n * 3 + k) * (nb + 1);
-            for (int i = 0; i < nb; ++i) jt[i + 1] += jt[i];
-        }
+    for (int n = 0; n < ns; ++n) {
+        int* jt = hjobs.data() + (size_t)n * jstride;
+        for (int k = 0; k < 2; ++k)
+            for (int i = 0; i < nb; ++i) jt[k * (nb + 1) + i + 1] += jt[k * (nb + 1) + i];
+        for (int i = 0; i < 2 * nb; ++i) jt[2 * (nb + 1) + i + 1] += jt[2 * (nb + 1) + i];
+    }
     DBuf<BStep> dsteps;
     DBuf<int> djobs;
     DBuf<BEmit> demit;
@@ -3015,8 +3024,8 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
     if (getenv("PKB_BCHAIN_DEBUG")) {
         long long jf = 0, jc = 0, ji = 0, wsteps = 0, sumN = 0, sumP = 0, summ = 0;
         for (int n = 0; n < ns; ++n) {
-            const int* hj = hjobs.data() + (size_t)n * 3 * (nb + 1);
-            jf += hj[nb]; jc += hj[(nb + 1) + nb]; ji += hj[2 * (nb + 1) + nb];
+            const int* hj = hjobs.data() + (size_t)n * jstride;
+            jf += hj[nb]; jc += hj[(nb + 1) + nb]; ji += hj[2 * (nb + 1) + 2 * nb];
         }
         for (const BStep& s : hsteps) { wsteps += s.d.win; sumN += s.d.N; sumP += s.d.P; summ += s.m; }
         fprintf(stderr, "bchain: %d of %d proposals, %d steps each (%lld window steps), mean N %.0f P %.0f m %.0f, %zu plans, smem %zu, occ %d/%d/%d (cap %d), "
@@ -3029,11 +3038,11 @@ static int solve_chains_batched(pkb_ctx* lc, const pkb_solve_args* sa, int np, p
     LAUNCH(lc, kb_finish, nb, PKB_BT, 0, (const BStep*)nullptr, (const BEmit*)demit.p, cells_dev, K, D, rn, negval);
     for (int n = 1; n < nd; ++n) {
         const BStep* st = dsteps.p + (size_t)(n - 1) * nb;
-        const int* jt = djobs.p + (size_t)(n - 1) * 3 * (nb + 1);
-        const int* hj = hjobs.data() + (size_t)(n - 1) * 3 * (nb + 1);
+        const int* jt = djobs.p + (size_t)(n - 1) * jstride;
+        const int* hj = hjobs.data() + (size_t)(n - 1) * jstride;
         LAUNCH(lc, kb_rows_fwd, std::min(hj[0 * (nb + 1) + nb], gmax_f), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt, nb);
         LAUNCH(lc, kb_cols, std::min(hj[1 * (nb + 1) + nb], gmax_c), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt + (nb + 1), nb, scr.p, scr_per_cta);
-        LAUNCH(lc, kb_rows_inv, std::min(hj[2 * (nb + 1) + nb], gmax_i), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt + 2 * (nb + 1), nb, negval);
+        LAUNCH(lc, kb_rows_inv, std::min(hj[2 * (nb + 1) + 2 * nb], gmax_i), PKB_BT, smem, st, (const FftPlan*)dplans.p, jt + 2 * (nb + 1), nb, negval);
         LAUNCH(lc, kb_finish, nb, PKB_BT, 0, st, (const BEmit*)(demit.p + (size_t)n * nb), cells_dev, K, D, rn, negval);
     }
     CU(cudaEventRecord(lc->ev[2], lc->stream));
