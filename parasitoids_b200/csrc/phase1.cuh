@@ -566,10 +566,15 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     }
     // exact two-plane accumulator (acc_add_exact) -> doubles, in place
     const double* al = acc_lo + (size_t)prob * nel;
-    for (int q = tid; q < nsub; q += T) { const int i = at(q); a[i] = acc_exact_to_double(a[i], al[i]); }
-    __syncthreads();
+    // (sum and minimum taken in the same sweep: same values, same order per thread as a second sweep would give)
     double s = 0.0, mn = 0.0;
-    for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
+    for (int q = tid; q < nsub; q += T) {
+        const int i = at(q);
+        const double v = acc_exact_to_double(a[i], al[i]);
+        a[i] = v;
+        s += v; mn = fmin(mn, v);
+    }
+    __syncthreads();
     const double pmfsum = block_sum(s, red);
     const double pmin = block_min(mn, red);
     const double loss = sh[0];
@@ -583,18 +588,29 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
         const int ncl = 2 * hl + 1;
         const double cell = dp.cell, r = cell / 2;
         const double wgt = 1.0 - total;
+        // The two assertions after the blob (:586-590) only need the new total and minimum.  The blob adds w * v to a few
+        // cells: the total is the old one plus what was added, and with the old minimum above -1e-8 no cell can have dropped
+        // below it unless a blob cell itself came out that negative -- so the second sweep over the window only runs when
+        // the first assertion already failed (both statuses are errors for the caller either way).
+        double added = 0.0, bmn = 0.0;
         for (int q = tid; q < ncl * ncl; q += T) {
             const int iy = q / ncl, ix = q - iy * ncl;      // iy: y index + hl, ix: x index + hl
             const double xl = (ix - hl) * cell - r, yl = (iy - hl) * cell - r;
             const double v = mvn_rect(bl, xl, xl + cell, yl, yl + cell, 0.0, 0.0);
             const int row = racc - (iy - hl), col = racc + (ix - hl);
-            a[(size_t)row * W + col] += wgt * v;
+            const double nv = a[(size_t)row * W + col] + wgt * v;
+            a[(size_t)row * W + col] = nv;
+            added += wgt * v; bmn = fmin(bmn, nv);
         }
         __syncthreads();
-        s = 0.0; mn = 0.0;
-        for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
-        const double sum2 = block_sum(s, red);
-        const double min2 = block_min(mn, red);
+        double sum2 = pmfsum + block_sum(added, red);
+        double min2 = fmin(pmin, block_min(bmn, red));
+        if (!(pmin >= -1e-8)) {
+            s = 0.0; mn = 0.0;
+            for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
+            sum2 = block_sum(s, red);
+            min2 = block_min(mn, red);
+        }
         if (!(min2 >= -1e-8)) status |= PKB_ST_PMF_NEG2;
         if (!(sum2 + loss <= 1.00001)) status |= PKB_ST_TOT_GT1;
     }
