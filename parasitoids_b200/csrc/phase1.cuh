@@ -346,7 +346,10 @@ __device__ __forceinline__ int py_slice_len(int start, int stop, int n) {
 // ---------------------------------------------------------------------------
 // grid = (periods, problems), block = 64 / 128 / 256 by lattice size (pkb200.cu), dyn smem = (6*nmax + tile_cap) doubles, tile_cap = min(PKB_LATTICE_CAP, nmax^2)
 // acc: per problem (2*racc+1)^2 window centred on the release cell
-__global__ void __launch_bounds__(256, 3) k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
+#ifndef PKB_PERIOD_B
+#define PKB_PERIOD_B 3
+#endif
+__global__ void __launch_bounds__(256, PKB_PERIOD_B) k_period(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, const PeriodInfo* __restrict__ pinfo,
                          const double* __restrict__ hprob, int periods, int nmax, int tile_cap, double* __restrict__ acc,
                          double* __restrict__ acc_lo, int racc, double* __restrict__ loss_t, DayMeta* __restrict__ meta) {
     PKB_DYN_SMEM(raw);
