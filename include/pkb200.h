@@ -110,6 +110,8 @@ int pkb_sync(pkb_ctx* ctx);
  *               csrc/bchain.cuh -- instead of one chain per proposal on the lanes, default 1; probability model and
  *               one-day releases, the other proposals take the per-proposal path either way),
  * "batch_occ" (resident CTAs per SM the batched chain kernels are launched for, default 4),
+ * "fin_clusters" (0/1: k_day_finalize as a thread-block cluster of eight CTAs per (proposal, day) problem when a launch carries
+ *                only a few dozen problems, default 1; same bits as one CTA per problem),
  * "coo_thread" (0/1: the per-day COO / CSR compaction and D2H of pkb_solve are enqueued by a helper host thread instead of
  *              the thread that paces the chain, default 1).
  * All of them select between implementations of the same arithmetic; results agree to rounding. */

@@ -14,6 +14,9 @@
 // the days of a solve (and the proposals of a batch) are the grid's y/z extent.
 #pragma once
 #include "bvn.cuh"
+#if !PKB_IS_EMUL
+#include <cooperative_groups.h>
+#endif
 
 namespace pkb {
 
@@ -495,14 +498,56 @@ __global__ void __launch_bounds__(256, PKB_PERIOD_B) k_period(const DayParams* _
 }
 
 // ---------------------------------------------------------------------------
-// grid = problems, block = 1024.  Works in place on the accumulation window.
-// pre (optional): receives the pre-threshold window (parity export).
+// grid = problems x csize, block = 1024, launched as thread-block CLUSTERS of csize CTAs (csize = 1 or PKB_FIN_SLICES).
+// Works in place on the accumulation window.  pre (optional): receives the pre-threshold window (parity export).
+//
+// The sub-window of a problem is cut into PKB_FIN_SLICES contiguous slices.  Every sum / minimum / maximum over the window is
+// taken per slice (fixed tree inside the CTA) and the slice values are combined in slice order, so the result does not depend on
+// how many CTAs share the work: with csize = 1 one CTA walks all slices (hundreds of problems in a launch: the likelihood batch),
+// with csize = PKB_FIN_SLICES each CTA of the cluster takes one slice and the slice values travel through distributed shared
+// memory (a handful of problems in a launch -- one solve's days -- would otherwise leave most SMs idle for several passes over
+// 5 MB windows).
+#define PKB_FIN_SLICES 8
+struct FinCluster {
+    int csize, crank;
+#if !PKB_IS_EMUL
+    __device__ __forceinline__ void sync() const { if (csize > 1) cooperative_groups::this_cluster().sync(); }
+    // slot `s` of the array `part` in the CTA that owns slice s
+    __device__ __forceinline__ const double* remote(double* part, int s) const {
+        if (csize == 1) return part;
+        return cooperative_groups::this_cluster().map_shared_rank(part, (unsigned)(s / (PKB_FIN_SLICES / csize)));
+    }
+#else
+    void sync() const {}
+    const double* remote(double* part, int) const { return part; }
+#endif
+};
+// part[PKB_FIN_SLICES][3]: this CTA has filled the rows of its own slices; returns the slice-ordered combination of column k
+// (op 0 sum, 1 min, 2 max) to every thread of every CTA of the cluster.  Two cluster barriers: after the fill, after the read.
+__device__ __forceinline__ void fin_combine(const FinCluster& fc, double* part, int ncol, const int* op, double* out) {
+    __syncthreads();
+    fc.sync();
+    for (int k = 0; k < ncol; ++k) {
+        double r = op[k] == 0 ? 0.0 : (op[k] == 1 ? INFINITY : -INFINITY);
+        for (int s = 0; s < PKB_FIN_SLICES; ++s) {
+            const double v = fc.remote(part, s)[s * 3 + k];
+            r = op[k] == 0 ? r + v : (op[k] == 1 ? fmin(r, v) : fmax(r, v));
+        }
+        out[k] = r;
+    }
+    fc.sync();
+    __syncthreads();
+}
 __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restrict__ dps, const BvnPar* __restrict__ bvn, int periods, double* __restrict__ acc,
                                const double* __restrict__ acc_lo, int racc, const double* __restrict__ loss_t, DayMeta* __restrict__ meta,
-                               double negval, double* __restrict__ pre, const PeriodInfo* __restrict__ pinfo) {
+                               double negval, double* __restrict__ pre, const PeriodInfo* __restrict__ pinfo, int csize) {
     PKB_SHARED(double, red, 1024);
     PKB_SHARED(double, sh, 4);
-    const int prob = blockIdx.x;
+    PKB_SHARED(double, part, PKB_FIN_SLICES * 3);
+    FinCluster fc;
+    fc.csize = csize;
+    fc.crank = (int)(blockIdx.x % (unsigned)csize);
+    const int prob = (int)(blockIdx.x / (unsigned)csize);
     const DayParams dp = dps[prob];
     const int P = dp.single ? 1 : periods;
     const int W = 2 * racc + 1;
@@ -524,6 +569,8 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     if (dp.kind) {
         // Day-0 spread kernel (Bayes_Run.py:252-270): sprd = f * longsprd shifted by the integer drift, += (1 - f) *
         // shrtsprd at the centre, centre += max(0, 1 - sum).  No threshold, no renormalisation; its shape is mlen.
+        // (a small blob: the first CTA of the cluster does it alone, no cluster barrier on this path)
+        if (fc.crank != 0) return;
         const PeriodInfo pi = pinfo[(size_t)prob * periods];
         const BvnPar& bs = bvn[dp.bvn_S];
         const BvnPar& bl = bvn[dp.bvn_Sl];
@@ -562,24 +609,31 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
         return;
     }
 
+    // slices of this CTA: [s0, s1); slice s covers the elements [s * chunk, (s + 1) * chunk) of the sub-window
+    const int per = PKB_FIN_SLICES / csize, s0 = fc.crank * per, s1 = s0 + per;
+    const int chunk = (nsub + PKB_FIN_SLICES - 1) / PKB_FIN_SLICES;
     if (tid == 0) {
         double loss = 0.0;
         for (int t = dp.start_indx; t < P; ++t) loss += loss_t[(size_t)prob * periods + t];   // same order as the loop (:546,558)
         sh[0] = loss;
     }
-    // exact two-plane accumulator (acc_add_exact) -> doubles, in place
+    // exact two-plane accumulator (acc_add_exact) -> doubles, in place; sum and minimum in the same sweep
     const double* al = acc_lo + (size_t)prob * nel;
-    // (sum and minimum taken in the same sweep: same values, same order per thread as a second sweep would give)
-    double s = 0.0, mn = 0.0;
-    for (int q = tid; q < nsub; q += T) {
-        const int i = at(q);
-        const double v = acc_exact_to_double(a[i], al[i]);
-        a[i] = v;
-        s += v; mn = fmin(mn, v);
+    for (int sl = s0; sl < s1; ++sl) {
+        const int lo = sl * chunk, hi = lo + chunk < nsub ? lo + chunk : nsub;
+        double s = 0.0, mn = 0.0;
+        for (int q = lo + tid; q < hi; q += T) {
+            const int i = at(q);
+            const double v = acc_exact_to_double(a[i], al[i]);
+            a[i] = v;
+            s += v; mn = fmin(mn, v);
+        }
+        const double bs = block_sum(s, red), bm = block_min(mn, red);
+        if (tid == 0) { part[sl * 3 + 0] = bs; part[sl * 3 + 1] = bm; }
     }
-    __syncthreads();
-    const double pmfsum = block_sum(s, red);
-    const double pmin = block_min(mn, red);
+    double cmb[3];
+    { const int op[2] = {0, 1}; fin_combine(fc, part, 2, op, cmb); }
+    const double pmfsum = cmb[0], pmin = cmb[1];
     const double loss = sh[0];
     double total = pmfsum + loss;
     if (!(loss >= 0.0)) status |= PKB_ST_NEG_LOSS;
@@ -587,69 +641,98 @@ __global__ void __launch_bounds__(1024) k_day_finalize(const DayParams* __restri
     if (!(pmfsum <= 1.00001)) status |= PKB_ST_PMF_GT1;
     if (total < 0.99999) {
         // wasps that did not fly diffuse locally around the release cell (:581-585)
-        const BvnPar& bl = bvn[dp.bvn_Sl];
-        const int ncl = 2 * hl + 1;
-        const double cell = dp.cell, r = cell / 2;
-        const double wgt = 1.0 - total;
         // The two assertions after the blob (:586-590) only need the new total and minimum.  The blob adds w * v to a few
         // cells: the total is the old one plus what was added, and with the old minimum above -1e-8 no cell can have dropped
-        // below it unless a blob cell itself came out that negative -- so the second sweep over the window only runs when
+        // below it unless a blob cell itself came out that negative -- so a second sweep over the window only runs when
         // the first assertion already failed (both statuses are errors for the caller either way).
+        // (the blob is small: the first CTA of the cluster adds it; the cluster barrier in fin_combine publishes its cells)
         double added = 0.0, bmn = 0.0;
-        for (int q = tid; q < ncl * ncl; q += T) {
-            const int iy = q / ncl, ix = q - iy * ncl;      // iy: y index + hl, ix: x index + hl
-            const double xl = (ix - hl) * cell - r, yl = (iy - hl) * cell - r;
-            const double v = mvn_rect(bl, xl, xl + cell, yl, yl + cell, 0.0, 0.0);
-            const int row = racc - (iy - hl), col = racc + (ix - hl);
-            const double nv = a[(size_t)row * W + col] + wgt * v;
-            a[(size_t)row * W + col] = nv;
-            added += wgt * v; bmn = fmin(bmn, nv);
+        if (fc.crank == 0) {
+            const BvnPar& bl = bvn[dp.bvn_Sl];
+            const int ncl = 2 * hl + 1;
+            const double cell = dp.cell, r = cell / 2;
+            const double wgt = 1.0 - total;
+            for (int q = tid; q < ncl * ncl; q += T) {
+                const int iy = q / ncl, ix = q - iy * ncl;      // iy: y index + hl, ix: x index + hl
+                const double xl = (ix - hl) * cell - r, yl = (iy - hl) * cell - r;
+                const double v = mvn_rect(bl, xl, xl + cell, yl, yl + cell, 0.0, 0.0);
+                const int row = racc - (iy - hl), col = racc + (ix - hl);
+                const double nv = a[(size_t)row * W + col] + wgt * v;
+                a[(size_t)row * W + col] = nv;
+                added += wgt * v; bmn = fmin(bmn, nv);
+            }
+            __threadfence();
         }
-        __syncthreads();
-        double sum2 = pmfsum + block_sum(added, red);
-        double min2 = fmin(pmin, block_min(bmn, red));
+        {
+            // (slot 0 belongs to the first CTA; the other slots carry neutral values)
+            const double ba = block_sum(added, red), bb = block_min(bmn, red);
+            for (int sl = s0; sl < s1; ++sl)
+                if (tid == 0) { part[sl * 3 + 0] = sl == 0 ? ba : 0.0; part[sl * 3 + 1] = sl == 0 ? bb : 0.0; }
+            const int op[2] = {0, 1};
+            fin_combine(fc, part, 2, op, cmb);
+        }
+        double sum2 = pmfsum + cmb[0];
+        double min2 = fmin(pmin, cmb[1]);
         if (!(pmin >= -1e-8)) {
-            s = 0.0; mn = 0.0;
-            for (int q = tid; q < nsub; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
-            sum2 = block_sum(s, red);
-            min2 = block_min(mn, red);
+            for (int sl = s0; sl < s1; ++sl) {
+                const int lo = sl * chunk, hi = lo + chunk < nsub ? lo + chunk : nsub;
+                double s = 0.0, mn = 0.0;
+                for (int q = lo + tid; q < hi; q += T) { const double v = a[at(q)]; s += v; mn = fmin(mn, v); }
+                const double bs = block_sum(s, red), bm = block_min(mn, red);
+                if (tid == 0) { part[sl * 3 + 0] = bs; part[sl * 3 + 1] = bm; }
+            }
+            const int op[2] = {0, 1};
+            fin_combine(fc, part, 2, op, cmb);
+            sum2 = cmb[0];
+            min2 = cmb[1];
         }
         if (!(min2 >= -1e-8)) status |= PKB_ST_PMF_NEG2;
         if (!(sum2 + loss <= 1.00001)) status |= PKB_ST_TOT_GT1;
     }
     // r_small_vals(coo(pmf), prob_model=True) (:605, CalcSol.py:112-136)
-    double ks = 0.0, kc = 0.0, kr = 0.0;
-    for (int q = tid; q < nsub; q += T) {
-        const int i = at(q);
-        const double v = a[i];
-        if (v != 0.0 && !(v < negval)) {
-            ks += v; kc += 1.0;
-            int rr = i / W - racc, cc = i % W - racc;
-            if (rr < 0) rr = -rr;
-            if (cc < 0) cc = -cc;
-            kr = fmax(kr, (double)(rr > cc ? rr : cc));
+    for (int sl = s0; sl < s1; ++sl) {
+        const int lo = sl * chunk, hi = lo + chunk < nsub ? lo + chunk : nsub;
+        double ks = 0.0, kc = 0.0, kr = 0.0;
+        for (int q = lo + tid; q < hi; q += T) {
+            const int i = at(q);
+            const double v = a[i];
+            if (v != 0.0 && !(v < negval)) {
+                ks += v; kc += 1.0;
+                int rr = i / W - racc, cc = i % W - racc;
+                if (rr < 0) rr = -rr;
+                if (cc < 0) cc = -cc;
+                kr = fmax(kr, (double)(rr > cc ? rr : cc));
+            }
         }
+        const double b0 = block_sum(ks, red), b1 = block_sum(kc, red), b2 = block_max(kr, red);
+        if (tid == 0) { part[sl * 3 + 0] = b0; part[sl * 3 + 1] = b1; part[sl * 3 + 2] = b2; }
     }
-    const double ksum = block_sum(ks, red);
-    const double kcnt = block_sum(kc, red);
-    const double krad = block_max(kr, red);
+    { const int op[3] = {0, 0, 2}; fin_combine(fc, part, 3, op, cmb); }
+    const double ksum = cmb[0], kcnt = cmb[1], krad = cmb[2];
     const double add = (1.0 - ksum) / kcnt;
     if (pre) {      // parity export: the whole window, zeros outside the sub-window
-        for (int i = tid; i < nel; i += T) pre[(size_t)prob * nel + i] = 0.0;
+        for (int i = fc.crank * T + tid; i < nel; i += T * csize) pre[(size_t)prob * nel + i] = 0.0;
         __syncthreads();
-        for (int q = tid; q < nsub; q += T) { const int i = at(q); pre[(size_t)prob * nel + i] = a[i]; }
+        fc.sync();
+        for (int sl = s0; sl < s1; ++sl) {
+            const int lo = sl * chunk, hi = lo + chunk < nsub ? lo + chunk : nsub;
+            for (int q = lo + tid; q < hi; q += T) { const int i = at(q); pre[(size_t)prob * nel + i] = a[i]; }
+        }
     }
-    for (int q = tid; q < nsub; q += T) {
-        const int i = at(q);
-        const double v = a[i];
-        a[i] = (v != 0.0 && !(v < negval)) ? v + add : 0.0;
+    for (int sl = s0; sl < s1; ++sl) {
+        const int lo = sl * chunk, hi = lo + chunk < nsub ? lo + chunk : nsub;
+        for (int q = lo + tid; q < hi; q += T) {
+            const int i = at(q);
+            const double v = a[i];
+            a[i] = (v != 0.0 && !(v < negval)) ? v + add : 0.0;
+        }
     }
-    if (tid == 0) {
+    if (tid == 0 && fc.crank == 0) {
         DayMeta& m = meta[prob];
         m.loss = loss; m.pmfsum = pmfsum; m.total = total; m.kept_sum = ksum; m.add = add;
         m.rad = (int)krad; m.nnz = (int)kcnt;
     }
-    if (status && tid == 0) atomicOr(&meta[prob].status, status);
+    if (status && tid == 0 && fc.crank == 0) atomicOr(&meta[prob].status, status);
 }
 
 // ---------------------------------------------------------------------------

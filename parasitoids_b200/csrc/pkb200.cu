@@ -91,6 +91,7 @@ struct pkb_ctx {
     cudaEvent_t ev_cp2;
     std::vector<cudaEvent_t> day_events;
     std::vector<cudaEvent_t> emit_events;   // day d of the fused solve has been emitted (the COO worker thread waits for it)
+    int fin_clusters;       // k_day_finalize as clusters of 8 CTAs per problem when a launch has fewer problems than SMs (option "fin_clusters", default 1)
     int coo_thread;         // the per-day COO / CSR compaction + D2H of pkb_solve is driven by a helper host thread (option "coo_thread", default 1)
     std::vector<cudaEvent_t> win_events;
     cudaEvent_t ev_cp;
@@ -364,6 +365,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->batch_lanes = 4;
     ctx->batch_threads = 1;
     ctx->coo_thread = 1;
+    ctx->fin_clusters = 1;
     ctx->batch_chain = 1;
     ctx->batch_occ = PKB_BCH_B;
     ctx->batch_group = 32;
@@ -536,6 +538,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "batch_chain")) {
         ctx->batch_chain = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "fin_clusters")) {
+        ctx->fin_clusters = value != 0;
         return 0;
     }
     if (!strcmp(key, "coo_thread")) {
@@ -898,6 +904,41 @@ static int check_dparams(const double d[3], const char* which) {
     return 0;
 }
 
+// k_day_finalize: one CTA per problem when the launch has enough problems to fill the GPU, else one thread-block CLUSTER of
+// PKB_FIN_SLICES CTAs per problem (distributed shared memory carries the slice sums, phase1.cuh) -- same arithmetic either way.
+static int launch_day_finalize(pkb_ctx* ctx, int nprob, const DayParams* ddp, const BvnPar* bvn, int periods, double* acc, const double* acc_lo, int racc,
+                               const double* loss_t, DayMeta* dmeta, double negval, double* pre, const PeriodInfo* pinfo) {
+#if PKB_IS_EMUL
+    const int csize = 1;
+    LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ddp, bvn, periods, acc, acc_lo, racc, loss_t, dmeta, negval, pre, pinfo, csize);
+#else
+    // (measured: 18 / 30 problems with 5 MB windows 0.75 -> 0.25 ms; 60 problems with 1 MB windows gain nothing from 480 CTAs)
+    const int csize = (ctx->fin_clusters && nprob * PKB_FIN_SLICES <= 2 * ctx->sm_count) ? PKB_FIN_SLICES : 1;
+    if (csize == 1) {
+        LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ddp, bvn, periods, acc, acc_lo, racc, loss_t, dmeta, negval, pre, pinfo, csize);
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(nprob * csize);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (ctx->prof_on) prof_begin(ctx, "k_day_finalize", ctx->stream);
+    CU(cudaLaunchKernelEx(&cfg, k_day_finalize, ddp, bvn, periods, acc, acc_lo, racc, loss_t, dmeta, negval, pre, pinfo, csize));
+    if (ctx->prof_on) prof_end(ctx, ctx->stream);
+    ctx->launches++;
+#endif
+    return 0;
+}
+
 // wind_dev: device pointer [nd_wind][periods][3]
 static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, int periods, const pkb_day_args* args, int nprob,
                              int keep_pre, pkb_kset** out) {
@@ -1009,8 +1050,8 @@ static int kernels_build_dev(pkb_ctx* ctx, const double* wind_dev, int nd_wind, 
     const int period_threads = lattice_items <= 256 ? 64 : (lattice_items <= 1024 ? 128 : 256);
     LAUNCH(ctx, k_period, dim3(periods, nprob), period_threads, smem, ks->ddp.p, ks->bvn.p, ks->pinfo.p, ks->hprob.p, periods, nmax, tile_cap, ks->acc.p, ks->acc_lo.p,
            racc, ks->loss_t.p, ks->dmeta.p);
-    LAUNCH(ctx, k_day_finalize, nprob, 1024, 0, ks->ddp.p, ks->bvn.p, periods, ks->acc.p, (const double*)ks->acc_lo.p, racc, ks->loss_t.p, ks->dmeta.p, 1e-8,
-           keep_pre ? ks->pre.p : (double*)nullptr, (const PeriodInfo*)ks->pinfo.p);
+    TRY(launch_day_finalize(ctx, nprob, ks->ddp.p, ks->bvn.p, periods, ks->acc.p, ks->acc_lo.p, racc, ks->loss_t.p, ks->dmeta.p, 1e-8,
+                            keep_pre ? ks->pre.p : (double*)nullptr, ks->pinfo.p));
     CU(cudaMemcpyAsync(ks->hmeta.data(), ks->dmeta.p, sizeof(DayMeta) * nprob, cudaMemcpyDeviceToHost, ctx->stream));
     TRY(sync_check(ctx, "phase 1"));
     guard.k = nullptr;

@@ -140,6 +140,26 @@ def test_prob_mass_is_bit_reproducible(pkb, tmp_path):
         assert np.array_equal(a.toarray(), b.toarray())
 
 
+def test_day_finalize_clusters_equal_single_cta(pkb, tmp_path):
+    """k_day_finalize runs as one CTA per (proposal, day) problem when a launch carries hundreds of them and as a
+    thread-block cluster of eight CTAs per problem otherwise (option fin_clusters; slice sums through distributed shared
+    memory).  Sums are taken per slice and combined in slice order either way: same bits."""
+    z, wind, days, args = _small(pkb, tmp_path)
+    pm_args = [(d, wind) + args for d in days]
+    ctx = pkb._lib.ctx()
+    out = {}
+    try:
+        for on in (1, 0):
+            ctx.set_option('fin_clusters', on)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                out[on] = pkb.PM.prob_mass_batch(pm_args)
+    finally:
+        ctx.set_option('fin_clusters', 1)
+    for a, b in zip(out[1], out[0]):
+        assert a.shape == b.shape and np.array_equal(a.toarray(), b.toarray())
+
+
 def test_ring_decision_in_reference_order(pkb, tmp_path):
     """Option ring_tol: where the support-ring test 1 - sum < 0.001 (ParasitoidModel.py:345-348) lands within
     ring_tol of the threshold it is re-taken with the reference's own running sum (centre, corners, sides in call
