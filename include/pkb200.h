@@ -112,6 +112,8 @@ int pkb_sync(pkb_ctx* ctx);
  * "batch_occ" (resident CTAs per SM the batched chain kernels are launched for, default 4),
  * "fin_clusters" (0/1: k_day_finalize as a thread-block cluster of eight CTAs per (proposal, day) problem when a launch carries
  *                only a few dozen problems, default 1; same bits as one CTA per problem),
+ * "cohort_lanes" (0/1: population model with a release of several days -- the cohort back-solves and the emission of day n run
+ *                on child contexts next to the main chain's step n + 1, default 1),
  * "coo_thread" (0/1: the per-day COO / CSR compaction and D2H of pkb_solve are enqueued by a helper host thread instead of
  *              the thread that paces the chain, default 1).
  * All of them select between implementations of the same arithmetic; results agree to rounding. */

@@ -92,6 +92,8 @@ struct pkb_ctx {
     std::vector<cudaEvent_t> day_events;
     std::vector<cudaEvent_t> emit_events;   // day d of the fused solve has been emitted (the COO worker thread waits for it)
     int fin_clusters;       // k_day_finalize as clusters of 8 CTAs per problem when a launch has fewer problems than SMs (option "fin_clusters", default 1)
+    int cohort_lanes;       // population model with a release of several days: the cohort back-solves of day n run on a child context next to the
+                            // main chain's step n + 1 (option "cohort_lanes", default 1)
     int coo_thread;         // the per-day COO / CSR compaction + D2H of pkb_solve is driven by a helper host thread (option "coo_thread", default 1)
     std::vector<cudaEvent_t> win_events;
     cudaEvent_t ev_cp;
@@ -365,6 +367,7 @@ extern "C" int pkb_create(int device, pkb_ctx** out) {
     ctx->batch_lanes = 4;
     ctx->batch_threads = 1;
     ctx->coo_thread = 1;
+    ctx->cohort_lanes = 1;
     ctx->fin_clusters = 1;
     ctx->batch_chain = 1;
     ctx->batch_occ = PKB_BCH_B;
@@ -542,6 +545,10 @@ extern "C" int pkb_set_option(pkb_ctx* ctx, const char* key, double value) {
     }
     if (!strcmp(key, "fin_clusters")) {
         ctx->fin_clusters = value != 0;
+        return 0;
+    }
+    if (!strcmp(key, "cohort_lanes")) {
+        ctx->cohort_lanes = value != 0;
         return 0;
     }
     if (!strcmp(key, "coo_thread")) {
@@ -1613,13 +1620,15 @@ extern "C" int pkb_chain_get_cursol(pkb_chain* ch, double negval, int mode, int 
 
 // cohorts of earlier release days: cohort j = state (*) F[nf-1] (*) ... (*) F[j]
 // F[j]: device window (Wk[j], radius m[j]); krt[j]/ready[j]: optional cached spectra.
+// src0 / ctrl0 (optional): the state to start from and its control block, when it is not this chain's own current state
+// (cohort lanes of the fused solve: the scratch, cohort buffers and stream of `ch`, the state of the main chain)
 static int back_solve_dev(pkb_chain* ch, const double* const* F, const int* Wk, const int* m, int nf, cplx* const* krt, bool* ready,
-                          cplx* const* krt_t = nullptr, bool* ready_t = nullptr) {
+                          cplx* const* krt_t = nullptr, bool* ready_t = nullptr, const double* src0 = nullptr, const ChainCtrl* ctrl0 = nullptr) {
     if (nf > PKB_MAX_COHORTS) return fail(PKB_ELIMIT, "at most %d earlier release days are supported", PKB_MAX_COHORTS);
     pkb_ctx* ctx = ch->ctx;
     const ChainDims& d = ch->d;
-    const double* src = ch->S[ch->cur].p;
-    const ChainCtrl* src_ctrl = ch->ctrl.p;
+    const double* src = src0 ? src0 : ch->S[ch->cur].p;
+    const ChainCtrl* src_ctrl = src0 ? ctrl0 : ch->ctrl.p;
     for (int j = nf - 1; j >= 0; --j) {
         if (!ch->coh[j].p) TRY(ch->coh[j].alloc(ctx, (size_t)d.P * d.ldS));
         cplx* kr = krt ? krt[j] : ch->Krt.p;
@@ -2207,6 +2216,26 @@ static void solve_day_args(const pkb_solve_args* a, pkb_day_args* dargs) {
 // Likelihood batches read the model only at K sample cells: with a sink the emission kernels evaluate
 // just those cells into out[nd][K] (device), no dense day is materialised, no result object is returned
 // and the chain is left enqueued on ctx's streams (the caller synchronises once per group of proposals).
+// a child context works with its parent's options
+static void lane_inherit(const pkb_ctx* ctx, pkb_ctx* lane) {
+    lane->stencil_max_radius = ctx->stencil_max_radius;
+    lane->fft_threads = ctx->fft_threads;
+    lane->use_windows = ctx->use_windows;
+    lane->use_fusion = ctx->use_fusion;
+    lane->use_step_torus = ctx->use_step_torus;
+    lane->use_trunc_torus = ctx->use_trunc_torus;
+    lane->use_spectral = ctx->use_spectral;
+    lane->spec_min_reach = ctx->spec_min_reach;
+    lane->use_rowwin = ctx->use_rowwin;
+    lane->use_tau_windows = ctx->use_tau_windows;
+    lane->tau_lag = ctx->tau_lag;
+    lane->ring_tol = ctx->ring_tol;
+    lane->rows_desc = ctx->rows_desc;
+    lane->prof_on = ctx->prof_on;
+    lane->batch_chain = ctx->batch_chain;
+    lane->batch_occ = ctx->batch_occ;
+}
+
 struct SampleSink {
     const int* cells;       // device [K][2]
     int K;
@@ -2764,8 +2793,58 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(emit_pop(day, (1 - wsum) * rn, 1, 0));
             TRY(emitted(day, ctx->stream));
         }
+        // Cohort lanes.  After the release the main chain's step n + 1 does not depend on the cohort back-solves of day n (they
+        // start from S_n and end in that day's output), and every convolution of an 801^2-sized domain is a one-wave kernel
+        // set that leaves SMs idle: the back-solves and the emission of day n run on one of two child contexts (own stream,
+        // scratch, cohort buffers and cached filter spectra) while the main chain goes on.  S_n is read by its lane until the
+        // lane's event; the main chain waits for it before the step that overwrites that buffer (two days later, same lane).
+        struct CohLane {
+            pkb_ctx* lc = nullptr;
+            pkb_chain* ch = nullptr;
+            cplx* krt[PKB_MAX_COHORTS];
+            cplx* krt_t[PKB_MAX_COHORTS];
+            bool ready[PKB_MAX_COHORTS], ready_t[PKB_MAX_COHORTS];
+            bool busy = false;
+        } lane[2];
+        struct LaneGuard {
+            CohLane* l;
+            ~LaneGuard() {
+                for (int i = 0; i < 2; ++i)
+                    if (l[i].ch) {
+                        cudaStreamSynchronize(l[i].lc->stream);
+                        delete l[i].ch;
+                    }
+            }
+        } lane_guard{lane};
+        int nlane = 0;
+#ifndef PKB_EMUL
+        if (rd > 1 && nd > rd + 1 && ctx->cohort_lanes && !ctx->prof_on && !sink) nlane = 2;
+#endif
+        for (int i = 0; i < nlane; ++i) {
+            while ((int)ctx->lanes.size() <= i) {
+                pkb_ctx* lc = nullptr;
+                TRY(pkb_create(ctx->device, &lc));
+                ctx->lanes.push_back(lc);
+            }
+            CohLane& ln = lane[i];
+            ln.lc = ctx->lanes[i];
+            lane_inherit(ctx, ln.lc);
+            TRY(chain_create(ln.lc, D, mmax, &ln.ch));
+            ln.ch->negval = negval;
+            for (int j = 0; j < PKB_MAX_COHORTS; ++j) { ln.krt[j] = nullptr; ln.krt_t[j] = nullptr; ln.ready[j] = false; ln.ready_t[j] = false; }
+            for (int j = 0; j + 1 < rd; ++j) {
+                TRY(ln.ch->kcache[j].alloc(ln.lc, spec_size(d.Nc + 1, d.ldK)));
+                ln.krt[j] = ln.ch->kcache[j].p;
+                if (ctx->use_trunc_torus) {
+                    TRY(ln.ch->kcache_t[j].alloc(ln.lc, spec_size(d.Nc + 1, d.ldK)));
+                    ln.krt_t[j] = ln.ch->kcache_t[j].p;
+                }
+            }
+        }
         // post-release days (CalcSol.py:308-323)
         for (int n = rd; n < nd; ++n) {
+            CohLane* ln = nlane ? &lane[n & 1] : nullptr;
+            if (ln && ln->busy) CU(cudaStreamWaitEvent(ctx->stream, ln->lc->ev_kr[0], 0));      // day n - 2 is done with the buffer this step writes
             const int* wp = rd == 1 ? step_window(n) : nullptr;
             cplx* kday = nullptr;
             cplx* kday_t = nullptr;
@@ -2775,6 +2854,31 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             ch->meta_main = dsm.p + n;
             TRY(chain_conv_main(ch, kern(n), ks->W, krad(n), 1, kday, wp, fuse, fused_m, kday_t, spec_try));
             fused_m = fuse ? krad(n) : -1;
+            if (ln) {
+                pkb_ctx* lc = ln->lc;
+                // (the next main step rewrites ch->ctrl[0] while this day's first back-solve step may still be queued: the lane
+                // reads a snapshot)
+                CU(cudaMemcpyAsync(ln->ch->ctrl.p, ch->ctrl.p, sizeof(ChainCtrl), cudaMemcpyDeviceToDevice, ctx->stream));
+                CU(cudaEventRecord(lc->ev_lane, ctx->stream));
+                CU(cudaStreamWaitEvent(lc->stream, lc->ev_lane, 0));
+                TRY(back_solve_dev(ln->ch, F, Wk, mm, rd - 1, ln->krt, ln->ready, ln->krt_t, ln->ready_t, ch->S[ch->cur].p, ln->ch->ctrl.p));
+                if (want_cmeta)
+                    CU(cudaMemcpyAsync(dcm.p + (size_t)n * PKB_MAX_COHORTS, ln->ch->meta.p + 1, sizeof(StepMeta) * (rd - 1), cudaMemcpyDeviceToDevice,
+                                       lc->stream));
+                for (int c = 0; c < rd; ++c) {
+                    ca.S[c] = c < rd - 1 ? ln->ch->coh[c].p : ch->S[ch->cur].p;
+                    ca.w[c] = a->r_dist[c];
+                }
+                ca.n = rd;
+                const int day = n - lead;
+                if (day >= 0)
+                    LAUNCH(lc, k_emit_population, D, 256, 0, ca, d, rn, 0.0, 0, negval, 0, res->dense.p + nD * day,
+                           res->pre.p ? res->pre.p + nD * day : (double*)nullptr);
+                TRY(emitted(n, lc->stream));
+                CU(cudaEventRecord(lc->ev_kr[0], lc->stream));
+                ln->busy = true;
+                continue;
+            }
             TRY(back_solve_dev(ch, F, Wk, mm, rd - 1, krt, ready, krt_t, ready_t));
             TRY(keep_cmeta(n, rd - 1));
             for (int c = 0; c < rd; ++c) {
@@ -2785,6 +2889,12 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             TRY(emit_pop(n, 0.0, 0, 0));
             TRY(emitted(n, ctx->stream));
         }
+        for (int i = 0; i < nlane; ++i)
+            if (lane[i].busy) {
+                CU(cudaStreamWaitEvent(ctx->stream, lane[i].lc->ev_kr[0], 0));
+                ctx->launches += lane[i].lc->launches;
+                lane[i].lc->launches = 0;
+            }
     }
     if (kr_wait) {      // spectra launched on the side stream and never used: still join before their buffers are released
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_kr[1], 0));
@@ -3222,23 +3332,7 @@ static int solve_batch_impl(pkb_ctx* ctx, const pkb_solve_args* base, const doub
         ctx->lanes.push_back(lane);
     }
     for (int l = 0; l < nlanes; ++l) {
-        pkb_ctx* lane = ctx->lanes[l];
-        lane->stencil_max_radius = ctx->stencil_max_radius;
-        lane->fft_threads = ctx->fft_threads;
-        lane->use_windows = ctx->use_windows;
-        lane->use_fusion = ctx->use_fusion;
-        lane->use_step_torus = ctx->use_step_torus;
-        lane->use_trunc_torus = ctx->use_trunc_torus;
-        lane->use_spectral = ctx->use_spectral;
-        lane->spec_min_reach = ctx->spec_min_reach;
-        lane->use_rowwin = ctx->use_rowwin;
-        lane->use_tau_windows = ctx->use_tau_windows;
-        lane->tau_lag = ctx->tau_lag;
-        lane->ring_tol = ctx->ring_tol;
-        lane->rows_desc = ctx->rows_desc;
-        lane->prof_on = ctx->prof_on;
-        lane->batch_chain = ctx->batch_chain;
-        lane->batch_occ = ctx->batch_occ;
+        lane_inherit(ctx, ctx->lanes[l]);
     }
     // after an error or at the end of a group: drain the lanes, fold their launch counts and per-kernel
     // profile into the parent (what pkb_launch_count / pkb_profile_get report)

@@ -547,6 +547,37 @@ def test_sparse_outputs_equal_dense_output(pkb):
         ctx.set_option('coo_thread', 1)
 
 
+def test_cohort_lanes_equal_sequential_back_solves(pkb):
+    """Population model with a release of several days: after the release the cohort back-solves and the emission of day n
+    run on child contexts beside the main chain's step n + 1 (option cohort_lanes; on the GPU).  Same kernels on the same
+    inputs in another order of launches: identical days and cohort flags."""
+    rng = np.random.default_rng(9)
+    nd, periods, rad_res, rad_dist = 8, 48, 40, 2000.0
+    w = np.zeros((nd, periods, 3))
+    for c in range(2):
+        w[:, :, c] = 0.3 * np.sin(np.linspace(0, 6 + c, nd * periods)).reshape(nd, periods) + rng.normal(0, 0.05, (nd, periods))
+    w[:, :, 2] = np.hypot(w[:, :, 0], w[:, :, 1])
+    args = (H.HPARAMS, H.DPARAMS, H.DLPARAMS, H.MU_R, 2, rad_dist, rad_res)
+    kw = dict(prob_model=False, r_dur=3, r_number=5000.0, r_start=0.3)
+    ctx = pkb._lib.ctx()
+    out = {}
+    try:
+        for on in (1, 0):
+            ctx.set_option('cohort_lanes', on)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                res = pkb.Run.solve(w, nd, *args, want_coo='csr', want_dense=True, **kw)
+            out[on] = ([res.dense(d).copy() for d in range(nd)], [m.toarray() for m in res.csr_list()], list(res.flags()),
+                       [list(res.cohort_flags(d, 2)) for d in range(3, nd)])
+            res.close()
+    finally:
+        ctx.set_option('cohort_lanes', 1)
+    for d in range(nd):
+        assert np.array_equal(out[1][0][d], out[0][0][d]), d
+        assert np.array_equal(out[1][1][d], out[1][0][d]), d          # the CSR output is the dense day
+    assert out[1][2] == out[0][2] and out[1][3] == out[0][3]
+
+
 def test_spectral_steps_match_exact_steps(pkb):
     """Option spectral: while the content outside the domain is below 1e-13 the chain keeps the product spectrum
     k_cols forms anyway and starts the next step from it (the reference's own chain state is spectral,
