@@ -2144,21 +2144,34 @@ struct CooWorker {
     }
     void run() {
         cudaSetDevice(ctx->device);
+        std::vector<int> days;
         for (;;) {
-            int day;
+            days.clear();
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [this]() { return done || !q.empty(); });
                 if (q.empty()) return;
-                day = q.front();
-                q.pop_front();
+                days.assign(q.begin(), q.end());      // everything handed over so far
+                q.clear();
             }
             if (rc) continue;                   // (drain the queue after an error)
-            cudaStream_t cs = (day & 1) ? ctx->cp2 : ctx->cp;
+            // Day by day: the wait for the day's size, its compaction and copies.  The counting / scan / size copy of the NEXT day
+            // (the other copy stream) is enqueued first, so that it runs under that wait -- but not further ahead: a later day of the
+            // same stream would queue its wait for a far emission in front of this day's compaction.
             int e = 0;
-            if (cudaStreamWaitEvent(cs, ctx->emit_events[day], 0) != cudaSuccess) e = fail(PKB_ECUDA, "COO worker: waiting for day %d failed", day);
-            if (!e) e = coo_day_ready(ctx, r, day, cs, &launches);
-            if (!e) e = coo_pump(ctx, r, st, true, day + 1, false, &launches);
+            size_t readied = 0;
+            auto ready_to = [&](size_t upto) {
+                for (; readied < upto && readied < days.size() && !e; ++readied) {
+                    const int day = days[readied];
+                    cudaStream_t cs = (day & 1) ? ctx->cp2 : ctx->cp;
+                    if (cudaStreamWaitEvent(cs, ctx->emit_events[day], 0) != cudaSuccess) e = fail(PKB_ECUDA, "COO worker: waiting for day %d failed", day);
+                    if (!e) e = coo_day_ready(ctx, r, day, cs, &launches);
+                }
+            };
+            for (size_t i = 0; i < days.size() && !e; ++i) {
+                ready_to(i + 2);
+                if (!e) e = coo_pump(ctx, r, st, true, days[i] + 1, false, &launches);
+            }
             if (e) { rc = e; msg = g_err; }
         }
     }
