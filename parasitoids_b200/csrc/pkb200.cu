@@ -22,6 +22,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -2333,9 +2334,9 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
     }
     // (day: chain day; nothing is emitted for the dropped leading day)
 #ifdef PKB_EMUL
-    const bool coo_threaded = false;                    // (the CPU emulation of CUDA blocks is not re-entrant)
+    bool coo_threaded = false;                          // (the CPU emulation of CUDA blocks is not re-entrant)
 #else
-    const bool coo_threaded = a->want_coo && ctx->coo_thread && !ctx->prof_on;      // (the per-kernel profile belongs to this thread)
+    bool coo_threaded = a->want_coo && ctx->coo_thread && !ctx->prof_on;      // (the per-kernel profile belongs to this thread)
 #endif
     CooWorker worker;
     if (coo_threaded) {
@@ -2344,7 +2345,12 @@ static int solve_chain(pkb_ctx* ctx, const pkb_solve_args* a, pkb_kset* ks, int 
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->emit_events.push_back(e);
         }
-        worker.start(ctx, res, &coo);
+        try {
+            worker.start(ctx, res, &coo);
+        } catch (const std::exception&) {               // no thread to be had: the chain's own thread does the output work
+            worker.running = false;
+            coo_threaded = false;
+        }
     }
     auto emitted = [&](int day, cudaStream_t strm) -> int {
         if (!a->want_coo || day < lead) return 0;
