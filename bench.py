@@ -789,6 +789,12 @@ def main():
                     'note': 'algorithmic bytes are SURVEY.md 8d\'s share of B_day(P) for one simulated day; launches on a support window move '
                             'fewer bytes than that (cells below 1e-15 are neither transformed nor stored), which is how frac can exceed 1',
                     'family_ms_per_solve': {k: round(fam[k][1] / args.steps, 4) for k in fam}}
+        if prof[dom][0]:
+            # the same kernel on its whole-torus launches only (the geometry the algorithmic bytes describe; in the fused C4 solve
+            # those are the spectral-resident steps of the last days, whose k_cols starts from the stored spectrum)
+            wms = prof[dom][1] / prof[dom][0]
+            roofline['whole_torus_launches'] = {'launches': prof[dom][0], 'avg_launch_ms': wms, 'achieved': share[dom] / (wms / 1000.0) / 1e9,
+                                                'frac': share[dom] / (wms / 1000.0) / 1e9 / peak}
     roofline_chain = None
     if nsteps_chain and not batch_mode and chain_total_ms > 0:      # batch mode: proposals differ in torus size; the per-kernel roofline above still applies
         nflag = sum(1 for f in flags if f)
