@@ -14,7 +14,7 @@ plus the 59-step convolution chain.
             daily solutions left on the device (device-side work only).
 `e2e`       the same solve through the public API (parasitoids_b200.Run.solve)
             with HOST buffers: wind uploaded from host memory and the
-            thresholded COO triplets of every day copied back inside the timed
+            thresholded CSR arrays of every day copied back inside the timed
             region -- what a caller of Run.main sees.
 `roofline`  the dominant chain kernel against the measured HBM copy bandwidth;
 `roofline_chain` all chain kernels of one simulated day against B_day(P, D).
@@ -33,9 +33,14 @@ plus the 59-step convolution chain.
             same solve_batch path, weak scaling); at N = 1 also c1/c2/c3
             (Kalbar / Carnarvon at 801^2) with the CPU port beside them.
 
-N > 1: independent parameter proposals of the same solve, one per rank (the
-batched-likelihood partitioning of SURVEY.md section 8e); the only collective
-is one NCCL all_gather of the sampled-cell outputs per step.
+N > 1: the SAME step on every rank -- one independent solve per GPU through
+Run.solve, exactly the N = 1 code path (replicas: one solve does not shard
+efficiently over GPUs; `--single-solve` measures that).
+The time is the maximum over the ranks between two barriers; no data-path
+collective.  The batched-likelihood partitioning of SURVEY.md section 8e, with
+its NCCL all_gather, is measured over the same ranks under `extra`
+(weak_batch, c5).  `--workload kalbar_batch512` makes the likelihood batch the
+step itself.
 """
 import argparse
 import json
@@ -678,7 +683,7 @@ def main():
         pass
 
     def step_device():
-        if world > 1 or batch_mode:
+        if batch_mode:
             with warnings.catch_warnings():
                 warnings.simplefilter('ignore')      # proposals with strong drift warn about wasps leaving the domain
                 batch.solve_batch(None, proposals, cells, ndays, rad_dist, rad_res, device=local,
@@ -688,7 +693,7 @@ def main():
                          wind_shape=wind.shape, device=local)
 
     def step_e2e():
-        if world > 1 or batch_mode:
+        if batch_mode:
             # host wind in, sampled cells of every proposal out (what the likelihood consumes)
             with warnings.catch_warnings():
                 warnings.simplefilter('ignore')
@@ -829,12 +834,13 @@ def main():
     e_ms = float(te[0])
     e2e = {'value': units * args.steps / (e_ms / 1000.0), 'unit': 'days/s',
            # batch modes: every rank uploads the wind once per call plus its share of the proposals and the cells
-           'h2d_bytes_per_step': int(wind.nbytes + (proposals[:-(-len(proposals) // world)].nbytes + cells.nbytes if (world > 1 or batch_mode) else 0)),
-           'd2h_bytes_per_step': (int(nnz_tot / args.steps * 16 + (ndays + 1) * 8) if (world > 1 or batch_mode) else
-                                  int(nnz_tot / args.steps * 12 + ndays * D * 8 + (ndays + 1) * 8)),
+           # (batch mode: every rank uploads the wind once per call plus its share of the proposals and the cells; otherwise one solve per rank)
+           'h2d_bytes_per_step': int(wind.nbytes + proposals[:-(-len(proposals) // world)].nbytes + cells.nbytes) if batch_mode else int(world * wind.nbytes),
+           'd2h_bytes_per_step': (int(nnz_tot / args.steps * 16 + (ndays + 1) * 8) if batch_mode else
+                                  int(world * (nnz_tot / args.steps * 12 + ndays * D * 8 + (ndays + 1) * 8))),
            'ms_per_step': e_ms / args.steps, 'timer': 'host wall clock between device synchronisations',
            'api': ('parasitoids_b200.batch.solve_batch: wind from pinned host memory on every rank, sampled cells of all proposals '
-                   'all-gathered and copied to host') if (world > 1 or batch_mode) else
+                   'all-gathered and copied to host') if batch_mode else
                   "parasitoids_b200.Run.solve(want_coo='csr'): wind from pinned host memory; the thresholded, renormalised solution of every day to "
                   'host as CSR arrays (row offsets, int32 column, fp64 value: what Run.main saves, Run.py:490-510)'}
 
@@ -848,7 +854,8 @@ def main():
                 'config': {'workload': args.workload, 'days': ndays, 'dom_len': D, 'torus_P': P, 'fft_len': N,
                            'periods_per_day': int(wind.shape[1]), 'kernel_radius_min_max': [int(min(radii)), int(max(radii))],
                            'support_window_steps': window_steps, 'spectral_resident_steps': spectral_steps,
-                           'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if (world > 1 or batch_mode) else 'single solve',
+                           'parallelism': ('likelihood batch of %d proposals sharded over %d GPU(s) (batch.solve_batch), one all_gather of 1024 sampled cells x days per step' % (len(proposals), world)) if batch_mode
+                                          else ('single solve' if world == 1 else 'one independent solve per GPU (%d replicas of the N = 1 step, max over ranks, no collective)' % world),
                            'l2': 'every solve writes %.1f GB of dense daily solutions (> 126 MB L2) between two timed solves; whole-torus chain '
                                  'steps work on %.0f MB; no explicit flush' % (ndays * 8.0 * D * D / 1e9, 3 * 8.0 * P * P / 1e6)},
                 'wall_ms_per_step': wall_ms / args.steps, 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
